@@ -1,0 +1,386 @@
+"""Python mirror of the reference's public API over the C ABI (include/lpb200.h).
+
+Names, argument meaning and error behaviour follow /root/reference/src:
+  Problem / ProblemBuilder      linear_program.rs:24-169
+  InteriorPoint(+Builder)       solvers/interior_point/mod.rs:41-197
+  EquationSolverType            solvers/interior_point/newton_equations.rs:36-46
+  Solver / OptimizeResult       solvers/mod.rs:12-49
+  LinearProgramError variants   error.rs:7-29
+Rust `Result<T, LinearProgramError>` becomes "return T or raise the variant's exception".
+All numerical work happens inside liblpb200.so on the GPU; this file only marshals arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from typing import Optional
+
+import numpy as np
+
+from . import _ffi
+
+
+# --------------------------------------------------------------------------- errors (error.rs:7-29)
+class LinearProgramError(Exception):
+    code = None
+
+    def __init__(self, msg: Optional[str] = None):
+        super().__init__(msg if msg is not None else (_MESSAGES.get(self.code, "")))
+
+
+class Unconstrained(LinearProgramError):
+    code = _ffi.LPB_ERR_UNCONSTRAINED
+
+
+class NumericalProblem(LinearProgramError):
+    code = _ffi.LPB_ERR_NUMERICAL_PROBLEM
+
+
+class InvalidParameter(LinearProgramError):
+    code = _ffi.LPB_ERR_INVALID_PARAMETER
+
+
+class IncompatibleInputDimensions(LinearProgramError):
+    code = _ffi.LPB_ERR_INCOMPATIBLE_INPUT_DIMENSIONS
+
+
+class Infeasible(LinearProgramError):
+    code = _ffi.LPB_ERR_INFEASIBLE
+
+
+class Unbounded(LinearProgramError):
+    code = _ffi.LPB_ERR_UNBOUNDED
+
+
+class IterationLimitExceeded(LinearProgramError):
+    """Carries the best x / tau in SLACK form, like the reference (interior_point/mod.rs:237-239)."""
+    code = _ffi.LPB_ERR_ITERATION_LIMIT_EXCEEDED
+
+    def __init__(self, x):
+        super().__init__()
+        self.x = x
+
+
+class DeviceError(RuntimeError):
+    """CUDA / NCCL / argument failures (negative lpb codes): no reference counterpart."""
+
+    def __init__(self, code, detail=""):
+        super().__init__("lpb error %d: %s" % (code, detail))
+        self.code = code
+
+
+_MESSAGES = {
+    _ffi.LPB_ERR_UNCONSTRAINED: "The problem is unconstrained, meaning the solution is the all-zeros vector if `c` "
+                                "is nonnegative, or unbounded otherwise.",
+    _ffi.LPB_ERR_NUMERICAL_PROBLEM: "The solver encountered numerical problems it could not recover from. Likely "
+                                    "causes are linearly dependent constraints or variables whose scale differs by "
+                                    "multiple orders of magnitude.",
+    _ffi.LPB_ERR_INVALID_PARAMETER: "A parameter was set to an invalid value",
+    _ffi.LPB_ERR_INCOMPATIBLE_INPUT_DIMENSIONS: "The dimensions of your cost- and constraint arrays do not align.",
+    _ffi.LPB_ERR_INFEASIBLE: "The solver finished successfully, it appears that the problem is infeasible.",
+    _ffi.LPB_ERR_UNBOUNDED: "The solver finished successfully, it appears that your problem is unbounded.",
+    _ffi.LPB_ERR_ITERATION_LIMIT_EXCEEDED: "The solver failed to converge within the maximum number of iterations.",
+}
+
+_BY_CODE = {cls.code: cls for cls in (Unconstrained, NumericalProblem, InvalidParameter,
+                                      IncompatibleInputDimensions, Infeasible, Unbounded)}
+
+
+def _raise_for(code: int, x=None):
+    if code == _ffi.LPB_OK:
+        return
+    if code == _ffi.LPB_ERR_ITERATION_LIMIT_EXCEEDED:
+        raise IterationLimitExceeded(x)
+    if code in _BY_CODE:
+        raise _BY_CODE[code]()
+    if code == _ffi.LPB_ERR_UNSUPPORTED:
+        raise InvalidParameter("unsupported on the B200 path: " + _ffi.last_error())
+    raise DeviceError(code, _ffi.last_error())
+
+
+# --------------------------------------------------------------------------- host buffers
+class _HostBuffer:
+    """A float64 array in pinned host memory when a CUDA device is visible (uploads at PCIe rate),
+    else ordinary NumPy memory (building a Problem needs no GPU, exactly like the reference)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(s) for s in shape)
+        nbytes = int(np.prod(self.shape)) * 8
+        self._ptr = None
+        lib = _ffi.load()
+        p = C.c_void_p()
+        if nbytes > 0 and lib.lpb_device_count() > 0 and lib.lpb_host_alloc(C.byref(p), nbytes) == _ffi.LPB_OK:
+            self._ptr = p
+            buf = (C.c_double * (nbytes // 8)).from_address(p.value)
+            self.array = np.frombuffer(buf, dtype=np.float64).reshape(self.shape)
+        else:
+            self.array = np.zeros(self.shape, dtype=np.float64)
+
+    def __del__(self):
+        if getattr(self, "_ptr", None) is not None:
+            try:
+                _ffi.load().lpb_host_free(self._ptr)
+            except Exception:
+                pass
+            self._ptr = None
+
+
+def _as_f64(a, ndim):
+    arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if arr.ndim != ndim:
+        raise IncompatibleInputDimensions()
+    return arr
+
+
+# --------------------------------------------------------------------------- Problem (linear_program.rs)
+class Problem:
+    """A linear program in slack form: min c'x st A x == b, x >= 0 (linear_program.rs:24-30)."""
+
+    def __init__(self, A_buf, b_buf, c_buf, c0: float, n_slack: int):
+        self._A, self._b, self._c = A_buf, b_buf, c_buf
+        self._c0 = float(c0)
+        self._n_slack = int(n_slack)
+
+    @staticmethod
+    def target(c) -> "ProblemBuilder":
+        """Problem::target (linear_program.rs:37-39)."""
+        return ProblemBuilder(c)
+
+    def A(self) -> np.ndarray:
+        return self._A.array
+
+    def b(self) -> np.ndarray:
+        return self._b.array
+
+    def c(self) -> np.ndarray:
+        return self._c.array
+
+    def c0(self) -> float:
+        return self._c0
+
+    def n_slack(self) -> int:
+        return self._n_slack
+
+    def denormalize_target(self, x_slack) -> float:
+        return float(self.c().dot(x_slack) + self._c0)  # linear_program.rs:61-63
+
+    def denormalize_x(self, x_slack) -> np.ndarray:
+        return np.array(x_slack[: len(x_slack) - self._n_slack])  # linear_program.rs:65-69
+
+
+class ProblemBuilder:
+    """ProblemBuilder (linear_program.rs:73-169)."""
+
+    def __init__(self, c):
+        self._c = c
+        self._ub = None
+        self._eq = None
+
+    def ub(self, A, b) -> "ProblemBuilder":
+        self._ub = (A, b)
+        return self
+
+    def eq(self, A, b) -> "ProblemBuilder":
+        self._eq = (A, b)
+        return self
+
+    def build(self) -> Problem:
+        """Validate + convert to slack form [[A_ub, I], [A_eq, 0]] (linear_program.rs:125-169)."""
+        lib = _ffi.load()
+        c = _as_f64(self._c, 1)
+        n_c = c.shape[0]
+
+        def unpack(pair):
+            if pair is None:  # (0, n) placeholders, linear_program.rs:127-130
+                return np.zeros((0, n_c)), np.zeros(0)
+            return _as_f64(pair[0], 2), _as_f64(pair[1], 1)
+
+        A_ub, b_ub = unpack(self._ub)
+        A_eq, b_eq = unpack(self._eq)
+        m = C.c_int64()
+        n = C.c_int64()
+        ns = C.c_int64()
+        rc = lib.lpb_slack_dims(n_c, A_ub.shape[0], A_ub.shape[1], b_ub.shape[0], A_eq.shape[0], A_eq.shape[1],
+                                b_eq.shape[0], C.byref(m), C.byref(n), C.byref(ns))
+        _raise_for(rc)
+        A_buf = _HostBuffer((m.value, n.value))
+        b_buf = _HostBuffer((m.value,))
+        c_buf = _HostBuffer((n.value,))
+        rc = lib.lpb_build_slack_form(
+            c.ctypes.data, n_c,
+            A_ub.ctypes.data if A_ub.size else None, A_ub.shape[0], A_ub.shape[1], A_ub.shape[1],
+            b_ub.ctypes.data if b_ub.size else None, b_ub.shape[0],
+            A_eq.ctypes.data if A_eq.size else None, A_eq.shape[0], A_eq.shape[1], A_eq.shape[1],
+            b_eq.ctypes.data if b_eq.size else None, b_eq.shape[0],
+            A_buf.array.ctypes.data, n.value, b_buf.array.ctypes.data, c_buf.array.ctypes.data)
+        _raise_for(rc)
+        return Problem(A_buf, b_buf, c_buf, 0.0, ns.value)
+
+
+# --------------------------------------------------------------------------- solver config
+class EquationSolverType(enum.IntEnum):
+    """newton_equations.rs:36-46.  Only Cholesky runs on the B200 path."""
+    Cholesky = _ffi.LPB_SOLVER_CHOLESKY
+    Inverse = _ffi.LPB_SOLVER_INVERSE
+    LeastSquares = _ffi.LPB_SOLVER_LEAST_SQUARES
+
+
+class OptimizeResult:
+    """solvers/mod.rs:19-49."""
+
+    def __init__(self, x, fun, iteration):
+        self._x, self._fun, self._iteration = x, float(fun), int(iteration)
+
+    def x(self) -> np.ndarray:
+        return self._x
+
+    def fun(self) -> float:
+        return self._fun
+
+    def iteration(self) -> int:
+        return self._iteration
+
+
+class Solver:
+    """solvers/mod.rs:12-16."""
+
+    def solve(self, problem: Problem) -> OptimizeResult:  # pragma: no cover - interface
+        raise NotImplementedError
+
+
+class InteriorPointBuilder:
+    """interior_point/mod.rs:41-138."""
+
+    def __init__(self):
+        o = _ffi.lpb_options()
+        _ffi.load().lpb_options_default(C.byref(o))  # mod.rs:51-60
+        self._o = o
+
+    def tol(self, tol: float) -> "InteriorPointBuilder":
+        self._o.tol = float(tol)
+        return self
+
+    def disp(self, disp: bool) -> "InteriorPointBuilder":
+        self._o.disp = 1 if disp else 0
+        return self
+
+    def ip(self, ip: bool) -> "InteriorPointBuilder":
+        self._o.ip = 1 if ip else 0
+        return self
+
+    def solver_type(self, solver_type: EquationSolverType) -> "InteriorPointBuilder":
+        self._o.solver_type = int(solver_type)
+        return self
+
+    def alpha0(self, alpha0: float) -> "InteriorPointBuilder":
+        self._o.alpha0 = float(alpha0)
+        return self
+
+    def max_iter(self, max_iter: int) -> "InteriorPointBuilder":
+        self._o.max_iter = int(max_iter)
+        return self
+
+    def build(self) -> "InteriorPoint":
+        """mod.rs:118-137: InvalidParameter unless 0 < alpha0 < 1 and tol > 0."""
+        o = self._o
+        if o.alpha0 <= 0.0 or o.alpha0 >= 1.0:
+            raise InvalidParameter("A parameter was set to an invalid value: Alpha0 must be between 0 and 1 (exclusive)")
+        if o.tol <= 0.0:
+            raise InvalidParameter("A parameter was set to an invalid value: The tolerance must be nonnegative.")
+        return InteriorPoint(o)
+
+
+class InteriorPoint(Solver):
+    """interior_point/mod.rs:145-197."""
+
+    def __init__(self, opts: _ffi.lpb_options):
+        self._o = _ffi.lpb_options()
+        C.memmove(C.byref(self._o), C.byref(opts), C.sizeof(_ffi.lpb_options))
+
+    @staticmethod
+    def default() -> "InteriorPoint":
+        return InteriorPointBuilder().build()  # mod.rs:154-159
+
+    @staticmethod
+    def custom() -> InteriorPointBuilder:
+        return InteriorPointBuilder()  # mod.rs:195-197
+
+    def _key(self):
+        o = self._o
+        return (o.tol, o.disp, o.ip, o.solver_type, o.alpha0, o.max_iter)
+
+    def __eq__(self, other):  # #[derive(PartialEq)] mod.rs:140
+        return isinstance(other, InteriorPoint) and self._key() == other._key()
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def solve(self, problem: Problem) -> OptimizeResult:
+        """Solver::solve (mod.rs:161-169): upload, run the loop on the GPU, de-normalise."""
+        with ResidentProblem(problem) as rp:
+            return self.solve_resident(rp)
+
+    def solve_resident(self, rp: "ResidentProblem") -> OptimizeResult:
+        lib = _ffi.load()
+        n = rp.n
+        x_slack = np.empty(n, dtype=np.float64)
+        fun = C.c_double()
+        it = C.c_int64()
+        rc = lib.lpb_solve(rp.handle, C.byref(self._o), x_slack.ctypes.data, C.byref(fun), C.byref(it))
+        rp.last_iterations = it.value
+        _raise_for(rc, x_slack)
+        x = np.array(x_slack[: n - rp.n_slack])  # denormalize_x_into, linear_program.rs:65-69
+        return OptimizeResult(x, fun.value, it.value)
+
+
+class ResidentProblem:
+    """A Problem uploaded to HBM once (an `lpb_ctx`), reusable across solves."""
+
+    def __init__(self, problem: Problem, stream: int = 0):
+        lib = _ffi.load()
+        A = problem.A()
+        self.m, self.n = A.shape
+        self.n_slack = problem.n_slack()
+        self.last_iterations = 0
+        h = C.c_void_p()
+        rc = lib.lpb_create(C.byref(h), self.m, self.n, A.ctypes.data, self.n, problem.b().ctypes.data,
+                            problem.c().ctypes.data, problem.c0(), _ffi.LPB_MEM_HOST, C.c_void_p(stream))
+        _raise_for(rc)
+        self.handle = h
+        self._problem = problem
+
+    def reupload(self, problem: Problem):
+        A = problem.A()
+        rc = _ffi.load().lpb_set_problem(self.handle, A.ctypes.data, self.n, problem.b().ctypes.data,
+                                         problem.c().ctypes.data, problem.c0(), _ffi.LPB_MEM_HOST)
+        _raise_for(rc)
+
+    def profile(self) -> dict:
+        p = _ffi.lpb_profile()
+        _raise_for(_ffi.load().lpb_get_profile(self.handle, C.byref(p)))
+        return {k: getattr(p, k) for k, _ in p._fields_}
+
+    def trace(self) -> np.ndarray:
+        rows = np.zeros((max(1, self.last_iterations), _ffi.LPB_TRACE_COLS))
+        k = _ffi.load().lpb_trace(self.handle, rows.ctypes.data, rows.shape[0])
+        return rows[:k]
+
+    def set_option(self, key: str, value: int):
+        _raise_for(_ffi.load().lpb_set_option(self.handle, key.encode(), int(value)))
+
+    def close(self):
+        if self.handle is not None:
+            _ffi.load().lpb_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

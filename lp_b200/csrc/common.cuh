@@ -1,0 +1,55 @@
+// common.cuh -- shared definitions for liblpb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/lpb200.h"
+
+namespace lpb {
+
+void set_last_error(const char* fmt, ...);
+const char* get_last_error();
+
+#define LPB_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      ::lpb::set_last_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return LPB_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define LPB_TRY(call)              \
+  do {                             \
+    int rc__ = (call);             \
+    if (rc__ != LPB_OK) return rc__; \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------ reductions
+// Deterministic two-stage reductions: each block writes one partial per value into
+// partials[val * kMaxRedBlocks + block]; `finalize_reduce` folds them in block order.
+constexpr int kMaxRedVals = 8;
+constexpr int kMaxRedBlocks = 1024;
+enum RedOp : int { kRedSum = 0, kRedMin = 1 };
+
+// ------------------------------------------------------------------ per-context launch state
+struct LaunchCtx {
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;       // kernels launched by this library on this context
+  double* red_partials = nullptr;  // kMaxRedVals * kMaxRedBlocks
+  double* red_out = nullptr;       // device, kMaxRedVals
+  double* red_host = nullptr;      // pinned, kMaxRedVals
+  double* gemv_partials = nullptr; // gemv_t row-chunk partials
+  int64_t gemv_partials_cap = 0;   // in doubles
+  int* info_dev = nullptr;         // potrf info flag
+  int* info_host = nullptr;        // pinned
+};
+
+}  // namespace lpb

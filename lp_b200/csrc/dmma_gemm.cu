@@ -1,0 +1,402 @@
+// dmma_gemm.cu -- K1: lower(M) = A diag(d) A^T, and the Cholesky trailing update C -= P P^T,
+// on the Blackwell FP64 tensor path (DMMA) fed by TMA.
+//
+// Replaces /root/reference/src/solvers/interior_point/newton_equations.rs:54-57
+// (`A.dot(&(Dinv[:,None] * A.t()))`: a full 2m^2n GEMM plus an n x m temporary) with a
+// triangle-only m(m+1)n SYRK whose D-scaling is fused into the operand fragments.
+//
+// Design (sm_100a):
+//  * tcgen05.mma has no f64 kind; FP64 tensor math on Blackwell is the warp-level
+//    mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  Both operands of M[i,j] = sum_k A[i,k] d[k] A[j,k]
+//    are K-contiguous rows of row-major A, which is exactly the `.row.col` form.
+//  * One persistent CTA per SM walks the lower-triangular 128x128 tile list.  A dedicated producer
+//    warp streams 128x16 operand boxes (128-byte rows, SWIZZLE_128B) plus the 16 d[k] values of
+//    each K-block with cp.async.bulk.tensor into a 4-stage mbarrier ring; 8 consumer warps hold a
+//    64x32 accumulator slab each (64 doubles / thread) and issue 64 DMMAs per K-block.
+//  * Fragments are read with conflict-free ld.shared.v2.f64: thread (g,t) of a warp fetches the
+//    16-byte chunk (2t+P)^g of row g, so a quarter-warp covers all 8 chunks of the 128-byte
+//    swizzle atom; the .x halves feed one DMMA k-group {4t+2P}, the .y halves the next {4t+2P+1}
+//    (any k permutation is legal as long as A- and B-fragments agree).
+//  * d[k] is applied to the B-fragment in registers (8 DMUL per 64 DMMA).
+#include <cuda.h>
+
+#include "kernels.hpp"
+
+namespace lpb {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int kStages = 4;
+constexpr int kConsumerWarps = 8;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr uint32_t kTileBytes = BM * BK * 8;  // 16 KB
+constexpr uint32_t kDBytes = BK * 8;          // 128 B
+constexpr uint32_t kSmemA = 0;
+constexpr uint32_t kSmemB = kSmemA + kStages * kTileBytes;
+constexpr uint32_t kSmemD = kSmemB + kStages * kTileBytes;
+constexpr uint32_t kSmemBar = kSmemD + kStages * kDBytes;
+constexpr uint32_t kSmemTotal = kSmemBar + 2 * kStages * 8;
+constexpr uint32_t kSmemAlloc = kSmemTotal + 1024;  // slack for 1024-byte alignment
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a lost TMA / barrier bug traps after ~4 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ double2 lds_v2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+// linear lower-triangle index -> (ti, tj), tj <= ti
+__device__ __forceinline__ void tri_decode(int L, int* ti, int* tj) {
+  int i = static_cast<int>((sqrt(8.0 * static_cast<double>(L) + 1.0) - 1.0) * 0.5);
+  while (i * (i + 1) / 2 > L) --i;
+  while ((i + 1) * (i + 2) / 2 <= L) ++i;
+  *ti = i;
+  *tj = L - i * (i + 1) / 2;
+}
+
+// SCALE: multiply the B operand by d[k].  ACCUM: C -= A B^T (Cholesky trailing update) else C = A B^T.
+template <bool SCALE, bool ACCUM>
+__global__ void __maxnreg__(224)
+syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
+                 double* __restrict__ C, int64_t ldc, int m_total, int tile0, int ntr, int k_begin, int nkb) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base + kSmemA, sB = smem_base + kSmemB, sD = smem_base + kSmemD;
+  const uint32_t bar_full = smem_base + kSmemBar, bar_empty = bar_full + kStages * 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_empty + s * 8, kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int ntiles = ntr * (ntr + 1) / 2;
+  int stage = 0;
+  uint32_t phase = 0;
+
+  if (warp == kConsumerWarps) {
+    // ------------------------------------------------------------ TMA producer (one lane)
+    if (lane == 0) {
+      const uint32_t bytes = 2 * kTileBytes + (SCALE ? kDBytes : 0);
+      for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
+        int ti, tj;
+        tri_decode(L, &ti, &tj);
+        const int row_i = (tile0 + ti) * BM, row_j = (tile0 + tj) * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+          const uint32_t full = bar_full + stage * 8;
+          mbar_expect_tx(full, bytes);
+          const int k = k_begin + kb * BK;
+          tma_load_2d(sA + stage * kTileBytes, &tmA, k, row_i, full);
+          tma_load_2d(sB + stage * kTileBytes, &tmA, k, row_j, full);
+          if (SCALE) tma_load_2d(sD + stage * kDBytes, &tmD, k, 0, full);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------- DMMA consumers
+  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps -> 64 x 32 slab each
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t offA = static_cast<uint32_t>(wm * 64 + g) * 128u;
+  const uint32_t offB = static_cast<uint32_t>(wn * 32 + g) * 128u;
+  const uint32_t sw[2] = {static_cast<uint32_t>(((2 * t + 0) ^ g) << 4), static_cast<uint32_t>(((2 * t + 1) ^ g) << 4)};
+  const uint32_t dof[2] = {static_cast<uint32_t>((2 * t + 0) << 4), static_cast<uint32_t>((2 * t + 1) << 4)};
+
+  for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
+    int ti, tj;
+    tri_decode(L, &ti, &tj);
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(bar_full + stage * 8, phase);
+      const uint32_t a_base = sA + stage * kTileBytes + offA;
+      const uint32_t b_base = sB + stage * kTileBytes + offB;
+      const uint32_t d_base = sD + stage * kDBytes;
+#pragma unroll
+      for (int P = 0; P < 2; ++P) {
+        double2 b[4];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = lds_v2(b_base + ni * 1024 + sw[P]);
+        if (SCALE) {
+          const double2 d = lds_v2(d_base + dof[P]);
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            b[ni].x *= d.x;
+            b[ni].y *= d.y;
+          }
+        }
+        double2 a[8];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) a[mi] = lds_v2(a_base + mi * 1024 + sw[P]);
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + stage * 8);
+      if (++stage == kStages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+
+    // ------------------------------------------------------------ epilogue (each warp its own slab)
+    const int row0 = (tile0 + ti) * BM + wm * 64 + g;
+    const int col0 = (tile0 + tj) * BN + wn * 32 + 2 * t;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+      const int r = row0 + mi * 8;
+      if (r < m_total) {
+        double* crow = C + static_cast<int64_t>(r) * ldc;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int c = col0 + ni * 8;
+          if (c < m_total) {
+            double2* p = reinterpret_cast<double2*>(crow + c);
+            double2 v;
+            if (ACCUM) {
+              const double2 old = *p;
+              v.x = old.x - acc[mi][ni][0];
+              v.y = old.y - acc[mi][ni][1];
+            } else {
+              v.x = acc[mi][ni][0];
+              v.y = acc[mi][ni][1];
+            }
+            *p = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    LPB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) {
+      set_last_error("cuTensorMapEncodeTiled not available from the driver");
+      return LPB_ERR_CUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *out = fn;
+  return LPB_OK;
+}
+
+int make_tmap(CUtensorMap* tm, const double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+              uint32_t box_cols, bool swizzle) {
+  EncodeTiledFn fn;
+  LPB_TRY(get_encode_fn(&fn));
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {ld * sizeof(double)};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu ld=%llu", (int)r, (const void*)base,
+                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+    return LPB_ERR_CUDA;
+  }
+  return LPB_OK;
+}
+
+template <bool SCALE, bool ACCUM>
+int launch_dmma(LaunchCtx& lc, const CUtensorMap& tmA, const CUtensorMap& tmD, double* C, int64_t ldc, int m_total,
+                int tile0, int ntr, int k_begin, int nkb) {
+  static bool configured = false;
+  auto kern = syrk_dmma_kernel<SCALE, ACCUM>;
+  if (!configured) {
+    LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAlloc));
+    configured = true;
+  }
+  const int ntiles = ntr * (ntr + 1) / 2;
+  const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
+  kern<<<grid, kThreads, kSmemAlloc, lc.stream>>>(tmA, tmD, C, ldc, m_total, tile0, ntr, k_begin, nkb);
+  lc.launches++;
+  LPB_CUDA(cudaGetLastError());
+  return LPB_OK;
+}
+
+}  // namespace
+
+int k_syrk_dmma(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* d, double* Cmat,
+                int64_t ldc) {
+  if ((lda & 1) || (ldc & 1) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(Cmat) & 15) ||
+      (d && (reinterpret_cast<uintptr_t>(d) & 15))) {
+    set_last_error("syrk_dmma: A, d, M must be 16-byte aligned with even leading dimensions");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  if (m <= 0 || n <= 0) return LPB_OK;
+  CUtensorMap tmA, tmD;
+  LPB_TRY(make_tmap(&tmA, A, (uint64_t)m, (uint64_t)n, (uint64_t)lda, BM, BK, true));
+  if (d)
+    LPB_TRY(make_tmap(&tmD, d, 1, (uint64_t)n, (uint64_t)round_up(n, 2), 1, BK, false));
+  else
+    tmD = tmA;
+  const int ntr = (int)ceil_div(m, BM);
+  const int nkb = (int)ceil_div(n, BK);
+  if (d) return launch_dmma<true, false>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb);
+  return launch_dmma<false, false>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb);
+}
+
+int k_trailing_update_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb) {
+  const int64_t row0 = k0 + kb;
+  if (row0 >= m) return LPB_OK;
+  if ((row0 % BM) || (kb % BK) || (ldm & 1) || (reinterpret_cast<uintptr_t>(Mat) & 15)) {
+    set_last_error("trailing_update_dmma: panel origin must be a multiple of %d, width a multiple of %d", BM, BK);
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  CUtensorMap tm;
+  LPB_TRY(make_tmap(&tm, Mat, (uint64_t)m, (uint64_t)m, (uint64_t)ldm, BM, BK, true));
+  const int ntr = (int)ceil_div(m - row0, BM);
+  return launch_dmma<false, true>(lc, tm, tm, Mat, ldm, (int)m, (int)(row0 / BM), ntr, (int)k0, (int)(kb / BK));
+}
+
+// ------------------------------------------------------------------ plain DFMA reference kernel
+// Used by the parity tests to bisect the DMMA/TMA kernel; never selected by default.
+template <bool ACCUM>
+__global__ void __launch_bounds__(256)
+syrk_simple_kernel(int m_total, int row_origin, int k_begin, int k_end, const double* __restrict__ A, int64_t lda,
+                   const double* __restrict__ d, double* __restrict__ C, int64_t ldc) {
+  __shared__ double sa[16][65], sb[16][65];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4, tid = threadIdx.x;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = k_begin; k0 < k_end; k0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256, r = idx >> 4, k = idx & 15;
+      const int gk = k0 + k, gi = row_origin + bi * 64 + r, gj = row_origin + bj * 64 + r;
+      const bool kin = gk < k_end;
+      sa[k][r] = (kin && gi < m_total) ? A[(int64_t)gi * lda + gk] : 0.0;
+      sb[k][r] = (kin && gj < m_total) ? A[(int64_t)gj * lda + gk] * (d ? d[gk] : 1.0) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sa[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sb[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row_origin + bi * 64 + ty * 4 + i;
+    if (r >= m_total) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = row_origin + bj * 64 + tx * 4 + j;
+      if (c >= m_total) continue;
+      double* p = C + (int64_t)r * ldc + c;
+      *p = ACCUM ? (*p - acc[i][j]) : acc[i][j];
+    }
+  }
+}
+
+int k_syrk_simple(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* d, double* Cmat,
+                  int64_t ldc) {
+  if (m <= 0) return LPB_OK;
+  const int nt = (int)ceil_div(m, 64);
+  syrk_simple_kernel<false><<<dim3(nt, nt), 256, 0, lc.stream>>>((int)m, 0, 0, (int)n, A, lda, d, Cmat, ldc);
+  lc.launches++;
+  LPB_CUDA(cudaGetLastError());
+  return LPB_OK;
+}
+
+int k_trailing_update_simple(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb) {
+  const int64_t row0 = k0 + kb;
+  if (row0 >= m) return LPB_OK;
+  const int nt = (int)ceil_div(m - row0, 64);
+  syrk_simple_kernel<true><<<dim3(nt, nt), 256, 0, lc.stream>>>((int)m, (int)row0, (int)k0, (int)(k0 + kb), Mat, ldm,
+                                                                 nullptr, Mat, ldm);
+  lc.launches++;
+  LPB_CUDA(cudaGetLastError());
+  return LPB_OK;
+}
+
+}  // namespace lpb

@@ -1,0 +1,92 @@
+// kernels.hpp -- host-side launchers of the sm_100a kernels (internal C++ interface).
+#pragma once
+#include "common.cuh"
+
+namespace lpb {
+
+// ---------------------------------------------------------------- reductions (vec_kernels.cu)
+struct RedSpec {
+  int nvals = 0;
+  int nblocks[kMaxRedVals] = {0};
+  int op[kMaxRedVals] = {0};
+};
+// Fold block partials (lc.red_partials) into lc.red_out[0..nvals).
+int reduce_finalize(LaunchCtx& lc, const RedSpec& spec);
+// D2H of lc.red_out[0..nvals) into lc.red_host + stream sync.
+int fetch_scalars(LaunchCtx& lc, int nvals);
+
+// ---------------------------------------------------------------- K5 vector kernels (vec_kernels.cu)
+int k_fill(LaunchCtx& lc, double* p, int64_t n, double v);
+int k_copy(LaunchCtx& lc, double* dst, const double* src, int64_t n);
+int k_dinv(LaunchCtx& lc, int64_t n, const double* x, const double* z, double* dinv);
+
+// rhat.rs:32 / :54-55 / :64 and the r1 = d_hat - xs/x of newton_equations.rs:188.
+//   mode 0 predictor: xs = (x*-1)*z + gm
+//   mode 1 corrector, ip: xs = (x*-1)*z - (dx*dz)*a2 + s
+//   mode 2 corrector:     xs = (x*-1)*z + gm - dx*dz
+int k_rhat(LaunchCtx& lc, int64_t n, int mode, double eta, double gm, double a2, double s, const double* x,
+           const double* z, const double* rD, const double* dx, const double* dz, double* xs, double* r1);
+
+// delta.rs:33,37 + ratio test feasible_point.rs:61-62; block partial mins -> red_partials rows
+// (val_base, val_base+1).  Returns number of blocks used in *nblocks.
+int k_assemble_delta_n(LaunchCtx& lc, int64_t n, double d_tau, const double* u, const double* p, const double* xs,
+                       const double* x, const double* z, double* dx, double* dz, int val_base, int* nblocks);
+// d_y = v + q d_tau (delta.rs:34)
+int k_assemble_delta_m(LaunchCtx& lc, int64_t m, double d_tau, const double* v, const double* q, double* dy);
+// feasible_point.rs:77-95
+int k_step(LaunchCtx& lc, int64_t n, double alpha, int clamp, double* x, const double* dx);
+// x_out = x / tau ; partial c.x_out -> red row val
+int k_extract_x(LaunchCtx& lc, int64_t n, double tau, const double* x, const double* c, double* xo, int val,
+                int* nblocks);
+
+// m-side epilogues of the A.w sweeps
+// rP = b*tau - t ; partials: sum rP^2 -> val_base, b.y -> val_base+1
+int k_resid_p(LaunchCtx& lc, int64_t m, double tau, const double* b, const double* t, const double* y, double* rP,
+              int val_base, int* nblocks);
+// rhs0 = rP*eta + t0 ; (with_pq) rhs1 = b + t1          (newton_equations.rs:220)
+int k_sym_fwd_rhs(LaunchCtx& lc, int64_t m, double eta, const double* rP, const double* b, const double* t0,
+                  const double* t1, double* rhs0, double* rhs1, int with_pq);
+// partials: b.v -> val_base ; (with_pq) b.q -> val_base+1, #NaN(q) -> val_base+2
+int k_dots_m(LaunchCtx& lc, int64_t m, const double* b, const double* v, const double* q, int with_pq, int val_base,
+             int* nblocks);
+
+// ---------------------------------------------------------------- K4 sweeps over A (vec_kernels.cu)
+// t_k = A (dinv? dinv∘w_k : w_k), k < nrhs (1 or 2).  Raw products (no epilogue).
+int k_gemv_n(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* dinv, const double* w0,
+             const double* w1, double* t0, double* t1, int nrhs);
+// Row-chunk partials of A^T v_k into lc.gemv_partials; returns chunk count.
+int k_gemv_t_partials(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* v0,
+                      const double* v1, int nrhs, int* nchunks);
+// n-side epilogues consuming the partials:
+//  raw: out = sum_chunks
+int k_gemv_t_raw(LaunchCtx& lc, int64_t n, int nchunks, int nrhs, double* out0, double* out1);
+//  residual: rD = c*tau - s - z ; partials sum rD^2 -> val_base, c.x -> +1, x.z -> +2
+int k_resid_d(LaunchCtx& lc, int64_t n, int nchunks, double tau, const double* c, const double* z, const double* x,
+              double* rD, int val_base, int* nblocks);
+//  sym_solve back (newton_equations.rs:223): u = dinv*(s0 - r1) ; (with_pq) p = dinv*(s1 - c)
+//  partials c.u -> val_base ; (with_pq) c.p -> +1, #NaN(p) -> +2
+int k_sym_back(LaunchCtx& lc, int64_t n, int nchunks, int with_pq, const double* dinv, const double* r1,
+               const double* c, double* u, double* p, int val_base, int* nblocks);
+
+// ---------------------------------------------------------------- K1 / K2 trailing update (dmma_gemm.cu)
+// C(lower tiles) = A diag(d) A^T over k in [0, n)           (accumulate == 0, d may be null)
+// C(lower tiles) -= P P^T with P = Mat[row0.., k0..k0+kb)    (accumulate == 1)
+int k_syrk_dmma(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* d, double* Cmat,
+                int64_t ldc);
+int k_trailing_update_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb);
+// plain DFMA reference kernels (tests / bisecting only)
+int k_syrk_simple(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* d, double* Cmat,
+                  int64_t ldc);
+int k_trailing_update_simple(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb);
+
+// ---------------------------------------------------------------- K2 / K3 (cholesky.cu)
+// In-place blocked right-looking lower Cholesky; info (device int) = 0 or first bad pivot + 1.
+int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl);
+// Solve L L^T X = B in place; B column-major m x nrhs.
+int k_potrs(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B, int nrhs);
+
+// ---------------------------------------------------------------- synthetic shard fill (vec_kernels.cu)
+int k_fill_normal(LaunchCtx& lc, double* A, int64_t rows, int64_t cols, int64_t lda, int64_t row0, int64_t col0,
+                  uint64_t seed);
+
+}  // namespace lpb

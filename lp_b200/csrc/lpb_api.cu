@@ -1,0 +1,768 @@
+// lpb_api.cu -- the CUDA device context and the extern "C" boundary (include/lpb200.h).
+//
+// `CudaDev` implements the phase calls that lp_b200/csrc/ipm_driver.hpp drives; lpb_solve is that
+// driver instantiated on it.  State layout in HBM (all FP64):
+//   A   m x lda   row-major slack-form constraint matrix (lda = n rounded up to 16 doubles)
+//   M   m x ldm   normal matrix, overwritten in place by its lower Cholesky factor
+//   n-vectors: c x z rD dinv xs r1 p u dx dz xo       m-vectors: b y rP dy t[2] W[2] (W0 = v, W1 = q)
+// Column-sharded contexts (world > 1) hold n_local columns of A and of every n-vector; m-vectors,
+// M and all scalars are replicated, with NCCL all-reduces where SURVEY.md 8(e) says.
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ipm_driver.hpp"
+#include "kernels.hpp"
+
+namespace lpb {
+int64_t gemv_t_partials_doubles(int64_t m, int64_t n);
+}
+
+using namespace lpb;
+
+enum Phase { PH_SYRK = 0, PH_POTRF, PH_SOLVE, PH_SWEEP, PH_VEC, PH_COMM, PH_COUNT };
+
+struct PhaseRec {
+  int phase;
+  cudaEvent_t a, b;
+};
+
+struct lpb_ctx {
+  LaunchCtx lc;
+  bool own_stream = false;
+  bool has_problem = false;
+  int64_t m = 0, n = 0, n_global = 0, col0 = 0, lda = 0, ldm = 0;
+  double c0 = 0.0;
+  double *A = nullptr, *M = nullptr;
+  double *b = nullptr, *y = nullptr, *rP = nullptr, *dy = nullptr, *t = nullptr, *W = nullptr;
+  double *c = nullptr, *x = nullptr, *z = nullptr, *rD = nullptr, *dinv = nullptr, *xs = nullptr, *r1 = nullptr,
+         *p = nullptr, *u = nullptr, *dx = nullptr, *dz = nullptr, *xo = nullptr;
+  bool have_pq = false;
+  double cp = 0.0, bq = 0.0;
+  int nan_pq = 0;
+  int syrk_impl = 0;
+  bool profile = true;
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  SolveOutput last;
+  lpb_profile prof;
+  std::vector<cudaEvent_t> ev_free;
+  std::vector<PhaseRec> recs;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+#define LPB_NCCL(call)                                                                      \
+  do {                                                                                      \
+    ncclResult_t r__ = (call);                                                              \
+    if (r__ != ncclSuccess) {                                                               \
+      set_last_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r__)); \
+      return LPB_ERR_NCCL;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+int dev_alloc(lpb_ctx* c, double** p, int64_t count) {
+  void* q = nullptr;
+  if (count < 1) count = 1;
+  LPB_CUDA(cudaMalloc(&q, sizeof(double) * (size_t)count));
+  c->allocs.push_back(q);
+  *p = static_cast<double*>(q);
+  return LPB_OK;
+}
+
+struct PhaseTimer {
+  lpb_ctx* c;
+  PhaseRec rec;
+  bool on;
+  PhaseTimer(lpb_ctx* ctx, int phase) : c(ctx), on(ctx->profile) {
+    if (!on) return;
+    rec.phase = phase;
+    rec.a = take();
+    rec.b = take();
+    if (rec.a && rec.b) cudaEventRecord(rec.a, c->lc.stream);
+  }
+  ~PhaseTimer() {
+    if (!on || !rec.a || !rec.b) return;
+    cudaEventRecord(rec.b, c->lc.stream);
+    c->recs.push_back(rec);
+  }
+  cudaEvent_t take() {
+    if (!c->ev_free.empty()) {
+      cudaEvent_t e = c->ev_free.back();
+      c->ev_free.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    return e;
+  }
+};
+
+void profile_reset(lpb_ctx* c) {
+  for (auto& r : c->recs) {
+    c->ev_free.push_back(r.a);
+    c->ev_free.push_back(r.b);
+  }
+  c->recs.clear();
+  std::memset(&c->prof, 0, sizeof(c->prof));
+}
+
+void profile_collect(lpb_ctx* c) {
+  double ms[PH_COUNT] = {0};
+  for (auto& r : c->recs) {
+    float f = 0.f;
+    if (cudaEventElapsedTime(&f, r.a, r.b) == cudaSuccess) ms[r.phase] += f;
+    c->ev_free.push_back(r.a);
+    c->ev_free.push_back(r.b);
+  }
+  c->recs.clear();
+  c->prof.syrk_ms = ms[PH_SYRK];
+  c->prof.potrf_ms = ms[PH_POTRF];
+  c->prof.solve_ms = ms[PH_SOLVE];
+  c->prof.sweep_ms = ms[PH_SWEEP];
+  c->prof.vector_ms = ms[PH_VEC];
+  c->prof.comm_ms = ms[PH_COMM];
+}
+
+int allreduce(lpb_ctx* c, double* buf, int64_t count, ncclRedOp_t op) {
+  if (c->world <= 1) return LPB_OK;
+  PhaseTimer tm(c, PH_COMM);
+  LPB_NCCL(ncclAllReduce(buf, buf, (size_t)count, ncclDouble, op, c->comm, c->lc.stream));
+  return LPB_OK;
+}
+
+// Fold partials, all-reduce the first `n_sharded` values (they are sums / mins over this rank's
+// columns), fetch all `nvals` to the host.
+int finish_scalars(lpb_ctx* c, const RedSpec& spec, int n_sharded, ncclRedOp_t op) {
+  LPB_TRY(reduce_finalize(c->lc, spec));
+  if (n_sharded > 0) LPB_TRY(allreduce(c, c->lc.red_out, n_sharded, op));
+  return fetch_scalars(c->lc, spec.nvals);
+}
+
+struct CudaDev {
+  lpb_ctx* c;
+
+  int blind_start() {  // feasible_point.rs:24-39
+    PhaseTimer tm(c, PH_VEC);
+    LPB_TRY(k_fill(c->lc, c->x, c->n, 1.0));
+    LPB_TRY(k_fill(c->lc, c->z, c->n, 1.0));
+    LPB_TRY(k_fill(c->lc, c->y, c->m, 0.0));
+    c->have_pq = false;
+    return LPB_OK;
+  }
+
+  int residuals(double tau, double kappa, lpb_residual_scalars* o) {
+    (void)kappa;
+    RedSpec spec;
+    spec.nvals = 5;
+    int nb_n = 0, nb_m = 0, nchunks = 0;
+    {
+      PhaseTimer tm(c, PH_SWEEP);
+      LPB_TRY(k_gemv_n(c->lc, c->m, c->n, c->A, c->lda, nullptr, c->x, nullptr, c->t, nullptr, 1));
+    }
+    LPB_TRY(allreduce(c, c->t, c->m, ncclSum));
+    {
+      PhaseTimer tm(c, PH_SWEEP);
+      LPB_TRY(k_resid_p(c->lc, c->m, tau, c->b, c->t, c->y, c->rP, 3, &nb_m));
+      LPB_TRY(k_gemv_t_partials(c->lc, c->m, c->n, c->A, c->lda, c->y, nullptr, 1, &nchunks));
+      LPB_TRY(k_resid_d(c->lc, c->n, nchunks, tau, c->c, c->z, c->x, c->rD, 0, &nb_n));
+    }
+    spec.nblocks[0] = spec.nblocks[1] = spec.nblocks[2] = nb_n;
+    spec.nblocks[3] = spec.nblocks[4] = nb_m;
+    LPB_TRY(finish_scalars(c, spec, 3, ncclSum));
+    const double* h = c->lc.red_host;
+    o->nrm_rd = std::sqrt(h[0]);
+    o->cx = h[1];
+    o->xz = h[2];
+    o->nrm_rp = std::sqrt(h[3]);
+    o->by = h[4];
+    return LPB_OK;
+  }
+
+  int form_and_factor() {  // newton_equations.rs:48-64
+    {
+      PhaseTimer tm(c, PH_SYRK);
+      LPB_TRY(k_dinv(c->lc, c->n, c->x, c->z, c->dinv));
+      if (c->syrk_impl == 1)
+        LPB_TRY(k_syrk_simple(c->lc, c->m, c->n, c->A, c->lda, c->dinv, c->M, c->ldm));
+      else
+        LPB_TRY(k_syrk_dmma(c->lc, c->m, c->n, c->A, c->lda, c->dinv, c->M, c->ldm));
+      c->prof.syrk_launches++;
+    }
+    LPB_TRY(allreduce(c, c->M, c->m * c->ldm, ncclSum));
+    {
+      PhaseTimer tm(c, PH_POTRF);
+      LPB_TRY(k_potrf(c->lc, c->m, c->M, c->ldm, c->syrk_impl));
+      c->prof.potrf_launches++;
+    }
+    LPB_CUDA(cudaMemcpyAsync(c->lc.info_host, c->lc.info_dev, sizeof(int), cudaMemcpyDeviceToHost, c->lc.stream));
+    LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+    c->have_pq = false;
+    if (*c->lc.info_host != 0) return LPB_ERR_NUMERICAL_PROBLEM;  // newton_equations.rs:63
+    return LPB_OK;
+  }
+
+  int direction(const lpb_direction_in& in, double tau, double kappa, lpb_direction_out* o) {
+    (void)tau;
+    (void)kappa;
+    const int with_pq = c->have_pq ? 0 : 1;
+    const int nrhs = with_pq ? 2 : 1;
+    const double gm = in.gamma * in.mu;
+    const double a2 = in.alpha * in.alpha;
+    const double s = (1.0 - in.alpha) * in.gamma * in.mu;
+    const int mode = !in.corrector ? 0 : (in.ip ? 1 : 2);
+    double* W0 = c->W;
+    double* W1 = c->W + c->m;
+    {
+      PhaseTimer tm(c, PH_VEC);
+      LPB_TRY(k_rhat(c->lc, c->n, mode, in.eta, gm, a2, s, c->x, c->z, c->rD, c->dx, c->dz, c->xs, c->r1));
+    }
+    {
+      PhaseTimer tm(c, PH_SWEEP);
+      LPB_TRY(k_gemv_n(c->lc, c->m, c->n, c->A, c->lda, c->dinv, c->r1, c->c, c->t, c->t + c->m, nrhs));
+    }
+    LPB_TRY(allreduce(c, c->t, c->m * nrhs, ncclSum));
+    {
+      PhaseTimer tm(c, PH_VEC);
+      LPB_TRY(k_sym_fwd_rhs(c->lc, c->m, in.eta, c->rP, c->b, c->t, c->t + c->m, W0, W1, with_pq));
+    }
+    {
+      PhaseTimer tm(c, PH_SOLVE);
+      LPB_TRY(k_potrs(c->lc, c->m, c->M, c->ldm, c->W, nrhs));
+    }
+    RedSpec spec;
+    spec.nvals = 6;
+    int nchunks = 0, nb_n = 0, nb_m = 0;
+    {
+      PhaseTimer tm(c, PH_SWEEP);
+      LPB_TRY(k_gemv_t_partials(c->lc, c->m, c->n, c->A, c->lda, W0, W1, nrhs, &nchunks));
+      LPB_TRY(k_sym_back(c->lc, c->n, nchunks, with_pq, c->dinv, c->r1, c->c, c->u, c->p, 0, &nb_n));
+      LPB_TRY(k_dots_m(c->lc, c->m, c->b, W0, W1, with_pq, 3, &nb_m));
+    }
+    spec.nblocks[0] = spec.nblocks[1] = spec.nblocks[2] = nb_n;
+    spec.nblocks[3] = spec.nblocks[4] = spec.nblocks[5] = nb_m;
+    LPB_TRY(finish_scalars(c, spec, 3, ncclSum));
+    const double* h = c->lc.red_host;
+    if (with_pq) {
+      c->cp = h[1];
+      c->bq = h[4];
+      c->nan_pq = (h[2] > 0.0 || h[5] > 0.0) ? 1 : 0;
+      c->have_pq = true;
+    }
+    o->cu = h[0];
+    o->bv = h[3];
+    o->cp = c->cp;
+    o->bq = c->bq;
+    o->nan_pq = c->nan_pq;
+    o->reserved = 0;
+    return LPB_OK;
+  }
+
+  int assemble_delta(double d_tau, double axz[2]) {
+    RedSpec spec;
+    spec.nvals = 2;
+    int nb = 0;
+    {
+      PhaseTimer tm(c, PH_VEC);
+      LPB_TRY(k_assemble_delta_n(c->lc, c->n, d_tau, c->u, c->p, c->xs, c->x, c->z, c->dx, c->dz, 0, &nb));
+      LPB_TRY(k_assemble_delta_m(c->lc, c->m, d_tau, c->W, c->W + c->m, c->dy));
+    }
+    spec.nblocks[0] = spec.nblocks[1] = nb;
+    spec.op[0] = spec.op[1] = kRedMin;
+    LPB_TRY(finish_scalars(c, spec, 2, ncclMin));
+    axz[0] = c->lc.red_host[0];
+    axz[1] = c->lc.red_host[1];
+    return LPB_OK;
+  }
+
+  int do_step(double alpha, int ip) {
+    PhaseTimer tm(c, PH_VEC);
+    LPB_TRY(k_step(c->lc, c->n, alpha, ip, c->x, c->dx));
+    LPB_TRY(k_step(c->lc, c->n, alpha, ip, c->z, c->dz));
+    LPB_TRY(k_step(c->lc, c->m, alpha, 0, c->y, c->dy));
+    return LPB_OK;
+  }
+
+  int extract_x(double tau, double* x_out, double* fun) {
+    RedSpec spec;
+    spec.nvals = 1;
+    int nb = 0;
+    LPB_TRY(k_extract_x(c->lc, c->n, tau, c->x, c->c, c->xo, 0, &nb));
+    spec.nblocks[0] = nb;
+    LPB_TRY(finish_scalars(c, spec, 1, ncclSum));
+    if (x_out)
+      LPB_CUDA(cudaMemcpyAsync(x_out, c->xo, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->lc.stream));
+    LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+    if (fun) *fun = c->lc.red_host[0] + c->c0;  // linear_program.rs:61-63
+    return LPB_OK;
+  }
+};
+
+int check_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    set_last_error("no CUDA device visible; liblpb200 has no CPU fallback");
+    return LPB_ERR_NO_DEVICE;
+  }
+  return LPB_OK;
+}
+
+int ctx_base_init(lpb_ctx* c, void* stream) {
+  if (stream) {
+    c->lc.stream = static_cast<cudaStream_t>(stream);
+  } else {
+    LPB_CUDA(cudaStreamCreateWithFlags(&c->lc.stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  LPB_TRY(dev_alloc(c, &c->lc.red_partials, (int64_t)kMaxRedVals * kMaxRedBlocks));
+  LPB_TRY(dev_alloc(c, &c->lc.red_out, kMaxRedVals));
+  LPB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->lc.red_host), sizeof(double) * kMaxRedVals));
+  LPB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->lc.info_host), sizeof(int)));
+  void* q = nullptr;
+  LPB_CUDA(cudaMalloc(&q, sizeof(int)));
+  c->allocs.push_back(q);
+  c->lc.info_dev = static_cast<int*>(q);
+  std::memset(&c->prof, 0, sizeof(c->prof));
+  return LPB_OK;
+}
+
+int ctx_alloc_vectors(lpb_ctx* c, int64_t m, int64_t n, bool with_matrices) {
+  c->m = m;
+  c->n = n;
+  c->lda = round_up(n, 16);
+  c->ldm = round_up(m, 16);
+  c->lc.gemv_partials_cap = gemv_t_partials_doubles(m, n);
+  LPB_TRY(dev_alloc(c, &c->lc.gemv_partials, c->lc.gemv_partials_cap));
+  if (!with_matrices) return LPB_OK;
+  LPB_TRY(dev_alloc(c, &c->A, m * c->lda));
+  LPB_TRY(dev_alloc(c, &c->M, m * c->ldm));
+  double** mv[] = {&c->b, &c->y, &c->rP, &c->dy};
+  for (auto p : mv) LPB_TRY(dev_alloc(c, p, m));
+  LPB_TRY(dev_alloc(c, &c->t, 2 * m));
+  LPB_TRY(dev_alloc(c, &c->W, 2 * m));
+  double** nv[] = {&c->c, &c->x, &c->z, &c->rD, &c->dinv, &c->xs, &c->r1, &c->p, &c->u, &c->dx, &c->dz, &c->xo};
+  for (auto p : nv) LPB_TRY(dev_alloc(c, p, round_up(n, 2)));
+  LPB_CUDA(cudaMemsetAsync(c->A, 0, sizeof(double) * (size_t)(m * c->lda), c->lc.stream));
+  LPB_CUDA(cudaMemsetAsync(c->M, 0, sizeof(double) * (size_t)(m * c->ldm), c->lc.stream));
+  LPB_CUDA(cudaMemsetAsync(c->dx, 0, sizeof(double) * (size_t)round_up(n, 2), c->lc.stream));
+  LPB_CUDA(cudaMemsetAsync(c->dz, 0, sizeof(double) * (size_t)round_up(n, 2), c->lc.stream));
+  return LPB_OK;
+}
+
+int upload_problem(lpb_ctx* c, const double* A, int64_t lda, const double* b, const double* cc, double c0, int mem) {
+  if (!A || !b || !cc || lda < c->n) {
+    set_last_error("set_problem: null pointer or lda < n");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  const cudaMemcpyKind kind = mem == LPB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  LPB_CUDA(cudaMemcpy2DAsync(c->A, sizeof(double) * c->lda, A, sizeof(double) * lda, sizeof(double) * c->n, c->m, kind,
+                             c->lc.stream));
+  LPB_CUDA(cudaMemcpyAsync(c->b, b, sizeof(double) * c->m, kind, c->lc.stream));
+  LPB_CUDA(cudaMemcpyAsync(c->c, cc, sizeof(double) * c->n, kind, c->lc.stream));
+  LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+  c->c0 = c0;
+  c->has_problem = true;
+  c->have_pq = false;
+  return LPB_OK;
+}
+
+void ctx_free(lpb_ctx* c) {
+  if (!c) return;
+  if (c->lc.stream) cudaStreamSynchronize(c->lc.stream);
+  if (c->comm) ncclCommDestroy(c->comm);
+  for (auto& r : c->recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (auto e : c->ev_free) cudaEventDestroy(e);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->lc.red_host) cudaFreeHost(c->lc.red_host);
+  if (c->lc.info_host) cudaFreeHost(c->lc.info_host);
+  if (c->own_stream && c->lc.stream) cudaStreamDestroy(c->lc.stream);
+  delete c;
+}
+
+int need_problem(lpb_ctx* c) {
+  if (!c || !c->has_problem) {
+    set_last_error("context has no problem attached");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  return LPB_OK;
+}
+
+}  // namespace
+
+// ====================================================================== extern "C"
+extern "C" {
+
+void lpb_options_default(lpb_options* o) {
+  if (o) options_default(o);
+}
+
+int lpb_options_validate(const lpb_options* o) {
+  const int rc = options_validate(o);
+  if (rc == LPB_ERR_UNSUPPORTED)
+    set_last_error("solver_type %d: only EquationSolverType::Cholesky runs on the GPU path", o->solver_type);
+  return rc;
+}
+
+const char* lpb_strerror(int code) {
+  switch (code) {
+    case LPB_OK: return "ok";
+    case LPB_ERR_UNCONSTRAINED:
+      return "The problem is unconstrained, meaning the solution is the all-zeros vector if `c` is nonnegative, or "
+             "unbounded otherwise.";
+    case LPB_ERR_NUMERICAL_PROBLEM:
+      return "The solver encountered numerical problems it could not recover from. Likely causes are linearly "
+             "dependent constraints or variables whose scale differs by multiple orders of magnitude.";
+    case LPB_ERR_INVALID_PARAMETER: return "A parameter was set to an invalid value";
+    case LPB_ERR_INCOMPATIBLE_INPUT_DIMENSIONS: return "The dimensions of your cost- and constraint arrays do not align.";
+    case LPB_ERR_INFEASIBLE: return "The solver finished successfully, it appears that the problem is infeasible.";
+    case LPB_ERR_UNBOUNDED: return "The solver finished successfully, it appears that your problem is unbounded.";
+    case LPB_ERR_ITERATION_LIMIT_EXCEEDED:
+      return "The solver failed to converge within the maximum number of iterations.";
+    case LPB_ERR_CUDA: return "CUDA error";
+    case LPB_ERR_NCCL: return "NCCL error";
+    case LPB_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+    case LPB_ERR_BAD_ARGUMENT: return "bad argument";
+    case LPB_ERR_UNSUPPORTED: return "unsupported on the B200 path";
+    default: return "unknown lpb status";
+  }
+}
+
+const char* lpb_last_error(void) { return get_last_error(); }
+int lpb_abi_version(void) { return LPB_ABI_VERSION; }
+
+int lpb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------- problem model (host only)
+int lpb_slack_dims(int64_t n_c, int64_t rows_ub, int64_t cols_ub, int64_t len_b_ub, int64_t rows_eq, int64_t cols_eq,
+                   int64_t len_b_eq, int64_t* m_out, int64_t* n_out, int64_t* n_slack_out) {
+  if (rows_ub < 0 || rows_eq < 0 || n_c < 0) return LPB_ERR_BAD_ARGUMENT;
+  if (rows_ub + rows_eq == 0) return LPB_ERR_UNCONSTRAINED;  // linear_program.rs:134-136
+  if (cols_ub != cols_eq || cols_eq != n_c || rows_ub != len_b_ub || rows_eq != len_b_eq)
+    return LPB_ERR_INCOMPATIBLE_INPUT_DIMENSIONS;            // :137-143
+  if (m_out) *m_out = rows_ub + rows_eq;
+  if (n_out) *n_out = n_c + rows_ub;
+  if (n_slack_out) *n_slack_out = rows_ub;                   // :161
+  return LPB_OK;
+}
+
+int lpb_build_slack_form(const double* c, int64_t n_c, const double* A_ub, int64_t rows_ub, int64_t cols_ub,
+                         int64_t ld_ub, const double* b_ub, int64_t len_b_ub, const double* A_eq, int64_t rows_eq,
+                         int64_t cols_eq, int64_t ld_eq, const double* b_eq, int64_t len_b_eq, double* A_out,
+                         int64_t ld_out, double* b_out, double* c_out) {
+  int64_t m, n, ns;
+  LPB_TRY(lpb_slack_dims(n_c, rows_ub, cols_ub, len_b_ub, rows_eq, cols_eq, len_b_eq, &m, &n, &ns));
+  if (!c || !A_out || !b_out || !c_out || ld_out < n || (rows_ub && (!A_ub || !b_ub || ld_ub < n_c)) ||
+      (rows_eq && (!A_eq || !b_eq || ld_eq < n_c))) {
+    set_last_error("build_slack_form: null pointer or leading dimension too small");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  for (int64_t i = 0; i < m; ++i) {  // A = [[A_ub, I], [A_eq, 0]]   linear_program.rs:145-156
+    double* row = A_out + i * ld_out;
+    const double* src = i < rows_ub ? A_ub + i * ld_ub : A_eq + (i - rows_ub) * ld_eq;
+    std::memcpy(row, src, sizeof(double) * (size_t)n_c);
+    for (int64_t j = 0; j < ns; ++j) row[n_c + j] = 0.0;
+    if (i < rows_ub) row[n_c + i] = 1.0;
+    b_out[i] = i < rows_ub ? b_ub[i] : b_eq[i - rows_ub];  // :157
+  }
+  std::memcpy(c_out, c, sizeof(double) * (size_t)n_c);     // :159
+  for (int64_t j = 0; j < ns; ++j) c_out[n_c + j] = 0.0;
+  return LPB_OK;
+}
+
+int lpb_host_alloc(void** p, uint64_t bytes) {
+  if (!p) return LPB_ERR_BAD_ARGUMENT;
+  LPB_TRY(check_device());
+  LPB_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+  return LPB_OK;
+}
+
+int lpb_host_free(void* p) {
+  if (p) LPB_CUDA(cudaFreeHost(p));
+  return LPB_OK;
+}
+
+// ---------------------------------------------------------------- contexts
+int lpb_create_bare(lpb_ctx** out, int64_t m_max, int64_t n_max, void* stream) {
+  if (!out || m_max <= 0 || n_max <= 0) return LPB_ERR_BAD_ARGUMENT;
+  LPB_TRY(check_device());
+  lpb_ctx* c = new (std::nothrow) lpb_ctx();
+  if (!c) return LPB_ERR_BAD_ARGUMENT;
+  int rc = ctx_base_init(c, stream);
+  if (rc == LPB_OK) rc = ctx_alloc_vectors(c, m_max, n_max, false);
+  if (rc != LPB_OK) {
+    ctx_free(c);
+    return rc;
+  }
+  c->n_global = n_max;
+  *out = c;
+  return LPB_OK;
+}
+
+int lpb_create(lpb_ctx** out, int64_t m, int64_t n, const double* A, int64_t lda, const double* b, const double* cc,
+               double c0, int mem, void* stream) {
+  if (!out || m <= 0 || n <= 0) {
+    set_last_error("create: m and n must be positive");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  LPB_TRY(check_device());
+  lpb_ctx* c = new (std::nothrow) lpb_ctx();
+  if (!c) return LPB_ERR_BAD_ARGUMENT;
+  int rc = ctx_base_init(c, stream);
+  if (rc == LPB_OK) rc = ctx_alloc_vectors(c, m, n, true);
+  if (rc == LPB_OK) rc = upload_problem(c, A, lda, b, cc, c0, mem);
+  if (rc != LPB_OK) {
+    ctx_free(c);
+    return rc;
+  }
+  c->n_global = n;
+  *out = c;
+  return LPB_OK;
+}
+
+int lpb_set_problem(lpb_ctx* c, const double* A, int64_t lda, const double* b, const double* cc, double c0, int mem) {
+  if (!c || !c->A) return LPB_ERR_BAD_ARGUMENT;
+  return upload_problem(c, A, lda, b, cc, c0, mem);
+}
+
+int lpb_destroy(lpb_ctx* c) {
+  ctx_free(c);
+  return LPB_OK;
+}
+
+int lpb_nccl_unique_id(void* id128) {
+  if (!id128) return LPB_ERR_BAD_ARGUMENT;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  LPB_NCCL(ncclGetUniqueId(&id));
+  std::memcpy(id128, &id, sizeof(id));
+  return LPB_OK;
+}
+
+int lpb_create_sharded(lpb_ctx** out, int64_t m, int64_t n_global, int64_t col0, int64_t n_local, const double* A_local,
+                       int64_t lda, const double* b, const double* c_local, double c0, int mem, int rank, int world,
+                       const void* nccl_unique_id, void* stream) {
+  if (!out || m <= 0 || n_local <= 0 || n_global < n_local || col0 < 0 || col0 + n_local > n_global || world < 1 ||
+      rank < 0 || rank >= world || (world > 1 && !nccl_unique_id)) {
+    set_last_error("create_sharded: inconsistent shard description");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  LPB_TRY(check_device());
+  lpb_ctx* c = new (std::nothrow) lpb_ctx();
+  if (!c) return LPB_ERR_BAD_ARGUMENT;
+  int rc = ctx_base_init(c, stream);
+  if (rc == LPB_OK) rc = ctx_alloc_vectors(c, m, n_local, true);
+  if (rc == LPB_OK && A_local) rc = upload_problem(c, A_local, lda, b, c_local, c0, mem);
+  if (rc == LPB_OK && world > 1) {
+    ncclUniqueId id;
+    std::memcpy(&id, nccl_unique_id, sizeof(id));
+    ncclResult_t r = ncclCommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) {
+      set_last_error("ncclCommInitRank -> %s", ncclGetErrorString(r));
+      rc = LPB_ERR_NCCL;
+    }
+  }
+  if (rc != LPB_OK) {
+    ctx_free(c);
+    return rc;
+  }
+  c->n_global = n_global;
+  c->col0 = col0;
+  c->rank = rank;
+  c->world = world;
+  *out = c;
+  return LPB_OK;
+}
+
+int lpb_create_sharded_synthetic(lpb_ctx** out, int64_t m, int64_t n_global, int64_t col0, int64_t n_local,
+                                 uint64_t seed, int rank, int world, const void* nccl_unique_id, void* stream) {
+  (void)out; (void)m; (void)n_global; (void)col0; (void)n_local; (void)seed; (void)rank; (void)world;
+  (void)nccl_unique_id; (void)stream;
+  set_last_error("create_sharded_synthetic: not implemented yet");
+  return LPB_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------- phases
+int lpb_blind_start(lpb_ctx* c) {
+  LPB_TRY(need_problem(c));
+  CudaDev d{c};
+  return d.blind_start();
+}
+int lpb_residuals(lpb_ctx* c, double tau, double kappa, lpb_residual_scalars* out) {
+  LPB_TRY(need_problem(c));
+  if (!out) return LPB_ERR_BAD_ARGUMENT;
+  CudaDev d{c};
+  return d.residuals(tau, kappa, out);
+}
+int lpb_form_and_factor(lpb_ctx* c) {
+  LPB_TRY(need_problem(c));
+  CudaDev d{c};
+  return d.form_and_factor();
+}
+int lpb_direction(lpb_ctx* c, const lpb_direction_in* in, double tau, double kappa, lpb_direction_out* out) {
+  LPB_TRY(need_problem(c));
+  if (!in || !out) return LPB_ERR_BAD_ARGUMENT;
+  CudaDev d{c};
+  return d.direction(*in, tau, kappa, out);
+}
+int lpb_assemble_delta(lpb_ctx* c, double d_tau, double alpha_xz[2]) {
+  LPB_TRY(need_problem(c));
+  if (!alpha_xz) return LPB_ERR_BAD_ARGUMENT;
+  CudaDev d{c};
+  return d.assemble_delta(d_tau, alpha_xz);
+}
+int lpb_do_step(lpb_ctx* c, double alpha, int ip) {
+  LPB_TRY(need_problem(c));
+  CudaDev d{c};
+  return d.do_step(alpha, ip);
+}
+int lpb_extract_x(lpb_ctx* c, double tau, double* x_out, double* fun) {
+  LPB_TRY(need_problem(c));
+  CudaDev d{c};
+  return d.extract_x(tau, x_out, fun);
+}
+
+// ---------------------------------------------------------------- whole solve
+int lpb_solve(lpb_ctx* c, const lpb_options* opts, double* x_out, double* fun, int64_t* iterations) {
+  LPB_TRY(need_problem(c));
+  lpb_options o;
+  if (opts)
+    o = *opts;
+  else
+    options_default(&o);
+  LPB_TRY(lpb_options_validate(&o));
+  profile_reset(c);
+  const int64_t launches0 = c->lc.launches;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->profile) {
+    LPB_CUDA(cudaEventCreate(&e0));
+    LPB_CUDA(cudaEventCreate(&e1));
+    LPB_CUDA(cudaEventRecord(e0, c->lc.stream));
+  }
+  CudaDev dev{c};
+  int rc = solve_normal_form(dev, o, c->n_global, c->c0, &c->last);
+  if (iterations) *iterations = c->last.iterations;
+  if (rc == LPB_OK || rc == LPB_ERR_ITERATION_LIMIT_EXCEEDED) {
+    const int rc2 = dev.extract_x(c->last.tau, x_out, fun);
+    if (rc2 != LPB_OK) rc = rc2;
+  }
+  if (c->profile) {
+    cudaEventRecord(e1, c->lc.stream);
+    cudaEventSynchronize(e1);
+    float f = 0.f;
+    cudaEventElapsedTime(&f, e0, e1);
+    profile_collect(c);
+    c->prof.total_ms = f;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  c->prof.launches = c->lc.launches - launches0;
+  c->prof.iterations = c->last.iterations;
+  return rc;
+}
+
+int64_t lpb_trace(lpb_ctx* c, double* rows, int64_t max_rows) {
+  if (!c || !rows) return 0;
+  int64_t k = 0;
+  for (; k < (int64_t)c->last.trace.size() && k < max_rows; ++k)
+    std::memcpy(rows + k * LPB_TRACE_COLS, c->last.trace[k].v, sizeof(double) * LPB_TRACE_COLS);
+  return k;
+}
+
+// ---------------------------------------------------------------- kernel entry points
+int lpb_k_syrk_adat(lpb_ctx* c, int64_t m, int64_t n, const double* dA, int64_t lda, const double* d_d, double* dM,
+                    int64_t ldm) {
+  if (!c || !dA || !dM) return LPB_ERR_BAD_ARGUMENT;
+  int rc = c->syrk_impl == 1 ? k_syrk_simple(c->lc, m, n, dA, lda, d_d, dM, ldm)
+                             : k_syrk_dmma(c->lc, m, n, dA, lda, d_d, dM, ldm);
+  if (rc != LPB_OK) return rc;
+  LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+  return LPB_OK;
+}
+
+int lpb_k_potrf(lpb_ctx* c, int64_t m, double* dM, int64_t ldm, int32_t* info_host) {
+  if (!c || !dM) return LPB_ERR_BAD_ARGUMENT;
+  LPB_TRY(k_potrf(c->lc, m, dM, ldm, c->syrk_impl));
+  LPB_CUDA(cudaMemcpyAsync(c->lc.info_host, c->lc.info_dev, sizeof(int), cudaMemcpyDeviceToHost, c->lc.stream));
+  LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+  if (info_host) *info_host = *c->lc.info_host;
+  return LPB_OK;
+}
+
+int lpb_k_potrs(lpb_ctx* c, int64_t m, const double* dL, int64_t ldm, double* dB, int64_t nrhs) {
+  if (!c || !dL || !dB) return LPB_ERR_BAD_ARGUMENT;
+  LPB_TRY(k_potrs(c->lc, m, dL, ldm, dB, (int)nrhs));
+  LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+  return LPB_OK;
+}
+
+int lpb_k_gemv_n(lpb_ctx* c, int64_t m, int64_t n, const double* dA, int64_t lda, const double* d_w, double* d_out) {
+  if (!c || !dA || !d_w || !d_out) return LPB_ERR_BAD_ARGUMENT;
+  LPB_TRY(k_gemv_n(c->lc, m, n, dA, lda, nullptr, d_w, nullptr, d_out, nullptr, 1));
+  LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+  return LPB_OK;
+}
+
+int lpb_k_gemv_t(lpb_ctx* c, int64_t m, int64_t n, const double* dA, int64_t lda, const double* d_v, double* d_out) {
+  if (!c || !dA || !d_v || !d_out) return LPB_ERR_BAD_ARGUMENT;
+  if (gemv_t_partials_doubles(m, n) > c->lc.gemv_partials_cap) {
+    set_last_error("gemv_t: context work buffers were sized for a smaller problem");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  int nchunks = 0;
+  LPB_TRY(k_gemv_t_partials(c->lc, m, n, dA, lda, d_v, nullptr, 1, &nchunks));
+  LPB_TRY(k_gemv_t_raw(c->lc, n, nchunks, 1, d_out, nullptr));
+  LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+  return LPB_OK;
+}
+
+int lpb_solve_batched(int64_t batch, int64_t m, int64_t n, const double* A, const double* b, const double* c,
+                      const lpb_options* opts, double* x_out, double* fun, int64_t* iterations, int32_t* status,
+                      int mem, void* stream) {
+  (void)batch; (void)m; (void)n; (void)A; (void)b; (void)c; (void)opts; (void)x_out; (void)fun; (void)iterations;
+  (void)status; (void)mem; (void)stream;
+  set_last_error("solve_batched: not implemented yet");
+  return LPB_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------- measurement
+int lpb_get_profile(lpb_ctx* c, lpb_profile* out) {
+  if (!c || !out) return LPB_ERR_BAD_ARGUMENT;
+  *out = c->prof;
+  return LPB_OK;
+}
+
+int64_t lpb_launch_count(lpb_ctx* c) { return c ? c->lc.launches : 0; }
+
+int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
+  if (!c || !key) return LPB_ERR_BAD_ARGUMENT;
+  const std::string k(key);
+  if (k == "syrk_impl") {
+    if (value != 0 && value != 1) return LPB_ERR_BAD_ARGUMENT;
+    c->syrk_impl = (int)value;
+    return LPB_OK;
+  }
+  if (k == "profile") {
+    c->profile = value != 0;
+    return LPB_OK;
+  }
+  set_last_error("unknown option '%s'", key);
+  return LPB_ERR_BAD_ARGUMENT;
+}
+
+}  // extern "C"

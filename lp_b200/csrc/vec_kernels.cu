@@ -1,0 +1,614 @@
+// vec_kernels.cu -- K4 (sweeps over A) and K5 (fused vector passes + reductions), sm_100a.
+//
+// All of these are HBM-bound: coalesced double2 loads, warp-shuffle + block reductions,
+// deterministic two-stage grid reductions (no floating-point atomics), as few launches as the
+// dependency chain of one IPM iteration allows (5 sweeps over A).
+#include <cstdarg>
+
+#include "kernels.hpp"
+
+namespace lpb {
+
+// ------------------------------------------------------------------ last-error plumbing
+static thread_local char g_last_error[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+const char* get_last_error() { return g_last_error; }
+
+#define LPB_LAUNCH_CHECK(lc)                                                              \
+  do {                                                                                    \
+    (lc).launches++;                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                 \
+    if (e__ != cudaSuccess) {                                                             \
+      set_last_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return LPB_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+constexpr int kVecThreads = 256;
+
+static inline int vec_blocks(int64_t n) {
+  int64_t b = ceil_div(n, (int64_t)kVecThreads * 4);
+  if (b < 1) b = 1;
+  if (b > kMaxRedBlocks) b = kMaxRedBlocks;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------ device reduction helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide reduce of up to NV values held per thread; thread 0 writes partials[val*kMaxRedBlocks+blk].
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], const int (&op)[NV], double* partials,
+                                                   int val_base) {
+  __shared__ double sm[NV][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double r = op[k] == kRedMin ? warp_min(v[k]) : warp_sum(v[k]);
+    if (lane == 0) sm[k][warp] = r;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double r = lane < nwarp ? sm[k][lane] : (op[k] == kRedMin ? INFINITY : 0.0);
+      r = op[k] == kRedMin ? warp_min(r) : warp_sum(r);
+      if (lane == 0) partials[(size_t)(val_base + k) * kMaxRedBlocks + blockIdx.x] = r;
+    }
+  }
+}
+
+struct RedSpecDev {
+  int nvals;
+  int nblocks[kMaxRedVals];
+  int op[kMaxRedVals];
+};
+
+__global__ void finalize_reduce_kernel(const double* __restrict__ partials, RedSpecDev spec,
+                                       double* __restrict__ out) {
+  // one warp per value; fixed fold order -> deterministic
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= spec.nvals) return;
+  const int nb = spec.nblocks[warp];
+  const bool is_min = spec.op[warp] == kRedMin;
+  double r = is_min ? INFINITY : 0.0;
+  for (int i = lane; i < nb; i += 32) {
+    const double p = partials[(size_t)warp * kMaxRedBlocks + i];
+    r = is_min ? fmin(r, p) : r + p;
+  }
+  r = is_min ? warp_min(r) : warp_sum(r);
+  if (lane == 0) out[warp] = r;
+}
+
+int reduce_finalize(LaunchCtx& lc, const RedSpec& spec) {
+  RedSpecDev d;
+  d.nvals = spec.nvals;
+  for (int i = 0; i < kMaxRedVals; ++i) {
+    d.nblocks[i] = spec.nblocks[i];
+    d.op[i] = spec.op[i];
+  }
+  finalize_reduce_kernel<<<1, 32 * kMaxRedVals, 0, lc.stream>>>(lc.red_partials, d, lc.red_out);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+int fetch_scalars(LaunchCtx& lc, int nvals) {
+  LPB_CUDA(cudaMemcpyAsync(lc.red_host, lc.red_out, sizeof(double) * nvals, cudaMemcpyDeviceToHost, lc.stream));
+  LPB_CUDA(cudaStreamSynchronize(lc.stream));
+  return LPB_OK;
+}
+
+// ------------------------------------------------------------------ simple elementwise
+__global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+int k_fill(LaunchCtx& lc, double* p, int64_t n, double v) {
+  if (n <= 0) return LPB_OK;
+  fill_kernel<<<vec_blocks(n), kVecThreads, 0, lc.stream>>>(p, n, v);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+int k_copy(LaunchCtx& lc, double* dst, const double* src, int64_t n) {
+  if (n <= 0) return LPB_OK;
+  LPB_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, lc.stream));
+  return LPB_OK;
+}
+
+__global__ void dinv_kernel(int64_t n, const double* __restrict__ x, const double* __restrict__ z,
+                            double* __restrict__ dinv) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dinv[i] = x[i] / z[i];  // newton_equations.rs:54
+}
+int k_dinv(LaunchCtx& lc, int64_t n, const double* x, const double* z, double* dinv) {
+  dinv_kernel<<<vec_blocks(n), kVecThreads, 0, lc.stream>>>(n, x, z, dinv);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+template <int MODE>
+__global__ void rhat_kernel(int64_t n, double eta, double gm, double a2, double s, const double* __restrict__ x,
+                            const double* __restrict__ z, const double* __restrict__ rD,
+                            const double* __restrict__ dx, const double* __restrict__ dz, double* __restrict__ xs,
+                            double* __restrict__ r1) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double xi = x[i];
+    const double mxz = (xi * -1.0) * z[i];
+    double v;
+    if (MODE == 0) {
+      v = mxz + gm;                          // rhat.rs:32
+    } else if (MODE == 1) {
+      v = mxz - (dx[i] * dz[i]) * a2 + s;    // rhat.rs:54-55
+    } else {
+      v = mxz + gm - (dx[i] * dz[i]);        // rhat.rs:64
+    }
+    xs[i] = v;
+    r1[i] = rD[i] * eta - v / xi;            // newton_equations.rs:188 (rhat.d - rhat.xs / x)
+  }
+}
+int k_rhat(LaunchCtx& lc, int64_t n, int mode, double eta, double gm, double a2, double s, const double* x,
+           const double* z, const double* rD, const double* dx, const double* dz, double* xs, double* r1) {
+  const int nb = vec_blocks(n);
+  if (mode == 0)
+    rhat_kernel<0><<<nb, kVecThreads, 0, lc.stream>>>(n, eta, gm, a2, s, x, z, rD, dx, dz, xs, r1);
+  else if (mode == 1)
+    rhat_kernel<1><<<nb, kVecThreads, 0, lc.stream>>>(n, eta, gm, a2, s, x, z, rD, dx, dz, xs, r1);
+  else
+    rhat_kernel<2><<<nb, kVecThreads, 0, lc.stream>>>(n, eta, gm, a2, s, x, z, rD, dx, dz, xs, r1);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+__global__ void assemble_delta_n_kernel(int64_t n, double d_tau, const double* __restrict__ u,
+                                        const double* __restrict__ p, const double* __restrict__ xs,
+                                        const double* __restrict__ x, const double* __restrict__ z,
+                                        double* __restrict__ dx, double* __restrict__ dz,
+                                        double* __restrict__ partials, int val_base) {
+  double v[2] = {1.0, 1.0};  // fold(F::one(), min)  feasible_point.rs:61-62
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double xi = x[i], zi = z[i];
+    const double dxi = u[i] + p[i] * d_tau;       // delta.rs:33
+    const double dzi = (xs[i] - zi * dxi) / xi;   // delta.rs:37
+    dx[i] = dxi;
+    dz[i] = dzi;
+    if (dxi < 0.0) v[0] = fmin(v[0], xi / -dxi);
+    if (dzi < 0.0) v[1] = fmin(v[1], zi / -dzi);
+  }
+  const int op[2] = {kRedMin, kRedMin};
+  block_reduce_store<2>(v, op, partials, val_base);
+}
+int k_assemble_delta_n(LaunchCtx& lc, int64_t n, double d_tau, const double* u, const double* p, const double* xs,
+                       const double* x, const double* z, double* dx, double* dz, int val_base, int* nblocks) {
+  const int nb = vec_blocks(n);
+  assemble_delta_n_kernel<<<nb, kVecThreads, 0, lc.stream>>>(n, d_tau, u, p, xs, x, z, dx, dz, lc.red_partials,
+                                                             val_base);
+  LPB_LAUNCH_CHECK(lc);
+  *nblocks = nb;
+  return LPB_OK;
+}
+
+__global__ void assemble_delta_m_kernel(int64_t m, double d_tau, const double* __restrict__ v,
+                                        const double* __restrict__ q, double* __restrict__ dy) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+    dy[i] = v[i] + q[i] * d_tau;  // delta.rs:34
+}
+int k_assemble_delta_m(LaunchCtx& lc, int64_t m, double d_tau, const double* v, const double* q, double* dy) {
+  assemble_delta_m_kernel<<<vec_blocks(m), kVecThreads, 0, lc.stream>>>(m, d_tau, v, q, dy);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+__global__ void step_kernel(int64_t n, double alpha, int clamp, double* __restrict__ x,
+                            const double* __restrict__ dx) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = x[i] + dx[i] * alpha;  // feasible_point.rs:77-79
+    if (clamp) v = fmax(v, 1.0);      // :89-91
+    x[i] = v;
+  }
+}
+int k_step(LaunchCtx& lc, int64_t n, double alpha, int clamp, double* x, const double* dx) {
+  step_kernel<<<vec_blocks(n), kVecThreads, 0, lc.stream>>>(n, alpha, clamp, x, dx);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+__global__ void extract_x_kernel(int64_t n, double tau, const double* __restrict__ x, const double* __restrict__ c,
+                                 double* __restrict__ xo, double* __restrict__ partials, int val) {
+  double v[1] = {0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double t = x[i] / tau;  // mod.rs:231
+    xo[i] = t;
+    v[0] += c[i] * t;             // linear_program.rs:62
+  }
+  const int op[1] = {kRedSum};
+  block_reduce_store<1>(v, op, partials, val);
+}
+int k_extract_x(LaunchCtx& lc, int64_t n, double tau, const double* x, const double* c, double* xo, int val,
+                int* nblocks) {
+  const int nb = vec_blocks(n);
+  extract_x_kernel<<<nb, kVecThreads, 0, lc.stream>>>(n, tau, x, c, xo, lc.red_partials, val);
+  LPB_LAUNCH_CHECK(lc);
+  *nblocks = nb;
+  return LPB_OK;
+}
+
+// ------------------------------------------------------------------ m-side epilogues
+__global__ void resid_p_kernel(int64_t m, double tau, const double* __restrict__ b, const double* __restrict__ t,
+                               const double* __restrict__ y, double* __restrict__ rP, double* __restrict__ partials,
+                               int val_base) {
+  double v[2] = {0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const double bi = b[i];
+    const double r = bi * tau - t[i];  // feasible_point.rs:122 / residual.rs:23
+    rP[i] = r;
+    v[0] += r * r;
+    v[1] += bi * y[i];
+  }
+  const int op[2] = {kRedSum, kRedSum};
+  block_reduce_store<2>(v, op, partials, val_base);
+}
+int k_resid_p(LaunchCtx& lc, int64_t m, double tau, const double* b, const double* t, const double* y, double* rP,
+              int val_base, int* nblocks) {
+  const int nb = vec_blocks(m);
+  resid_p_kernel<<<nb, kVecThreads, 0, lc.stream>>>(m, tau, b, t, y, rP, lc.red_partials, val_base);
+  LPB_LAUNCH_CHECK(lc);
+  *nblocks = nb;
+  return LPB_OK;
+}
+
+__global__ void sym_fwd_rhs_kernel(int64_t m, double eta, const double* __restrict__ rP,
+                                   const double* __restrict__ b, const double* __restrict__ t0,
+                                   const double* __restrict__ t1, double* __restrict__ rhs0,
+                                   double* __restrict__ rhs1, int with_pq) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    rhs0[i] = rP[i] * eta + t0[i];           // r2 + A (Dinv∘r1), r2 = rhat.p = r_P*eta
+    if (with_pq) rhs1[i] = b[i] + t1[i];     // r2 = b
+  }
+}
+int k_sym_fwd_rhs(LaunchCtx& lc, int64_t m, double eta, const double* rP, const double* b, const double* t0,
+                  const double* t1, double* rhs0, double* rhs1, int with_pq) {
+  sym_fwd_rhs_kernel<<<vec_blocks(m), kVecThreads, 0, lc.stream>>>(m, eta, rP, b, t0, t1, rhs0, rhs1, with_pq);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+__global__ void dots_m_kernel(int64_t m, const double* __restrict__ b, const double* __restrict__ v,
+                              const double* __restrict__ q, int with_pq, double* __restrict__ partials,
+                              int val_base) {
+  double r[3] = {0.0, 0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const double bi = b[i];
+    r[0] += bi * v[i];
+    if (with_pq) {
+      const double qi = q[i];
+      r[1] += bi * qi;
+      r[2] += (qi != qi) ? 1.0 : 0.0;
+    }
+  }
+  const int op[3] = {kRedSum, kRedSum, kRedSum};
+  block_reduce_store<3>(r, op, partials, val_base);
+}
+int k_dots_m(LaunchCtx& lc, int64_t m, const double* b, const double* v, const double* q, int with_pq, int val_base,
+             int* nblocks) {
+  const int nb = vec_blocks(m);
+  dots_m_kernel<<<nb, kVecThreads, 0, lc.stream>>>(m, b, v, q, with_pq, lc.red_partials, val_base);
+  LPB_LAUNCH_CHECK(lc);
+  *nblocks = nb;
+  return LPB_OK;
+}
+
+// ------------------------------------------------------------------ K4: t = A w   (row-major A, warp per row)
+constexpr int kGemvNWarps = 8;
+
+template <int NRHS, bool SCALE>
+__global__ void __launch_bounds__(kGemvNWarps * 32)
+gemv_n_kernel(int64_t m, int64_t n, const double* __restrict__ A, int64_t lda, const double* __restrict__ dinv,
+              const double* __restrict__ w0, const double* __restrict__ w1, double* __restrict__ t0,
+              double* __restrict__ t1) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * kGemvNWarps + warp;
+  if (row >= m) return;
+  const double2* __restrict__ Ar = reinterpret_cast<const double2*>(A + row * lda);
+  const double2* __restrict__ W0 = reinterpret_cast<const double2*>(w0);
+  const double2* __restrict__ W1 = reinterpret_cast<const double2*>(w1);
+  const double2* __restrict__ D2 = reinterpret_cast<const double2*>(dinv);
+  const int64_t n2 = n >> 1;
+  double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 4
+  for (int64_t j = lane; j < n2; j += 32) {
+    const double2 a = __ldg(Ar + j);
+    double2 w = W0[j];
+    if (SCALE) {
+      const double2 d = D2[j];
+      w.x *= d.x;
+      w.y *= d.y;
+      if (NRHS == 2) {
+        double2 ww = W1[j];
+        ww.x *= d.x;
+        ww.y *= d.y;
+        acc1 += a.x * ww.x;
+        acc1 += a.y * ww.y;
+      }
+    } else if (NRHS == 2) {
+      const double2 ww = W1[j];
+      acc1 += a.x * ww.x;
+      acc1 += a.y * ww.y;
+    }
+    acc0 += a.x * w.x;
+    acc0 += a.y * w.y;
+  }
+  if ((n & 1) && lane == 0) {
+    const int64_t j = n - 1;
+    const double a = A[row * lda + j];
+    const double d = SCALE ? dinv[j] : 1.0;
+    acc0 += a * (SCALE ? d * w0[j] : w0[j]);
+    if (NRHS == 2) acc1 += a * (SCALE ? d * w1[j] : w1[j]);
+  }
+  acc0 = warp_sum(acc0);
+  if (NRHS == 2) acc1 = warp_sum(acc1);
+  if (lane == 0) {
+    t0[row] = acc0;
+    if (NRHS == 2) t1[row] = acc1;
+  }
+}
+
+int k_gemv_n(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* dinv, const double* w0,
+             const double* w1, double* t0, double* t1, int nrhs) {
+  if ((lda & 1) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(w0) & 15) ||
+      (dinv && (reinterpret_cast<uintptr_t>(dinv) & 15)) || (nrhs == 2 && (reinterpret_cast<uintptr_t>(w1) & 15))) {
+    set_last_error("gemv_n: A/w/dinv must be 16-byte aligned and lda even");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  const int nb = (int)ceil_div(m, kGemvNWarps);
+  const dim3 block(kGemvNWarps * 32);
+  if (nrhs == 2) {
+    if (dinv)
+      gemv_n_kernel<2, true><<<nb, block, 0, lc.stream>>>(m, n, A, lda, dinv, w0, w1, t0, t1);
+    else
+      gemv_n_kernel<2, false><<<nb, block, 0, lc.stream>>>(m, n, A, lda, dinv, w0, w1, t0, t1);
+  } else {
+    if (dinv)
+      gemv_n_kernel<1, true><<<nb, block, 0, lc.stream>>>(m, n, A, lda, dinv, w0, w0, t0, t0);
+    else
+      gemv_n_kernel<1, false><<<nb, block, 0, lc.stream>>>(m, n, A, lda, dinv, w0, w0, t0, t0);
+  }
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+// ------------------------------------------------------------------ K4: s = A^T v  (row chunks -> partials)
+constexpr int kGemvTThreads = 128;
+constexpr int kGemvTMaxRows = 1024;  // rows per chunk staged in smem (8 KB per rhs)
+constexpr int kGemvTMaxChunks = 64;
+
+template <int NRHS>
+__global__ void __launch_bounds__(kGemvTThreads)
+gemv_t_kernel(int64_t m, int64_t n, const double* __restrict__ A, int64_t lda, const double* __restrict__ v0,
+              const double* __restrict__ v1, double* __restrict__ partials, int64_t n_pad, int rows_per_chunk) {
+  __shared__ double sv[NRHS][kGemvTMaxRows];
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+  int64_t r1 = r0 + rows_per_chunk;
+  if (r1 > m) r1 = m;
+  const int nr = (int)(r1 - r0);
+  for (int i = threadIdx.x; i < nr; i += blockDim.x) {
+    sv[0][i] = v0[r0 + i];
+    if (NRHS == 2) sv[1][i] = v1[r0 + i];
+  }
+  __syncthreads();
+  const int64_t j2 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // double2 column index
+  const int64_t j = j2 * 2;
+  if (j >= n) return;
+  double ax0 = 0.0, ay0 = 0.0, ax1 = 0.0, ay1 = 0.0;
+  if (j + 1 < n) {
+    const double2* __restrict__ Ap = reinterpret_cast<const double2*>(A + r0 * lda) + j2;
+    const int64_t ld2 = lda >> 1;
+#pragma unroll 8
+    for (int i = 0; i < nr; ++i) {
+      const double2 a = __ldg(Ap + (int64_t)i * ld2);
+      const double s0 = sv[0][i];
+      ax0 += a.x * s0;
+      ay0 += a.y * s0;
+      if (NRHS == 2) {
+        const double s1 = sv[1][i];
+        ax1 += a.x * s1;
+        ay1 += a.y * s1;
+      }
+    }
+  } else {  // last odd column
+    const double* __restrict__ Ap = A + r0 * lda + j;
+    for (int i = 0; i < nr; ++i) {
+      const double a = __ldg(Ap + (int64_t)i * lda);
+      ax0 += a * sv[0][i];
+      if (NRHS == 2) ax1 += a * sv[1][i];
+    }
+  }
+  double* P0 = partials + ((size_t)blockIdx.y * NRHS + 0) * n_pad + j;
+  P0[0] = ax0;
+  P0[1] = ay0;  // n_pad is even, so j+1 < n_pad always
+  if (NRHS == 2) {
+    double* P1 = partials + ((size_t)blockIdx.y * NRHS + 1) * n_pad + j;
+    P1[0] = ax1;
+    P1[1] = ay1;
+  }
+}
+
+static inline void gemv_t_shape(int64_t m, int64_t n, int* nchunks, int* rows_per_chunk, int* colblocks) {
+  const int64_t cb = ceil_div(ceil_div(n, 2), kGemvTThreads);
+  int64_t want = ceil_div((int64_t)kNumSMs * 8, cb);  // ~8 CTAs of 128 threads per SM
+  if (want < 1) want = 1;
+  if (want > kGemvTMaxChunks) want = kGemvTMaxChunks;
+  int64_t rpc = ceil_div(m, want);
+  if (rpc < 8) rpc = 8;
+  if (rpc > kGemvTMaxRows) rpc = kGemvTMaxRows;
+  int64_t nc = ceil_div(m, rpc);
+  if (nc > kGemvTMaxChunks) {  // m very large: more chunks than the cap -> grow rows per chunk is impossible
+    nc = ceil_div(m, kGemvTMaxRows);
+    rpc = kGemvTMaxRows;
+  }
+  *nchunks = (int)nc;
+  *rows_per_chunk = (int)rpc;
+  *colblocks = (int)cb;
+}
+
+int64_t gemv_t_partials_doubles(int64_t m, int64_t n) {
+  int nc, rpc, cb;
+  gemv_t_shape(m, n, &nc, &rpc, &cb);
+  return (int64_t)nc * 2 * round_up(n, 2);
+}
+
+int k_gemv_t_partials(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* v0,
+                      const double* v1, int nrhs, int* nchunks) {
+  if ((lda & 1) || (reinterpret_cast<uintptr_t>(A) & 15)) {
+    set_last_error("gemv_t: A must be 16-byte aligned and lda even");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  int nc, rpc, cb;
+  gemv_t_shape(m, n, &nc, &rpc, &cb);
+  const int64_t n_pad = round_up(n, 2);
+  if ((int64_t)nc * nrhs * n_pad > lc.gemv_partials_cap) {
+    set_last_error("gemv_t: partials workspace too small (%lld > %lld)", (long long)((int64_t)nc * nrhs * n_pad),
+                   (long long)lc.gemv_partials_cap);
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  const dim3 grid(cb, nc);
+  if (nrhs == 2)
+    gemv_t_kernel<2><<<grid, kGemvTThreads, 0, lc.stream>>>(m, n, A, lda, v0, v1, lc.gemv_partials, n_pad, rpc);
+  else
+    gemv_t_kernel<1><<<grid, kGemvTThreads, 0, lc.stream>>>(m, n, A, lda, v0, v0, lc.gemv_partials, n_pad, rpc);
+  LPB_LAUNCH_CHECK(lc);
+  *nchunks = nc;
+  return LPB_OK;
+}
+
+__device__ __forceinline__ double sum_chunks(const double* __restrict__ partials, int nchunks, int nrhs, int k,
+                                             int64_t n_pad, int64_t j) {
+  double s = 0.0;
+  for (int c = 0; c < nchunks; ++c) s += partials[((size_t)c * nrhs + k) * n_pad + j];
+  return s;
+}
+
+__global__ void gemv_t_raw_kernel(int64_t n, int64_t n_pad, int nchunks, int nrhs,
+                                  const double* __restrict__ partials, double* __restrict__ out0,
+                                  double* __restrict__ out1) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    out0[j] = sum_chunks(partials, nchunks, nrhs, 0, n_pad, j);
+    if (nrhs == 2) out1[j] = sum_chunks(partials, nchunks, nrhs, 1, n_pad, j);
+  }
+}
+int k_gemv_t_raw(LaunchCtx& lc, int64_t n, int nchunks, int nrhs, double* out0, double* out1) {
+  gemv_t_raw_kernel<<<vec_blocks(n), kVecThreads, 0, lc.stream>>>(n, round_up(n, 2), nchunks, nrhs,
+                                                                  lc.gemv_partials, out0, out1);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+__global__ void resid_d_kernel(int64_t n, int64_t n_pad, int nchunks, double tau,
+                               const double* __restrict__ partials, const double* __restrict__ c,
+                               const double* __restrict__ z, const double* __restrict__ x, double* __restrict__ rD,
+                               double* __restrict__ red, int val_base) {
+  double v[3] = {0.0, 0.0, 0.0};
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const double s = sum_chunks(partials, nchunks, 1, 0, n_pad, j);
+    const double cj = c[j], zj = z[j], xj = x[j];
+    const double r = cj * tau - s - zj;  // feasible_point.rs:123 / residual.rs:24-26
+    rD[j] = r;
+    v[0] += r * r;
+    v[1] += cj * xj;
+    v[2] += xj * zj;
+  }
+  const int op[3] = {kRedSum, kRedSum, kRedSum};
+  block_reduce_store<3>(v, op, red, val_base);
+}
+int k_resid_d(LaunchCtx& lc, int64_t n, int nchunks, double tau, const double* c, const double* z, const double* x,
+              double* rD, int val_base, int* nblocks) {
+  const int nb = vec_blocks(n);
+  resid_d_kernel<<<nb, kVecThreads, 0, lc.stream>>>(n, round_up(n, 2), nchunks, tau, lc.gemv_partials, c, z, x, rD,
+                                                    lc.red_partials, val_base);
+  LPB_LAUNCH_CHECK(lc);
+  *nblocks = nb;
+  return LPB_OK;
+}
+
+__global__ void sym_back_kernel(int64_t n, int64_t n_pad, int nchunks, int with_pq,
+                                const double* __restrict__ partials, const double* __restrict__ dinv,
+                                const double* __restrict__ r1, const double* __restrict__ c, double* __restrict__ u,
+                                double* __restrict__ p, double* __restrict__ red, int val_base) {
+  double v[3] = {0.0, 0.0, 0.0};
+  const int nrhs = with_pq ? 2 : 1;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const double dj = dinv[j], cj = c[j];
+    const double s0 = sum_chunks(partials, nchunks, nrhs, 0, n_pad, j);
+    const double uj = dj * (s0 - r1[j]);  // newton_equations.rs:223
+    u[j] = uj;
+    v[0] += cj * uj;
+    if (with_pq) {
+      const double s1 = sum_chunks(partials, nchunks, nrhs, 1, n_pad, j);
+      const double pj = dj * (s1 - cj);
+      p[j] = pj;
+      v[1] += cj * pj;
+      v[2] += (pj != pj) ? 1.0 : 0.0;
+    }
+  }
+  const int op[3] = {kRedSum, kRedSum, kRedSum};
+  block_reduce_store<3>(v, op, red, val_base);
+}
+int k_sym_back(LaunchCtx& lc, int64_t n, int nchunks, int with_pq, const double* dinv, const double* r1,
+               const double* c, double* u, double* p, int val_base, int* nblocks) {
+  const int nb = vec_blocks(n);
+  sym_back_kernel<<<nb, kVecThreads, 0, lc.stream>>>(n, round_up(n, 2), nchunks, with_pq, lc.gemv_partials, dinv, r1,
+                                                     c, u, p, lc.red_partials, val_base);
+  LPB_LAUNCH_CHECK(lc);
+  *nblocks = nb;
+  return LPB_OK;
+}
+
+// ------------------------------------------------------------------ synthetic shard fill (multi-GPU config C5)
+// Counter-based generator: element (row, col) of the m x n0 Gaussian block depends only on
+// (seed, row, col), so any column sharding reproduces the same matrix.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ double counter_normal(uint64_t seed, uint64_t row, uint64_t col) {
+  const uint64_t k = splitmix64(seed ^ splitmix64(row * 0x100000001B3ull + 0x1234567ull) ^
+                                splitmix64(col + 0xABCDEF0123ull));
+  const uint64_t a = splitmix64(k), b = splitmix64(k ^ 0xD1B54A32D192ED03ull);
+  const double u1 = ((a >> 11) + 1.0) * (1.0 / 9007199254740993.0);  // (0,1]
+  const double u2 = (b >> 11) * (1.0 / 9007199254740992.0);          // [0,1)
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+__global__ void fill_normal_kernel(double* __restrict__ A, int64_t rows, int64_t cols, int64_t lda, int64_t row0,
+                                   int64_t col0, uint64_t seed) {
+  const int64_t total = rows * cols;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / cols, c = idx - r * cols;
+    A[r * lda + c] = counter_normal(seed, (uint64_t)(row0 + r), (uint64_t)(col0 + c));
+  }
+}
+int k_fill_normal(LaunchCtx& lc, double* A, int64_t rows, int64_t cols, int64_t lda, int64_t row0, int64_t col0,
+                  uint64_t seed) {
+  if (rows <= 0 || cols <= 0) return LPB_OK;
+  fill_normal_kernel<<<kNumSMs * 8, 256, 0, lc.stream>>>(A, rows, cols, lda, row0, col0, seed);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+}  // namespace lpb
