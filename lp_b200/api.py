@@ -328,8 +328,10 @@ class InteriorPoint(Solver):
         it = C.c_int64()
         rc = lib.lpb_solve(rp.handle, C.byref(self._o), x_slack.ctypes.data, C.byref(fun), C.byref(it))
         rp.last_iterations = it.value
+        if rc in (_ffi.LPB_OK, _ffi.LPB_ERR_ITERATION_LIMIT_EXCEEDED):
+            x_slack = rp.gather_x(x_slack)
         _raise_for(rc, x_slack)
-        x = np.array(x_slack[: n - rp.n_slack])  # denormalize_x_into, linear_program.rs:65-69
+        x = np.array(x_slack[: len(x_slack) - rp.n_slack])  # denormalize_x_into, linear_program.rs:65-69
         return OptimizeResult(x, fun.value, it.value)
 
 
@@ -348,6 +350,9 @@ class ResidentProblem:
         _raise_for(rc)
         self.handle = h
         self._problem = problem
+
+    def gather_x(self, x_local):
+        return x_local
 
     def reupload(self, problem: Problem):
         A = problem.A()
@@ -384,3 +389,75 @@ class ResidentProblem:
             self.close()
         except Exception:
             pass
+
+
+def shard_columns(n: int, world: int):
+    """Contiguous column blocks [col0, col0 + n_local) per rank (even widths keep 16-byte alignment)."""
+    per = -(-n // world)
+    per += per & 1
+    out = []
+    for r in range(world):
+        c0 = min(n, r * per)
+        out.append((c0, max(0, min(per, n - c0))))
+    return out
+
+
+class ShardedProblem(ResidentProblem):
+    """Column shard of a slack-form Problem on this rank's GPU (SURVEY.md 8e).  One process per GPU;
+    `dist` is torch.distributed (plumbing: it carries the ncclUniqueId and gathers x)."""
+
+    def __init__(self, problem: Problem, rank: int, world: int, dist, stream: int = 0):
+        lib = _ffi.load()
+        A = problem.A()
+        self.m, n_global = A.shape
+        self.n_global = n_global
+        self.n_slack = problem.n_slack()
+        self.rank, self.world, self._dist = rank, world, dist
+        self.shards = shard_columns(n_global, world)
+        self.col0, self.n = self.shards[rank]
+        if self.n <= 0:
+            raise ValueError("more ranks than column blocks")
+        self.last_iterations = 0
+        self._problem = problem
+        uid = self._broadcast_unique_id(lib)
+        h = C.c_void_p()
+        a_ptr = A.ctypes.data + 8 * self.col0
+        c_ptr = problem.c().ctypes.data + 8 * self.col0
+        rc = lib.lpb_create_sharded(C.byref(h), self.m, n_global, self.col0, self.n, a_ptr, n_global,
+                                    problem.b().ctypes.data, c_ptr, problem.c0(), _ffi.LPB_MEM_HOST, rank, world,
+                                    uid, C.c_void_p(stream))
+        _raise_for(rc)
+        self.handle = h
+
+    def _broadcast_unique_id(self, lib):
+        if self.world == 1:
+            return None
+        import torch
+        buf = (C.c_ubyte * 128)()
+        if self.rank == 0:
+            _raise_for(lib.lpb_nccl_unique_id(buf))
+        t = torch.tensor(list(buf), dtype=torch.uint8)
+        on_gpu = self._dist.get_backend() == "nccl"
+        if on_gpu:
+            t = t.cuda()
+        self._dist.broadcast(t, src=0)
+        data = bytes(t.cpu().tolist())
+        self._uid = (C.c_ubyte * 128).from_buffer_copy(data)
+        return C.cast(self._uid, C.c_void_p)
+
+    def gather_x(self, x_local):
+        if self.world == 1:
+            return x_local
+        import torch
+        per = max(nl for _, nl in self.shards)
+        t = torch.zeros(per, dtype=torch.float64)
+        t[: self.n] = torch.from_numpy(np.ascontiguousarray(x_local[: self.n]))
+        on_gpu = self._dist.get_backend() == "nccl"
+        if on_gpu:
+            t = t.cuda()
+        outs = [torch.zeros_like(t) for _ in range(self.world)]
+        self._dist.all_gather(outs, t)
+        return np.concatenate([o.cpu().numpy()[:nl] for o, (_, nl) in zip(outs, self.shards)])
+
+    def reupload(self, problem: Problem):
+        raise NotImplementedError

@@ -186,8 +186,11 @@ struct CudaDev {
 
   int form_and_factor() {  // newton_equations.rs:48-64
     {
-      PhaseTimer tm(c, PH_SYRK);
+      PhaseTimer tm(c, PH_VEC);
       LPB_TRY(k_dinv(c->lc, c->n, c->x, c->z, c->dinv));
+    }
+    {
+      PhaseTimer tm(c, PH_SYRK);
       if (c->syrk_impl == 1)
         LPB_TRY(k_syrk_simple(c->lc, c->m, c->n, c->A, c->lda, c->dinv, c->M, c->ldm));
       else

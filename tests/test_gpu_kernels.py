@@ -1,0 +1,116 @@
+"""Kernel-level parity on the B200, through the C ABI (lpb_k_*), against NumPy/LAPACK on the host.
+
+FP64 throughout; tolerances are relative to the magnitude of the exact result and stated per test.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from lp_b200 import _ffi
+from tests.gpu_util import BareCtx, ok, pad_cols, to_dev
+
+pytestmark = pytest.mark.gpu
+
+SYRK_SHAPES = [(8, 16), (100, 250), (128, 256), (129, 257), (300, 1000), (513, 1031), (1024, 2048)]
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("m,n", SYRK_SHAPES)
+@pytest.mark.parametrize("scaled", [True, False])
+def test_syrk_adat_matches_numpy(m, n, impl, scaled):
+    """K1 vs newton_equations.rs:54-57 computed with NumPy; rel. tol 1e-12 of |A| D |A|^T."""
+    rng = np.random.default_rng(m * 1000 + n)
+    A = rng.standard_normal((m, n))
+    d = np.exp(rng.uniform(-6, 6, n)) if scaled else None
+    Ap, lda = pad_cols(A)
+    ldm = (m + 15) // 16 * 16
+    dA = to_dev(Ap)
+    dd = to_dev(d) if scaled else None
+    import torch
+    dM = torch.full((m, ldm), float("nan"), dtype=torch.float64, device="cuda")
+    with BareCtx(m, n) as ctx:
+        ctx.set("syrk_impl", impl)
+        ok(ctx.lib.lpb_k_syrk_adat(ctx.h, m, n, dA.data_ptr(), lda, dd.data_ptr() if scaled else None,
+                                   dM.data_ptr(), ldm))
+    M = dM.cpu().numpy()[:, :m]
+    D = d if scaled else np.ones(n)
+    ref = (A * D) @ A.T
+    scale = (np.abs(A) * D) @ np.abs(A).T
+    low = np.tril_indices(m)
+    err = np.abs(M[low] - ref[low]) / scale[low]
+    assert np.isfinite(M[low]).all()
+    assert err.max() < 1e-12
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("m", [5, 64, 128, 129, 200, 384, 1000, 1536])
+def test_potrf_matches_lapack(m, impl):
+    """K2 vs numpy.linalg.cholesky (LAPACK potrf); ||L L^T - M|| / ||M|| < 1e-13 and L close to LAPACK's."""
+    rng = np.random.default_rng(m)
+    B = rng.standard_normal((m, m + 8))
+    M = B @ B.T + 0.1 * np.eye(m)
+    Mp, ldm = pad_cols(M)
+    dM = to_dev(Mp)
+    info = C.c_int32(-1)
+    with BareCtx(m, m) as ctx:
+        ctx.set("syrk_impl", impl)
+        ok(ctx.lib.lpb_k_potrf(ctx.h, m, dM.data_ptr(), ldm, C.byref(info)))
+    assert info.value == 0
+    L = np.tril(dM.cpu().numpy()[:, :m])
+    assert np.linalg.norm(L @ L.T - M) / np.linalg.norm(M) < 1e-13
+    Lref = np.linalg.cholesky(M)
+    assert np.abs(L - Lref).max() / np.abs(Lref).max() < 1e-10
+
+
+def test_potrf_reports_non_positive_pivot():
+    """newton_equations.rs:63: a failed factorisation must surface (info = first bad pivot + 1)."""
+    m = 300
+    rng = np.random.default_rng(7)
+    B = rng.standard_normal((m, m))
+    M = B @ B.T + np.eye(m)
+    M[200, 200] = -1.0
+    Mp, ldm = pad_cols(M)
+    dM = to_dev(Mp)
+    info = C.c_int32(0)
+    with BareCtx(m, m) as ctx:
+        ok(ctx.lib.lpb_k_potrf(ctx.h, m, dM.data_ptr(), ldm, C.byref(info)))
+    assert info.value == 201
+
+
+@pytest.mark.parametrize("nrhs", [1, 2])
+@pytest.mark.parametrize("m", [7, 128, 130, 500, 1536])
+def test_potrs_matches_lapack(m, nrhs):
+    """K3 vs scipy cho_solve; rel. error < 1e-10 on a well conditioned system."""
+    from scipy.linalg import cho_solve
+    rng = np.random.default_rng(m + nrhs)
+    Bm = rng.standard_normal((m, m + 8))
+    M = Bm @ Bm.T + m * np.eye(m)
+    L = np.linalg.cholesky(M)
+    Lp, ldm = pad_cols(L)
+    rhs = rng.standard_normal((nrhs, m))  # column-major m x nrhs == row-major nrhs x m
+    dL, dB = to_dev(Lp), to_dev(rhs)
+    with BareCtx(m, m) as ctx:
+        ok(ctx.lib.lpb_k_potrs(ctx.h, m, dL.data_ptr(), ldm, dB.data_ptr(), nrhs))
+    X = dB.cpu().numpy()
+    ref = cho_solve((L, True), rhs.T).T
+    assert np.abs(X - ref).max() / np.abs(ref).max() < 1e-10
+
+
+@pytest.mark.parametrize("m,n", [(3, 5), (64, 128), (100, 251), (512, 1024), (1000, 4097)])
+def test_gemv_sweeps_match_numpy(m, n):
+    """K4: A w and A^T v, rel. tol 1e-13 of |A||w|."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((m, n))
+    w = rng.standard_normal(n)
+    v = rng.standard_normal(m)
+    Ap, lda = pad_cols(A)
+    dA, dw, dv = to_dev(Ap), to_dev(w), to_dev(v)
+    import torch
+    o_n = torch.zeros(m, dtype=torch.float64, device="cuda")
+    o_t = torch.zeros(n, dtype=torch.float64, device="cuda")
+    with BareCtx(m, n) as ctx:
+        ok(ctx.lib.lpb_k_gemv_n(ctx.h, m, n, dA.data_ptr(), lda, dw.data_ptr(), o_n.data_ptr()))
+        ok(ctx.lib.lpb_k_gemv_t(ctx.h, m, n, dA.data_ptr(), lda, dv.data_ptr(), o_t.data_ptr()))
+    assert (np.abs(o_n.cpu().numpy() - A @ w) / (np.abs(A) @ np.abs(w))).max() < 1e-13
+    assert (np.abs(o_t.cpu().numpy() - A.T @ v) / (np.abs(A.T) @ np.abs(v))).max() < 1e-13

@@ -1,0 +1,184 @@
+"""Whole-solve parity on the B200 through the reference-shaped API (Problem / InteriorPoint) and the
+C ABI, against the CPU oracle.  Bar (BASELINE.json north_star): same termination status, iteration
+count within +-1, x within 1e-6 absolute, objective within 1e-8 relative."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import lp_b200
+from lp_b200 import _ffi
+from lp_b200.api import ResidentProblem
+from oracle import ipm_oracle as o
+from tests.golden_problems import GOLDEN, golden_arrays, symmetric_example
+
+pytestmark = pytest.mark.gpu
+
+
+def build(c, A_ub, b_ub, A_eq, b_eq):
+    b = lp_b200.Problem.target(c)
+    if A_ub is not None:
+        b = b.ub(A_ub, b_ub)
+    if A_eq is not None:
+        b = b.eq(A_eq, b_eq)
+    return b.build()
+
+
+def assert_parity(res, ref, x_tol=1e-6, f_tol=1e-8):
+    assert abs(res.iteration() - ref.iteration) <= 1
+    assert np.abs(res.x() - ref.x).max() <= x_tol
+    assert abs(res.fun() - ref.fun) <= f_tol * max(1.0, abs(ref.fun))
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN))
+def test_reference_known_answers(name):
+    """The reference's own unit tests / doctests (G1..G4), assert_abs_diff_eq!(x, expected, 1e-6)."""
+    c, A_ub, b_ub, A_eq, b_eq, x_ref, eps = golden_arrays(name)
+    res = lp_b200.InteriorPoint.default().solve(build(c, A_ub, b_ub, A_eq, b_eq))
+    assert np.abs(res.x() - x_ref).max() <= eps
+    ref = o.InteriorPoint().solve(o.build_problem(c, A_ub, b_ub, A_eq, b_eq))
+    assert res.iteration() == ref.iteration
+    assert_parity(res, ref)
+
+
+def test_symmetric_example_G5():
+    """examples/symmetric.rs: N=1000, x == 1 to 1e-10."""
+    c, A_ub, b_ub, _, _, x_ref, eps = symmetric_example(1000)
+    res = lp_b200.InteriorPoint.custom().disp(True).build().solve(build(c, A_ub, b_ub, None, None))
+    assert np.abs(res.x() - x_ref).max() <= eps
+    assert abs(res.fun() + 1000.0) < 1e-6
+    assert res.iteration() == 4
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("ip", [True, False])
+@pytest.mark.parametrize("m,n,seed", [(64, 128, 0), (64, 128, 3), (96, 200, 1), (130, 301, 2), (512, 1024, 0)])
+def test_synthetic_parity_with_oracle(m, n, seed, ip, impl):
+    """SURVEY 8(d) generator incl. config C1 (512x1024) and ragged sizes; per-iteration trace agrees."""
+    if (m % 2) or n <= m // 2:
+        pytest.skip("generator needs even m")
+    args = o.synthetic_lp(m, n, seed)
+    tr = []
+    ref = o.InteriorPoint(ip=ip).solve(o.build_problem(*args), trace=tr)
+    pb = build(*args)
+    solver = lp_b200.InteriorPoint.custom().ip(ip).build()
+    with ResidentProblem(pb) as rp:
+        rp.set_option("syrk_impl", impl)
+        res = solver.solve_resident(rp)
+        trace = rp.trace()
+        prof = rp.profile()
+    assert_parity(res, ref)
+    assert prof["launches"] > 0 and prof["iterations"] == res.iteration()
+    for k in range(min(4, len(tr), len(trace))):
+        r = tr[k]
+        want = [r["alpha"], r["rho_p"], r["rho_d"], r["rho_A"], r["rho_g"], r["rho_mu"], r["obj"], r["bty"],
+                r["tau"], r["kappa"]]
+        np.testing.assert_allclose(trace[k], want, rtol=1e-6, atol=1e-9)
+
+
+def test_status_paths():
+    """Infeasible / Unbounded / IterationLimitExceeded / InvalidParameter, vs the oracle's outcome."""
+    with pytest.raises(lp_b200.Infeasible):
+        lp_b200.InteriorPoint.default().solve(build([1.0, 1.0], [[1.0, 1.0]], [-1.0], None, None))
+    with pytest.raises(lp_b200.Unbounded):
+        lp_b200.InteriorPoint.default().solve(build([-1.0, 0.0], [[1.0, -1.0]], [1.0], None, None))
+    c, A_ub, b_ub, A_eq, b_eq, _, _ = golden_arrays("G1")
+    pb = build(c, A_ub, b_ub, A_eq, b_eq)
+    with pytest.raises(lp_b200.IterationLimitExceeded) as e:
+        lp_b200.InteriorPoint.custom().max_iter(1).build().solve(pb)
+    with pytest.raises(o.IterationLimitExceeded) as eo:
+        o.InteriorPoint(max_iter=1).solve(o.build_problem(c, A_ub, b_ub, A_eq, b_eq))
+    np.testing.assert_allclose(e.value.x, eo.value.x, rtol=1e-9, atol=1e-12)  # slack-form x/tau, mod.rs:237-239
+    with pytest.raises(lp_b200.InvalidParameter):
+        lp_b200.InteriorPoint.custom().solver_type(lp_b200.EquationSolverType.Inverse).build().solve(pb)
+
+
+def test_numerical_problem_on_singular_normal_matrix():
+    """Duplicated equality rows make M singular: pivot <= 0 -> NumericalProblem (newton_equations.rs:63)
+    whenever the oracle's scalar Cholesky says so."""
+    A_eq = np.array([[1.0, 2.0, 3.0], [1.0, 2.0, 3.0]])
+    try:
+        o.InteriorPoint(backend="scalar").solve(o.build_problem([1.0, 1.0, 1.0], A_eq=A_eq, b_eq=[1.0, 1.0]))
+        expect = None
+    except o.NumericalProblem:
+        expect = lp_b200.NumericalProblem
+    except o.LinearProgramError:
+        pytest.skip("oracle ends differently")
+    pb = build([1.0, 1.0, 1.0], None, None, A_eq, [1.0, 1.0])
+    if expect is None:
+        lp_b200.InteriorPoint.default().solve(pb)
+    else:
+        with pytest.raises(expect):
+            lp_b200.InteriorPoint.default().solve(pb)
+
+
+def test_host_driven_phase_calls_equal_lpb_solve():
+    """The exported phase calls (what the Rust shim would drive) reproduce lpb_solve exactly."""
+    lib = _ffi.load()
+    args = o.synthetic_lp(64, 128, 5)
+    pb = build(*args)
+    res = lp_b200.InteriorPoint.default().solve(pb)
+    with ResidentProblem(pb) as rp:
+        h = rp.handle
+        n = rp.n
+        tau = kappa = 1.0
+        assert lib.lpb_blind_start(h) == 0
+        rs = _ffi.lpb_residual_scalars()
+        assert lib.lpb_residuals(h, tau, kappa, C.byref(rs)) == 0
+        ini = (rs.nrm_rp, rs.nrm_rd, abs(kappa + rs.cx - rs.by), (rs.xz + tau * kappa) / (n + 1))
+        ip = True
+        it = 0
+        while True:
+            it += 1
+            gamma = 1.0 if ip else 0.0
+            eta = 1.0 if ip else 1.0 - gamma
+            r_G = rs.cx - rs.by + kappa
+            mu = (rs.xz + tau * kappa) / (n + 1)
+            assert lib.lpb_form_and_factor(h) == 0
+            din = _ffi.lpb_direction_in(0, int(ip), eta, gamma, mu, 0.0)
+            dout = _ffi.lpb_direction_out()
+            assert lib.lpb_direction(h, C.byref(din), tau, kappa, C.byref(dout)) == 0
+            tk = gamma * mu - tau * kappa
+
+            def dscal(g_hat, tk):
+                d_tau = (g_hat + 1.0 / tau * tk - (-dout.cu + dout.bv)) / (1.0 / tau * kappa + (-dout.cp + dout.bq))
+                return d_tau, 1.0 / tau * (tk - kappa * d_tau)
+
+            def step(axz, d_tau, d_kappa, a0):
+                at = min(1.0, tau / -d_tau) if d_tau < 0 else 1.0
+                ak = min(1.0, kappa / -d_kappa) if d_kappa < 0 else 1.0
+                return min(1.0, axz[0], at, axz[1], ak) * a0
+
+            d_tau, d_kappa = dscal(r_G * eta, tk)
+            axz = (C.c_double * 2)()
+            assert lib.lpb_assemble_delta(h, d_tau, axz) == 0
+            alpha = step(axz, d_tau, d_kappa, 1.0)
+            gamma = 10.0 if ip else (1 - alpha) ** 2 * min(0.1, 1 - alpha)
+            eta = 1.0 if ip else 1.0 - gamma
+            if ip:
+                tk = (1.0 - alpha) * gamma * mu - tau * kappa - alpha * alpha * d_tau * d_kappa
+            else:
+                tk = gamma * mu - tau * kappa - d_tau * d_kappa
+            din = _ffi.lpb_direction_in(1, int(ip), eta, gamma, mu, alpha)
+            assert lib.lpb_direction(h, C.byref(din), tau, kappa, C.byref(dout)) == 0
+            d_tau, d_kappa = dscal(r_G * eta, tk)
+            assert lib.lpb_assemble_delta(h, d_tau, axz) == 0
+            alpha = 1.0 if ip else step(axz, d_tau, d_kappa, 0.99995)
+            assert lib.lpb_do_step(h, alpha, int(ip)) == 0
+            tau, kappa = tau + d_tau * alpha, kappa + d_kappa * alpha
+            if ip:
+                tau, kappa = max(tau, 1.0), max(kappa, 1.0)
+            ip = False
+            assert lib.lpb_residuals(h, tau, kappa, C.byref(rs)) == 0
+            rho_p = rs.nrm_rp / max(ini[0], 1.0)
+            rho_d = rs.nrm_rd / max(ini[1], 1.0)
+            rho_A = abs(rs.cx - rs.by) / (tau + abs(rs.by))
+            if rho_p < 1e-8 and rho_d < 1e-8 and rho_A < 1e-8:
+                break
+            assert it < 50
+        x = np.zeros(n)
+        fun = C.c_double()
+        assert lib.lpb_extract_x(h, tau, x.ctypes.data, C.byref(fun)) == 0
+    assert it == res.iteration()
+    np.testing.assert_array_equal(x[: len(res.x())], res.x())
+    assert fun.value == res.fun()
