@@ -9,10 +9,12 @@
 //  * tcgen05.mma has no f64 kind; FP64 tensor math on Blackwell is the warp-level
 //    mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  Both operands of M[i,j] = sum_k A[i,k] d[k] A[j,k]
 //    are K-contiguous rows of row-major A, which is exactly the `.row.col` form.
-//  * One persistent CTA per SM walks the lower-triangular 128x128 tile list.  A dedicated producer
-//    warp streams 128x16 operand boxes (128-byte rows, SWIZZLE_128B) plus the 16 d[k] values of
-//    each K-block with cp.async.bulk.tensor into a 4-stage mbarrier ring; 8 consumer warps hold a
-//    64x32 accumulator slab each (64 doubles / thread) and issue 64 DMMAs per K-block.
+//  * One persistent CTA per SM walks the lower-triangular 128x128 tile list.  Lane 0 of warp 0
+//    streams 128x16 operand boxes (128-byte rows, SWIZZLE_128B) plus the 16 d[k] values of each
+//    K-block with cp.async.bulk.tensor into a 5-stage mbarrier ring, 3 K-blocks ahead of the math
+//    (a ninth, dedicated producer warp does not fit: the register file is 4 x 16K per sub-partition
+//    and each DMMA warp needs ~200 registers); 8 warps hold a 64x32 accumulator slab each
+//    (64 doubles / thread) and issue 64 DMMAs per K-block.
 //  * Fragments are read with conflict-free ld.shared.v2.f64: thread (g,t) of a warp fetches the
 //    16-byte chunk (2t+P)^g of row g, so a quarter-warp covers all 8 chunks of the 128-byte
 //    swizzle atom; the .x halves feed one DMMA k-group {4t+2P}, the .y halves the next {4t+2P+1}
@@ -27,9 +29,10 @@ namespace lpb {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int kStages = 4;
+constexpr int kStages = 5;
+constexpr int kLead = 3;  // TMA runs this many K-blocks ahead of the DMMA warps
 constexpr int kConsumerWarps = 8;
-constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kThreads = kConsumerWarps * 32;
 constexpr uint32_t kTileBytes = BM * BK * 8;  // 16 KB
 constexpr uint32_t kDBytes = BK * 8;          // 128 B
 constexpr uint32_t kSmemA = 0;
@@ -97,9 +100,17 @@ __device__ __forceinline__ void tri_decode(int L, int* ti, int* tj) {
   *tj = L - i * (i + 1) / 2;
 }
 
+// Producer cursor: walks this CTA's (tile, k-block) sequence `kLead` iterations ahead of the
+// consumers.  Lives in lane 0 of warp 0 (the register file is split 4 x 16K per SM sub-partition,
+// so a ninth warp would not fit next to eight 200-register DMMA warps).
+struct LoadCursor {
+  int L, kb, row_i, row_j, stage;
+  uint32_t phase;
+};
+
 // SCALE: multiply the B operand by d[k].  ACCUM: C -= A B^T (Cholesky trailing update) else C = A B^T.
 template <bool SCALE, bool ACCUM>
-__global__ void __maxnreg__(224)
+__global__ void __maxnreg__(255)
 syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
                  double* __restrict__ C, int64_t ldc, int m_total, int tile0, int ntr, int k_begin, int nkb) {
   extern __shared__ uint8_t smem_raw[];
@@ -118,36 +129,51 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
 
   const int ntiles = ntr * (ntr + 1) / 2;
-  int stage = 0;
-  uint32_t phase = 0;
+  const bool is_producer = threadIdx.x == 0;
+  constexpr uint32_t kBytes = 2 * kTileBytes + (SCALE ? kDBytes : 0);
 
-  if (warp == kConsumerWarps) {
-    // ------------------------------------------------------------ TMA producer (one lane)
-    if (lane == 0) {
-      const uint32_t bytes = 2 * kTileBytes + (SCALE ? kDBytes : 0);
-      for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
-        int ti, tj;
-        tri_decode(L, &ti, &tj);
-        const int row_i = (tile0 + ti) * BM, row_j = (tile0 + tj) * BN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(bar_empty + stage * 8, phase ^ 1u);
-          const uint32_t full = bar_full + stage * 8;
-          mbar_expect_tx(full, bytes);
-          const int k = k_begin + kb * BK;
-          tma_load_2d(sA + stage * kTileBytes, &tmA, k, row_i, full);
-          tma_load_2d(sB + stage * kTileBytes, &tmA, k, row_j, full);
-          if (SCALE) tma_load_2d(sD + stage * kDBytes, &tmD, k, 0, full);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
-      }
+  LoadCursor pc;
+  pc.L = blockIdx.x;
+  pc.kb = 0;
+  pc.stage = 0;
+  pc.phase = 0;
+  pc.row_i = pc.row_j = 0;
+  auto cursor_tile = [&]() {
+    if (pc.L < ntiles) {
+      int ti, tj;
+      tri_decode(pc.L, &ti, &tj);
+      pc.row_i = (tile0 + ti) * BM;
+      pc.row_j = (tile0 + tj) * BN;
     }
-    return;
+  };
+  // issue the TMA loads of the cursor's iteration (if any is left) and advance it
+  auto produce_one = [&]() {
+    if (pc.L >= ntiles) return;
+    mbar_wait(bar_empty + pc.stage * 8, pc.phase ^ 1u);
+    const uint32_t full = bar_full + pc.stage * 8;
+    mbar_expect_tx(full, kBytes);
+    const int k = k_begin + pc.kb * BK;
+    tma_load_2d(sA + pc.stage * kTileBytes, &tmA, k, pc.row_i, full);
+    tma_load_2d(sB + pc.stage * kTileBytes, &tmA, k, pc.row_j, full);
+    if (SCALE) tma_load_2d(sD + pc.stage * kDBytes, &tmD, k, 0, full);
+    if (++pc.stage == kStages) {
+      pc.stage = 0;
+      pc.phase ^= 1u;
+    }
+    if (++pc.kb == nkb) {
+      pc.kb = 0;
+      pc.L += gridDim.x;
+      cursor_tile();
+    }
+  };
+  if (is_producer) {
+    cursor_tile();
+    for (int i = 0; i < kLead; ++i) produce_one();
   }
 
-  // -------------------------------------------------------------- DMMA consumers
+  // -------------------------------------------------------------- DMMA consumers (all 8 warps)
+  int stage = 0;
+  uint32_t phase = 0;
   const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps -> 64 x 32 slab each
   const int g = lane >> 2, t = lane & 3;
   const uint32_t offA = static_cast<uint32_t>(wm * 64 + g) * 128u;
@@ -165,6 +191,9 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
     for (int kb = 0; kb < nkb; ++kb) {
+      // keep the ring kLead iterations ahead: the stage being refilled was released kStages - kLead
+      // iterations ago, so this wait does not normally stall
+      if (is_producer) produce_one();
       mbar_wait(bar_full + stage * 8, phase);
       const uint32_t a_base = sA + stage * kTileBytes + offA;
       const uint32_t b_base = sB + stage * kTileBytes + offB;

@@ -13,6 +13,12 @@
 
 #include "../../include/lpb200.h"
 
+#if defined(__CUDACC__)
+#define LPB_HD __host__ __device__
+#else
+#define LPB_HD
+#endif
+
 namespace lpb {
 
 struct Indicators {  // indicators.rs:8-23
@@ -22,8 +28,8 @@ struct Indicators {  // indicators.rs:8-23
 enum class Status { Optimal, Infeasible, Unbounded, Unfinished };  // indicators.rs:85-90
 
 // indicators.rs:66-83.  All comparisons are `<` / `>` so NaN indicators give Unfinished.
-inline Status indicators_status(const Indicators& i, double tau, double kappa, double tol) {
-  const bool tau_too_small = tau < tol * std::fmax(kappa, 1.0);
+LPB_HD inline Status indicators_status(const Indicators& i, double tau, double kappa, double tol) {
+  const bool tau_too_small = tau < tol * fmax(kappa, 1.0);
   const bool inf1 = (i.rho_p < tol && i.rho_d < tol && i.rho_g < tol) && tau_too_small;
   const bool inf2 = i.rho_mu < tol && tau_too_small;
   if (inf1 || inf2) return i.bty > tol ? Status::Infeasible : Status::Unbounded;
@@ -36,35 +42,35 @@ struct InitialResiduals {  // residual.rs:5-10 evaluated at the blind start
 };
 
 // residual.rs:13-44 from the reduction scalars of one residual sweep.
-inline void residual_values(const lpb_residual_scalars& rs, double tau, double kappa, int64_t n_total,
+LPB_HD inline void residual_values(const lpb_residual_scalars& rs, double tau, double kappa, int64_t n_total,
                             double* rho_p, double* rho_d, double* rho_g, double* rho_mu) {
   *rho_p = rs.nrm_rp;
   *rho_d = rs.nrm_rd;
-  *rho_g = std::fabs(kappa + rs.cx - rs.by);
+  *rho_g = fabs(kappa + rs.cx - rs.by);
   *rho_mu = (rs.xz + tau * kappa) / static_cast<double>(n_total + 1);
 }
 
 // indicators.rs:37-55.
-inline Indicators make_indicators(const lpb_residual_scalars& rs, const InitialResiduals& ini, double tau,
+LPB_HD inline Indicators make_indicators(const lpb_residual_scalars& rs, const InitialResiduals& ini, double tau,
                                   double kappa, int64_t n_total, double c0) {
   Indicators out;
   double rp, rd, rg, rmu;
   residual_values(rs, tau, kappa, n_total, &rp, &rd, &rg, &rmu);
   out.obj = rs.cx / tau + c0;  // c.(x/tau) + c0 (display only)
   out.bty = rs.by;
-  out.rho_A = std::fabs(rs.cx - rs.by) / (tau + std::fabs(rs.by));
-  out.rho_p = rp / std::fmax(ini.rho_p, 1.0);
-  out.rho_d = rd / std::fmax(ini.rho_d, 1.0);
-  out.rho_g = rg / std::fmax(ini.rho_g, 1.0);
+  out.rho_A = fabs(rs.cx - rs.by) / (tau + fabs(rs.by));
+  out.rho_p = rp / fmax(ini.rho_p, 1.0);
+  out.rho_d = rd / fmax(ini.rho_d, 1.0);
+  out.rho_g = rg / fmax(ini.rho_g, 1.0);
   out.rho_mu = rmu / ini.rho_mu;
   return out;
 }
 
 // Rust's f64::min: NaN-ignoring, like fmin.
-inline double rmin(double a, double b) { return std::fmin(a, b); }
+LPB_HD inline double rmin(double a, double b) { return fmin(a, b); }
 
 // feasible_point.rs:53-72; alpha_x / alpha_z come from the device ratio test (already min'ed with 1).
-inline double step_size(double alpha_x, double alpha_z, double tau, double d_tau, double kappa, double d_kappa,
+LPB_HD inline double step_size(double alpha_x, double alpha_z, double tau, double d_tau, double kappa, double d_kappa,
                         double alpha0) {
   const double alpha_tau = d_tau < 0.0 ? rmin(1.0, tau / -d_tau) : 1.0;
   const double alpha_kappa = d_kappa < 0.0 ? rmin(1.0, kappa / -d_kappa) : 1.0;
@@ -72,7 +78,7 @@ inline double step_size(double alpha_x, double alpha_z, double tau, double d_tau
 }
 
 // feasible_point.rs:155-165.
-inline double update_gamma(bool ip, double alpha) {
+LPB_HD inline double update_gamma(bool ip, double alpha) {
   if (ip) return 10.0;
   const double beta1 = 0.1;
   const double one_m = 1.0 - alpha;
@@ -83,19 +89,44 @@ struct TraceRow {
   double v[LPB_TRACE_COLS];
 };
 
+// Plain-scalar result of the loop (usable from device code).
+struct SolveScalars {
+  int64_t iterations;
+  double tau, kappa;
+};
+
 struct SolveOutput {
   int64_t iterations = 0;
   double tau = 1.0, kappa = 1.0;
   std::vector<TraceRow> trace;
 };
 
-inline void print_indicators(double alpha, const Indicators& i) {
-  // mod.rs:228 "{alpha:3.8}\t{indicators}", indicators.rs:25-33
-  std::printf("%.8f\t%.8f\t%.8f\t%.8f\t%.8f\t%8.3f\n", alpha, i.rho_p, i.rho_d, i.rho_g, i.rho_mu, i.obj);
-}
+// Host recorder: `disp` printing (mod.rs:208-211, :227-229; indicators.rs:25-33) + per-iteration trace.
+struct HostRecorder {
+  bool disp;
+  std::vector<TraceRow>* trace;
+  void start(const Indicators& i) {
+    if (!disp) return;
+    std::printf("alpha     \trho_p     \trho_d     \trho_g     \trho_mu    \tobj       \n");
+    std::printf("1.00000000\t%.8f\t%.8f\t%.8f\t%.8f\t%8.3f\n", i.rho_p, i.rho_d, i.rho_g, i.rho_mu, i.obj);
+  }
+  void iteration(double alpha, const Indicators& i, double tau, double kappa) {
+    if (disp) std::printf("%.8f\t%.8f\t%.8f\t%.8f\t%.8f\t%8.3f\n", alpha, i.rho_p, i.rho_d, i.rho_g, i.rho_mu, i.obj);
+    if (trace) {
+      TraceRow row = {{alpha, i.rho_p, i.rho_d, i.rho_A, i.rho_g, i.rho_mu, i.obj, i.bty, tau, kappa}};
+      trace->push_back(row);
+    }
+  }
+};
+
+// Device recorder (batched kernel): nothing to record.
+struct NullRecorder {
+  LPB_HD void start(const Indicators&) {}
+  LPB_HD void iteration(double, const Indicators&, double, double) {}
+};
 
 // One Delta::compute worth of host scalars (delta.rs:29-32, :38).
-inline void delta_scalars(double g_hat, double tk_hat, double tau, double kappa, const lpb_direction_out& d,
+LPB_HD inline void delta_scalars(double g_hat, double tk_hat, double tau, double kappa, const lpb_direction_out& d,
                           double* d_tau, double* d_kappa) {
   *d_tau = (g_hat + 1.0 / tau * tk_hat - (-d.cu + d.bv)) / (1.0 / tau * kappa + (-d.cp + d.bq));
   *d_kappa = 1.0 / tau * (tk_hat - kappa * *d_tau);
@@ -108,12 +139,14 @@ inline void delta_scalars(double g_hat, double tk_hat, double tau, double kappa,
 //   blind_start(); residuals(tau, kappa, lpb_residual_scalars*); form_and_factor();
 //   direction(const lpb_direction_in&, tau, kappa, lpb_direction_out*);
 //   assemble_delta(d_tau, double alpha_xz[2]); do_step(alpha, ip);
-template <class Dev>
-int solve_normal_form(Dev& dev, const lpb_options& o, int64_t n_total, double c0, SolveOutput* out) {
+template <class Dev, class Rec>
+LPB_HD int solve_normal_form_rec(Dev& dev, const lpb_options& o, int64_t n_total, double c0, SolveScalars* out,
+                                 Rec& rec) {
   int rc;
   double tau = 1.0, kappa = 1.0;  // feasible_point.rs:29-30
-  out->trace.clear();
   out->iterations = 0;
+  out->tau = tau;
+  out->kappa = kappa;
   if ((rc = dev.blind_start()) != LPB_OK) return rc;
 
   lpb_residual_scalars rs;
@@ -122,11 +155,7 @@ int solve_normal_form(Dev& dev, const lpb_options& o, int64_t n_total, double c0
   residual_values(rs, tau, kappa, n_total, &ini.rho_p, &ini.rho_d, &ini.rho_g, &ini.rho_mu);
 
   Indicators ind = make_indicators(rs, ini, tau, kappa, n_total, c0);  // mod.rs:206
-  if (o.disp) {  // mod.rs:208-211
-    std::printf("alpha     \trho_p     \trho_d     \trho_g     \trho_mu    \tobj       \n");
-    std::printf("1.00000000\t%.8f\t%.8f\t%.8f\t%.8f\t%8.3f\n", ind.rho_p, ind.rho_d, ind.rho_g, ind.rho_mu,
-                ind.obj);
-  }
+  rec.start(ind);
 
   bool ip = o.ip != 0;
   for (int64_t iteration = 1; iteration <= o.max_iter; ++iteration) {  // mod.rs:213
@@ -183,17 +212,15 @@ int solve_normal_form(Dev& dev, const lpb_options& o, int64_t n_total, double c0
     tau = tau + d_tau * alpha;       // feasible_point.rs:80
     kappa = kappa + d_kappa * alpha; // :81
     if (ip) {                        // :92-93
-      tau = std::fmax(tau, 1.0);
-      kappa = std::fmax(kappa, 1.0);
+      tau = fmax(tau, 1.0);
+      kappa = fmax(kappa, 1.0);
     }
     ip = false;
 
     // ---- indicators (mod.rs:225-235)
     if ((rc = dev.residuals(tau, kappa, &rs)) != LPB_OK) return rc;
     ind = make_indicators(rs, ini, tau, kappa, n_total, c0);
-    if (o.disp) print_indicators(alpha, ind);
-    TraceRow row = {{alpha, ind.rho_p, ind.rho_d, ind.rho_A, ind.rho_g, ind.rho_mu, ind.obj, ind.bty, tau, kappa}};
-    out->trace.push_back(row);
+    rec.iteration(alpha, ind, tau, kappa);
     out->iterations = iteration;
     out->tau = tau;
     out->kappa = kappa;
@@ -209,8 +236,21 @@ int solve_normal_form(Dev& dev, const lpb_options& o, int64_t n_total, double c0
   return LPB_ERR_ITERATION_LIMIT_EXCEEDED;  // mod.rs:237-239
 }
 
+// Host form: records the trace into `out` and honours `disp`.
+template <class Dev>
+int solve_normal_form(Dev& dev, const lpb_options& o, int64_t n_total, double c0, SolveOutput* out) {
+  out->trace.clear();
+  HostRecorder rec{o.disp != 0, &out->trace};
+  SolveScalars sc;
+  const int rc = solve_normal_form_rec(dev, o, n_total, c0, &sc, rec);
+  out->iterations = sc.iterations;
+  out->tau = sc.tau;
+  out->kappa = sc.kappa;
+  return rc;
+}
+
 // InteriorPointBuilder::new / build (mod.rs:51-60, :118-128)
-inline void options_default(lpb_options* o) {
+LPB_HD inline void options_default(lpb_options* o) {
   o->tol = 1e-8;
   o->disp = 0;
   o->ip = 1;
@@ -220,7 +260,7 @@ inline void options_default(lpb_options* o) {
   o->max_iter = 1000;
 }
 
-inline int options_validate(const lpb_options* o) {
+LPB_HD inline int options_validate(const lpb_options* o) {
   if (!o) return LPB_ERR_BAD_ARGUMENT;
   if (o->alpha0 <= 0.0 || o->alpha0 >= 1.0) return LPB_ERR_INVALID_PARAMETER;
   if (o->tol <= 0.0) return LPB_ERR_INVALID_PARAMETER;
