@@ -6,6 +6,10 @@ Importing this package never touches CUDA; the first compute call loads liblpb20
 (``lp_b200/_lib``) and fails loudly if it was not built or no B200 is visible.
 """
 from .api import (  # noqa: F401
+    BatchedResult,
+    ResidentProblem,
+    ShardedProblem,
+    solve_batched,
     EquationSolverType,
     IncompatibleInputDimensions,
     Infeasible,
@@ -24,6 +28,7 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
+    "BatchedResult", "ResidentProblem", "ShardedProblem", "solve_batched",
     "EquationSolverType", "IncompatibleInputDimensions", "Infeasible", "InteriorPoint", "InteriorPointBuilder",
     "InvalidParameter", "IterationLimitExceeded", "LinearProgramError", "NumericalProblem", "OptimizeResult",
     "Problem", "ProblemBuilder", "Solver", "Unbounded", "Unconstrained",

@@ -391,6 +391,36 @@ class ResidentProblem:
             pass
 
 
+class BatchedResult:
+    """Outcome of `solve_batched`: per-problem x (user variables only), fun, iteration and status code
+    (0 = Optimal, else the LPB_ERR_* code of the LinearProgramError variant)."""
+
+    def __init__(self, x, x_slack, fun, iteration, status):
+        self.x, self.x_slack, self.fun, self.iteration, self.status = x, x_slack, fun, iteration, status
+
+
+def solve_batched(A, b, c, n_slack: int = 0, solver: Optional["InteriorPoint"] = None, stream: int = 0):
+    """Solve `batch` independent slack-form LPs (A: batch x m x n, b: batch x m, c: batch x n) with one
+    CTA per problem (the whole solve_normal_form loop on device).  Host arrays in, host arrays out."""
+    lib = _ffi.load()
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    if A.ndim != 3 or b.shape != A.shape[:2] or c.shape != (A.shape[0], A.shape[2]):
+        raise IncompatibleInputDimensions()
+    batch, m, n = A.shape
+    solver = solver or InteriorPoint.default()
+    x = np.zeros((batch, n))
+    fun = np.zeros(batch)
+    it = np.zeros(batch, dtype=np.int64)
+    st = np.zeros(batch, dtype=np.int32)
+    rc = lib.lpb_solve_batched(batch, m, n, A.ctypes.data, b.ctypes.data, c.ctypes.data, C.byref(solver._o),
+                               x.ctypes.data, fun.ctypes.data, it.ctypes.data, st.ctypes.data, _ffi.LPB_MEM_HOST,
+                               C.c_void_p(stream))
+    _raise_for(rc)
+    return BatchedResult(x[:, : n - n_slack].copy(), x, fun, it, st)
+
+
 def shard_columns(n: int, world: int):
     """Contiguous column blocks [col0, col0 + n_local) per rank (even widths keep 16-byte alignment)."""
     per = -(-n // world)

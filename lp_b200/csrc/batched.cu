@@ -1,0 +1,438 @@
+// batched.cu -- K6: many small independent LPs, one CTA per problem, the whole
+// solve_normal_form loop (interior_point/mod.rs:199-240) on the device.
+//
+// The CTA keeps A (m x n), M / L (m x m) and every iterate vector in shared memory and runs the
+// SAME driver template as the single-problem path (ipm_driver.hpp: solve_normal_form_rec), here
+// instantiated on `SmemDev`, whose phase calls are block-cooperative device functions.  All 256
+// threads execute the scalar logic redundantly on block-broadcast reduction results, so control
+// flow is uniform and the statuses / iteration counts follow the reference exactly like the
+// large-problem path does.  Problems are independent: sharding a batch over GPUs needs no collective.
+#include "ipm_driver.hpp"
+#include "kernels.hpp"
+
+namespace lpb {
+namespace {
+
+constexpr int kBT = 256;       // threads per CTA
+constexpr int kBWarps = kBT / 32;
+constexpr int kMaxM = 64;      // register-tiled SYRK covers 64 x 64
+
+__device__ __forceinline__ double bw_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double bw_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block all-reduce of NV values; every thread returns with the folded results (fixed order).
+template <int NV>
+__device__ __forceinline__ void block_allreduce(double (&v)[NV], const bool is_min, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double r = is_min ? bw_min(v[k]) : bw_sum(v[k]);
+    if (lane == 0) red[k * kBWarps + warp] = r;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double r = red[k * kBWarps];
+#pragma unroll
+    for (int w = 1; w < kBWarps; ++w) r = is_min ? fmin(r, red[k * kBWarps + w]) : r + red[k * kBWarps + w];
+    v[k] = r;
+  }
+  __syncthreads();
+}
+
+struct SmemDev {
+  int m, n, lda, ldm;
+  double *A, *M, *diag, *b, *c, *x, *y, *z, *rP, *rD, *dinv, *xs, *r1, *p, *q, *u, *v, *dx, *dy, *dz, *t0, *t1, *sx,
+      *red;
+  int have_pq, nan_pq;
+  double cp, bq;
+
+  // t_k[i] = sum_j A[i][j] * (w_k[j] * (scale ? dinv[j] : 1)); warp per row
+  template <int NRHS, bool SCALE>
+  __device__ __forceinline__ void rows_dot(const double* w0, const double* w1, double* o0, double* o1) const {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = warp; i < m; i += kBWarps) {
+      const double* ar = A + i * lda;
+      double s0 = 0.0, s1 = 0.0;
+      for (int j = lane; j < n; j += 32) {
+        const double a = ar[j];
+        const double d = SCALE ? dinv[j] : 1.0;
+        s0 += a * (SCALE ? d * w0[j] : w0[j]);
+        if (NRHS == 2) s1 += a * (SCALE ? d * w1[j] : w1[j]);
+      }
+      s0 = bw_sum(s0);
+      if (NRHS == 2) s1 = bw_sum(s1);
+      if (lane == 0) {
+        o0[i] = s0;
+        if (NRHS == 2) o1[i] = s1;
+      }
+    }
+  }
+
+  // s_k[j] = sum_i A[i][j] v_k[i]; thread per column
+  template <int NRHS>
+  __device__ __forceinline__ void col_dot(int j, const double* v0, const double* v1, double* s0, double* s1) const {
+    double a0 = 0.0, a1 = 0.0;
+    for (int i = 0; i < m; ++i) {
+      const double a = A[i * lda + j];
+      a0 += a * v0[i];
+      if (NRHS == 2) a1 += a * v1[i];
+    }
+    *s0 = a0;
+    if (NRHS == 2) *s1 = a1;
+  }
+
+  __device__ int blind_start() {  // feasible_point.rs:24-39
+    for (int j = threadIdx.x; j < n; j += kBT) {
+      x[j] = 1.0;
+      z[j] = 1.0;
+    }
+    for (int i = threadIdx.x; i < m; i += kBT) y[i] = 0.0;
+    have_pq = 0;
+    __syncthreads();
+    return LPB_OK;
+  }
+
+  __device__ int residuals(double tau, double kappa, lpb_residual_scalars* o) {
+    (void)kappa;
+    rows_dot<1, false>(x, nullptr, t0, nullptr);
+    double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int j = threadIdx.x; j < n; j += kBT) {
+      double s, unused;
+      col_dot<1>(j, y, nullptr, &s, &unused);
+      const double cj = c[j], zj = z[j], xj = x[j];
+      const double rd = cj * tau - s - zj;  // feasible_point.rs:123
+      rD[j] = rd;
+      r[0] += rd * rd;
+      r[1] += cj * xj;
+      r[2] += xj * zj;
+    }
+    __syncthreads();  // t0 complete
+    for (int i = threadIdx.x; i < m; i += kBT) {
+      const double bi = b[i];
+      const double rp = bi * tau - t0[i];  // feasible_point.rs:122
+      rP[i] = rp;
+      r[3] += rp * rp;
+      r[4] += bi * y[i];
+    }
+    block_allreduce<5>(r, false, red);
+    o->nrm_rd = sqrt(r[0]);
+    o->cx = r[1];
+    o->xz = r[2];
+    o->nrm_rp = sqrt(r[3]);
+    o->by = r[4];
+    return LPB_OK;
+  }
+
+  __device__ int form_and_factor() {  // newton_equations.rs:48-64
+    for (int j = threadIdx.x; j < n; j += kBT) dinv[j] = x[j] / z[j];
+    __syncthreads();
+    {  // M = A diag(dinv) A^T : 4x4 strided register tile per thread (rows ty+16i, cols tx+16j)
+      const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+      double acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+      const double* ar[4];
+      const double* br[4];
+      bool av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        av[i] = ty + 16 * i < m;
+        bv[i] = tx + 16 * i < m;
+        ar[i] = A + (av[i] ? ty + 16 * i : 0) * lda;
+        br[i] = A + (bv[i] ? tx + 16 * i : 0) * lda;
+      }
+      for (int k = 0; k < n; ++k) {
+        const double d = dinv[k];
+        double a[4], bb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a[i] = ar[i][k];
+          bb[i] = br[i][k] * d;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * bb[j];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (av[i] && bv[j]) M[(ty + 16 * i) * ldm + tx + 16 * j] = acc[i][j];
+    }
+    __syncthreads();
+    // in-place lower Cholesky (right-looking), pivot <= 0 or non-finite -> NumericalProblem (:63)
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = 0; j < m; ++j) {
+      const double ajj = M[j * ldm + j];
+      if (!(ajj > 0.0) || !isfinite(ajj)) return LPB_ERR_NUMERICAL_PROBLEM;  // uniform across the CTA
+      const double d = sqrt(ajj);
+      if (threadIdx.x == 0) diag[j] = d;
+      for (int i = j + 1 + threadIdx.x; i < m; i += kBT) M[i * ldm + j] /= d;
+      __syncthreads();
+      for (int i = j + 1 + ty; i < m; i += kBWarps) {
+        const double lij = M[i * ldm + j];
+        for (int k = j + 1 + tx; k <= i; k += 32) M[i * ldm + k] -= lij * M[k * ldm + j];
+      }
+      __syncthreads();
+    }
+    for (int j = threadIdx.x; j < m; j += kBT) M[j * ldm + j] = diag[j];
+    have_pq = 0;
+    __syncthreads();
+    return LPB_OK;
+  }
+
+  // solve L L^T w = rhs in place for NRHS vectors (r0, r1v); thread i owns row i
+  template <int NRHS>
+  __device__ __forceinline__ void chol_solve(double* r0, double* r1v) {
+    const int i = threadIdx.x;
+    double b0 = 0.0, b1 = 0.0;
+    if (i < m) {
+      b0 = r0[i];
+      if (NRHS == 2) b1 = r1v[i];
+    }
+    for (int l = 0; l < m; ++l) {
+      if (i == l) {
+        const double dl = M[l * ldm + l];
+        sx[l] = b0 = b0 / dl;
+        if (NRHS == 2) sx[kMaxM + l] = b1 = b1 / dl;
+      }
+      __syncthreads();
+      if (i > l && i < m) {
+        const double lil = M[i * ldm + l];
+        b0 -= sx[l] * lil;
+        if (NRHS == 2) b1 -= sx[kMaxM + l] * lil;
+      }
+    }
+    __syncthreads();
+    for (int l = m - 1; l >= 0; --l) {
+      if (i == l) {
+        const double dl = M[l * ldm + l];
+        sx[l] = b0 = b0 / dl;
+        if (NRHS == 2) sx[kMaxM + l] = b1 = b1 / dl;
+      }
+      __syncthreads();
+      if (i < l) {
+        const double lli = M[l * ldm + i];
+        b0 -= sx[l] * lli;
+        if (NRHS == 2) b1 -= sx[kMaxM + l] * lli;
+      }
+    }
+    if (i < m) {
+      r0[i] = b0;
+      if (NRHS == 2) r1v[i] = b1;
+    }
+    __syncthreads();
+  }
+
+  __device__ int direction(const lpb_direction_in& in, double tau, double kappa, lpb_direction_out* o) {
+    (void)tau;
+    (void)kappa;
+    const int with_pq = have_pq ? 0 : 1;
+    const double gm = in.gamma * in.mu;
+    const double a2 = in.alpha * in.alpha;
+    const double s = (1.0 - in.alpha) * in.gamma * in.mu;
+    for (int j = threadIdx.x; j < n; j += kBT) {
+      const double xj = x[j];
+      const double mxz = (xj * -1.0) * z[j];
+      double val;
+      if (!in.corrector)
+        val = mxz + gm;                          // rhat.rs:32
+      else if (in.ip)
+        val = mxz - (dx[j] * dz[j]) * a2 + s;    // rhat.rs:54-55
+      else
+        val = mxz + gm - (dx[j] * dz[j]);        // rhat.rs:64
+      xs[j] = val;
+      r1[j] = rD[j] * in.eta - val / xj;         // newton_equations.rs:188
+    }
+    __syncthreads();
+    if (with_pq)
+      rows_dot<2, true>(r1, c, t0, t1);
+    else
+      rows_dot<1, true>(r1, nullptr, t0, nullptr);
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += kBT) {
+      v[i] = rP[i] * in.eta + t0[i];             // newton_equations.rs:220
+      if (with_pq) q[i] = b[i] + t1[i];
+    }
+    __syncthreads();
+    if (with_pq)
+      chol_solve<2>(v, q);
+    else
+      chol_solve<1>(v, nullptr);
+    double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int j = threadIdx.x; j < n; j += kBT) {
+      double s0, s1 = 0.0;
+      if (with_pq)
+        col_dot<2>(j, v, q, &s0, &s1);
+      else
+        col_dot<1>(j, v, nullptr, &s0, &s1);
+      const double dj = dinv[j], cj = c[j];
+      const double uj = dj * (s0 - r1[j]);       // newton_equations.rs:223
+      u[j] = uj;
+      r[0] += cj * uj;
+      if (with_pq) {
+        const double pj = dj * (s1 - cj);
+        p[j] = pj;
+        r[1] += cj * pj;
+        r[2] += (pj != pj) ? 1.0 : 0.0;
+      }
+    }
+    for (int i = threadIdx.x; i < m; i += kBT) {
+      const double bi = b[i];
+      r[3] += bi * v[i];
+      if (with_pq) {
+        const double qi = q[i];
+        r[4] += bi * qi;
+        r[5] += (qi != qi) ? 1.0 : 0.0;
+      }
+    }
+    block_allreduce<6>(r, false, red);
+    if (with_pq) {
+      cp = r[1];
+      bq = r[4];
+      nan_pq = (r[2] > 0.0 || r[5] > 0.0) ? 1 : 0;
+      have_pq = 1;
+    }
+    o->cu = r[0];
+    o->bv = r[3];
+    o->cp = cp;
+    o->bq = bq;
+    o->nan_pq = nan_pq;
+    o->reserved = 0;
+    return LPB_OK;
+  }
+
+  __device__ int assemble_delta(double d_tau, double axz[2]) {
+    double r[2] = {1.0, 1.0};
+    for (int j = threadIdx.x; j < n; j += kBT) {
+      const double xj = x[j], zj = z[j];
+      const double dxj = u[j] + p[j] * d_tau;        // delta.rs:33
+      const double dzj = (xs[j] - zj * dxj) / xj;    // delta.rs:37
+      dx[j] = dxj;
+      dz[j] = dzj;
+      if (dxj < 0.0) r[0] = fmin(r[0], xj / -dxj);   // feasible_point.rs:61
+      if (dzj < 0.0) r[1] = fmin(r[1], zj / -dzj);   // :62
+    }
+    for (int i = threadIdx.x; i < m; i += kBT) dy[i] = v[i] + q[i] * d_tau;  // delta.rs:34
+    block_allreduce<2>(r, true, red);
+    axz[0] = r[0];
+    axz[1] = r[1];
+    return LPB_OK;
+  }
+
+  __device__ int do_step(double alpha, int ip) {  // feasible_point.rs:76-106
+    for (int j = threadIdx.x; j < n; j += kBT) {
+      double xv = x[j] + dx[j] * alpha, zv = z[j] + dz[j] * alpha;
+      if (ip) {
+        xv = fmax(xv, 1.0);
+        zv = fmax(zv, 1.0);
+      }
+      x[j] = xv;
+      z[j] = zv;
+    }
+    for (int i = threadIdx.x; i < m; i += kBT) y[i] = y[i] + dy[i] * alpha;
+    __syncthreads();
+    return LPB_OK;
+  }
+};
+
+__host__ __device__ inline size_t batched_smem_doubles(int m, int n) {
+  return (size_t)m * (n + 1) + (size_t)m * (m + 1) + 10 * (size_t)n + 7 * (size_t)m + 2 * kMaxM + 8 * kBWarps;
+}
+
+__global__ void __launch_bounds__(kBT)
+batched_ipm_kernel(int64_t batch, int m, int n, const double* __restrict__ gA, const double* __restrict__ gb,
+                   const double* __restrict__ gc, lpb_options opts, double* __restrict__ x_out,
+                   double* __restrict__ fun_out, int64_t* __restrict__ it_out, int32_t* __restrict__ st_out) {
+  extern __shared__ double sm[];
+  for (int64_t lp = blockIdx.x; lp < batch; lp += gridDim.x) {
+    SmemDev d;
+    d.m = m;
+    d.n = n;
+    d.lda = n + 1;
+    d.ldm = m + 1;
+    double* ptr = sm;
+    auto take = [&](size_t cnt) {
+      double* r = ptr;
+      ptr += cnt;
+      return r;
+    };
+    d.A = take((size_t)m * d.lda);
+    d.M = take((size_t)m * d.ldm);
+    d.c = take(n); d.x = take(n); d.z = take(n); d.rD = take(n); d.dinv = take(n); d.xs = take(n);
+    d.r1 = take(n); d.p = take(n); d.dx = take(n); d.dz = take(n);
+    d.u = d.r1;        // u[j] = dinv[j] * (s - r1[j]) overwrites r1[j] in place (r1 is dead afterwards)
+    d.b = take(m); d.y = take(m); d.rP = take(m); d.q = take(m); d.v = take(m); d.dy = take(m);
+    d.t0 = take(m);
+    d.t1 = d.dy;       // t1 is consumed (q = b + t1) before d_y is written
+    d.sx = take(2 * kMaxM);
+    d.diag = d.sx;     // the factorisation's pivots live in the substitution scratch
+    d.red = take(8 * kBWarps);
+    d.have_pq = 0;
+    d.nan_pq = 0;
+    d.cp = d.bq = 0.0;
+
+    const double* A = gA + lp * (int64_t)m * n;
+    for (int idx = threadIdx.x; idx < m * n; idx += kBT) {
+      const int i = idx / n, j = idx - i * n;
+      d.A[i * d.lda + j] = A[idx];
+    }
+    for (int i = threadIdx.x; i < m; i += kBT) d.b[i] = gb[lp * m + i];
+    for (int j = threadIdx.x; j < n; j += kBT) {
+      d.c[j] = gc[lp * n + j];
+      d.dx[j] = 0.0;
+      d.dz[j] = 0.0;
+    }
+    __syncthreads();
+
+    SolveScalars sc;
+    NullRecorder rec;
+    const int rc = solve_normal_form_rec(d, opts, (int64_t)n, 0.0, &sc, rec);
+
+    double f[1] = {0.0};
+    if (rc == LPB_OK || rc == LPB_ERR_ITERATION_LIMIT_EXCEEDED) {
+      for (int j = threadIdx.x; j < n; j += kBT) {
+        const double t = d.x[j] / sc.tau;  // mod.rs:231
+        x_out[lp * n + j] = t;
+        f[0] += d.c[j] * t;                // linear_program.rs:62
+      }
+    }
+    block_allreduce<1>(f, false, d.red);
+    if (threadIdx.x == 0) {
+      fun_out[lp] = f[0];
+      it_out[lp] = sc.iterations;
+      st_out[lp] = rc;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+int batched_launch(int64_t batch, int m, int n, const double* dA, const double* db, const double* dc,
+                   const lpb_options& o, double* dx, double* dfun, int64_t* dit, int32_t* dst, cudaStream_t stream) {
+  const size_t smem = batched_smem_doubles(m, n) * sizeof(double);
+  if (m > kMaxM || smem > 227 * 1024) {
+    set_last_error("solve_batched: needs m <= %d and %zu bytes of shared memory <= 227 KB", kMaxM, smem);
+    return LPB_ERR_UNSUPPORTED;
+  }
+  LPB_CUDA(cudaFuncSetAttribute(batched_ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t grid = batch < (int64_t)kNumSMs * 64 ? batch : (int64_t)kNumSMs * 64;
+  batched_ipm_kernel<<<(unsigned)grid, kBT, smem, stream>>>(batch, m, n, dA, db, dc, o, dx, dfun, dit, dst);
+  LPB_CUDA(cudaGetLastError());
+  return LPB_OK;
+}
+
+}  // namespace lpb

@@ -20,6 +20,8 @@
 
 namespace lpb {
 int64_t gemv_t_partials_doubles(int64_t m, int64_t n);
+int batched_launch(int64_t batch, int m, int n, const double* dA, const double* db, const double* dc,
+                   const lpb_options& o, double* dx, double* dfun, int64_t* dit, int32_t* dst, cudaStream_t stream);
 }
 
 using namespace lpb;
@@ -737,10 +739,64 @@ int lpb_k_gemv_t(lpb_ctx* c, int64_t m, int64_t n, const double* dA, int64_t lda
 int lpb_solve_batched(int64_t batch, int64_t m, int64_t n, const double* A, const double* b, const double* c,
                       const lpb_options* opts, double* x_out, double* fun, int64_t* iterations, int32_t* status,
                       int mem, void* stream) {
-  (void)batch; (void)m; (void)n; (void)A; (void)b; (void)c; (void)opts; (void)x_out; (void)fun; (void)iterations;
-  (void)status; (void)mem; (void)stream;
-  set_last_error("solve_batched: not implemented yet");
-  return LPB_ERR_UNSUPPORTED;
+  if (batch <= 0 || m <= 0 || n <= 0 || !A || !b || !c || !x_out || !fun || !iterations || !status) {
+    set_last_error("solve_batched: null pointer or non-positive size");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  lpb_options o;
+  if (opts)
+    o = *opts;
+  else
+    options_default(&o);
+  LPB_TRY(lpb_options_validate(&o));
+  LPB_TRY(check_device());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mem == LPB_MEM_DEVICE) {
+    LPB_TRY(batched_launch(batch, (int)m, (int)n, A, b, c, o, x_out, fun, iterations, status, st));
+    LPB_CUDA(cudaStreamSynchronize(st));
+    return LPB_OK;
+  }
+  double *dA = nullptr, *db = nullptr, *dc = nullptr, *dx = nullptr, *df = nullptr;
+  int64_t* dit = nullptr;
+  int32_t* dst = nullptr;
+  int rc = LPB_OK;
+  auto cleanup = [&]() {
+    cudaFree(dA); cudaFree(db); cudaFree(dc); cudaFree(dx); cudaFree(df); cudaFree(dit); cudaFree(dst);
+  };
+#define LPB_BCUDA(call)                                                                         \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      set_last_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));     \
+      cleanup();                                                                                \
+      return LPB_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+  const size_t sA = sizeof(double) * (size_t)(batch * m * n), sb = sizeof(double) * (size_t)(batch * m),
+               sc = sizeof(double) * (size_t)(batch * n);
+  LPB_BCUDA(cudaMalloc(&dA, sA));
+  LPB_BCUDA(cudaMalloc(&db, sb));
+  LPB_BCUDA(cudaMalloc(&dc, sc));
+  LPB_BCUDA(cudaMalloc(&dx, sc));
+  LPB_BCUDA(cudaMalloc(&df, sizeof(double) * (size_t)batch));
+  LPB_BCUDA(cudaMalloc(&dit, sizeof(int64_t) * (size_t)batch));
+  LPB_BCUDA(cudaMalloc(&dst, sizeof(int32_t) * (size_t)batch));
+  LPB_BCUDA(cudaMemcpyAsync(dA, A, sA, cudaMemcpyHostToDevice, st));
+  LPB_BCUDA(cudaMemcpyAsync(db, b, sb, cudaMemcpyHostToDevice, st));
+  LPB_BCUDA(cudaMemcpyAsync(dc, c, sc, cudaMemcpyHostToDevice, st));
+  rc = batched_launch(batch, (int)m, (int)n, dA, db, dc, o, dx, df, dit, dst, st);
+  if (rc != LPB_OK) {
+    cleanup();
+    return rc;
+  }
+  LPB_BCUDA(cudaMemcpyAsync(x_out, dx, sc, cudaMemcpyDeviceToHost, st));
+  LPB_BCUDA(cudaMemcpyAsync(fun, df, sizeof(double) * (size_t)batch, cudaMemcpyDeviceToHost, st));
+  LPB_BCUDA(cudaMemcpyAsync(iterations, dit, sizeof(int64_t) * (size_t)batch, cudaMemcpyDeviceToHost, st));
+  LPB_BCUDA(cudaMemcpyAsync(status, dst, sizeof(int32_t) * (size_t)batch, cudaMemcpyDeviceToHost, st));
+  LPB_BCUDA(cudaStreamSynchronize(st));
+#undef LPB_BCUDA
+  cleanup();
+  return LPB_OK;
 }
 
 // ---------------------------------------------------------------- measurement
