@@ -205,7 +205,9 @@ int lpb_k_syrk_adat(lpb_ctx* ctx, int64_t m, int64_t n, const double* dA, int64_
 /* K2: in-place lower Cholesky of the m x m row-major matrix (M.cholesky(), :130 / potrf :88).
  * *info_host = 0 ok, j+1 = first bad pivot. */
 int lpb_k_potrf(lpb_ctx* ctx, int64_t m, double* dM, int64_t ldm, int32_t* info_host);
-/* K3: solve L L^T X = B in place, B column-major m x nrhs (nrhs 1 or 2) (solvec, :154 / :100). */
+/* K3: solve L L^T X = B in place, B column-major m x nrhs (nrhs 1 or 2) (solvec, :154 / :100).
+ * If dL is the matrix the last lpb_k_potrf on this context factored, the fused fast path (stored
+ * inverted diagonal blocks) is used; any other L goes through plain blocked substitution. */
 int lpb_k_potrs(lpb_ctx* ctx, int64_t m, const double* dL, int64_t ldm, double* dB, int64_t nrhs);
 /* K4: out = A w (gemv_n) / out = A^T v (gemv_t), raw products. */
 int lpb_k_gemv_n(lpb_ctx* ctx, int64_t m, int64_t n, const double* dA, int64_t lda,

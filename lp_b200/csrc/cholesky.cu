@@ -6,10 +6,13 @@
 // A non-positive or non-finite pivot sets the device `info` flag -> LPB_ERR_NUMERICAL_PROBLEM
 // (newton_equations.rs:63); there is no fallback chain.
 //
-// Per 128-wide panel:  potf2 (one CTA, block in shared memory)  ->  TRSM of the rows below
-// (warp-cooperative substitution, 64 rows per CTA)  ->  trailing update C -= P P^T on the DMMA
-// path (dmma_gemm.cu).  The solves walk the same 128-blocks: a one-CTA triangular solve of the
-// diagonal block, then a coalesced rank-128 update of the remaining right-hand side.
+// Per 128-wide panel:  potf2_inv (one CTA: factor the diagonal block in shared memory and invert
+// it in place, quad-per-column)  ->  panel TRSM as a DMMA GEMM  P <- P inv(L_kk)^T  ->  trailing
+// update C -= P P^T on the DMMA path (dmma_gemm.cu).  The inverted diagonal blocks are kept
+// (m x 128 doubles) so the solves need no serial substitution: every 128-block step is ONE launch
+// in which each CTA forms x_k = inv(L_kk) b_k itself (a 128 x 128 GEMV out of L2) and applies the
+// rank-128 update to its own rows / columns.
+// The substitution-based trsm / trsv kernels below are the plain reference path (syrk_impl = 1).
 #include "kernels.hpp"
 
 namespace lpb {
@@ -54,6 +57,82 @@ potf2_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __restr
   __syncthreads();
   for (int i = ty; i < nb; i += 16)
     for (int k = tx; k <= i; k += 32) blk[(int64_t)i * ldm + k] = (k == i) ? diag[i] : S[i * LDS + k];
+}
+
+// ------------------------------------------------------------------ potf2 + in-place inverse (one CTA)
+// Factor as above, then X = inv(L_kk): column c is owned by a quad of threads; x_i for i > c is
+//   x_i = -(sum_{l=c}^{i-1} L[i][l] x_l) / L[i][i]
+// with the partial sums split over the quad (2 shuffles).  X^T is kept in the strictly upper triangle
+// of the same shared block (row c holds column c), its diagonal in rdiag.  L goes back to Mat, X to
+// Linv (dense 128 x 128, zero above the diagonal and beyond nb).
+__global__ void __launch_bounds__(512)
+potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __restrict__ info,
+                 double* __restrict__ Linv) {
+  extern __shared__ double S[];  // NB*LDS block + NB diag + NB rdiag
+  double* diag = S + NB * LDS;
+  double* rdiag = diag + NB;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+  double* blk = Mat + (int64_t)k0 * ldm + k0;
+  for (int i = ty; i < nb; i += 16)
+    for (int k = tx; k <= i; k += 32) S[i * LDS + k] = blk[(int64_t)i * ldm + k];
+  __syncthreads();
+
+  bool failed = false;
+  for (int j = 0; j < nb; ++j) {
+    const double ajj = S[j * LDS + j];
+    if (!(ajj > 0.0) || !isfinite(ajj)) {  // uniform: every thread reads the same shared value
+      if (tid == 0 && *info == 0) *info = k0 + j + 1;
+      for (int i = j + tid; i < nb; i += 512) {
+        diag[i] = __longlong_as_double(0x7ff8000000000000ll);
+        rdiag[i] = diag[i];
+      }
+      failed = true;
+      break;
+    }
+    const double d = sqrt(ajj);
+    const double rd = 1.0 / d;
+    if (tid == 0) {
+      diag[j] = d;
+      rdiag[j] = rd;
+    }
+    if (tid < nb - j - 1) S[(j + 1 + tid) * LDS + j] /= d;
+    __syncthreads();
+    for (int i = j + 1 + ty; i < nb; i += 16) {
+      const double lij = S[i * LDS + j];
+      for (int k = j + 1 + tx; k <= i; k += 32) S[i * LDS + k] -= lij * S[k * LDS + j];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int i = ty; i < nb; i += 16)
+    for (int k = tx; k <= i; k += 32) blk[(int64_t)i * ldm + k] = (k == i) ? diag[i] : S[i * LDS + k];
+
+  // ---- inverse (skipped values are still written so Linv is always defined)
+  if (!failed) {
+    const int c = tid >> 2, q = tid & 3;
+    const int i_first = (tid >> 5) * 8 + 1;  // smallest c of this warp + 1: keeps the warp's trip count uniform
+    const double xc = c < nb ? rdiag[c] : 0.0;
+    for (int i = i_first; i < nb; ++i) {
+      double s = 0.0;
+      if (c < i) {
+        for (int l = c + q; l < i; l += 4) {
+          const double xl = (l == c) ? xc : S[c * LDS + l];
+          s += S[i * LDS + l] * xl;
+        }
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (c < i && q == 0) S[c * LDS + i] = -s * rdiag[i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NB * NB; idx += 512) {
+    const int i = idx >> 7, c = idx & (NB - 1);
+    double v = 0.0;
+    if (i < nb && c <= i) v = (c == i) ? rdiag[i] : S[c * LDS + i];
+    Linv[idx] = v;
+  }
 }
 
 // ------------------------------------------------------------------ TRSM: X L_kk^T = B, 64 rows per CTA
@@ -233,6 +312,145 @@ trsv_update_bwd_kernel(const double* __restrict__ L, int64_t ldm, int k0, int nb
   }
 }
 
+// ------------------------------------------------------------------ K3 fast path: fused solve steps
+// Forward step k (L w = b):  every CTA computes w_k = inv(L_kk) b_k (Linv block out of L2); CTA 0 also
+// publishes it to Y; CTA j then applies b_i -= L[i][k-block] w_k to its own 128 rows i (blockIdx.x >= 1).
+// Grid = 1 + number of 128-row blocks below block k.  B is the running right-hand side, Y the result.
+template <int NRHS>
+__global__ void __launch_bounds__(256)
+solve_fwd_step_kernel(const double* __restrict__ L, int64_t ldm, const double* __restrict__ Linv, int k0, int nb,
+                      double* __restrict__ B, double* __restrict__ Y, int64_t m) {
+  __shared__ double sb[NRHS][NB];
+  __shared__ double sw[NRHS][NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < NB; i += 256) {
+    sb[0][i] = i < nb ? B[k0 + i] : 0.0;
+    if (NRHS == 2) sb[1][i] = i < nb ? B[m + k0 + i] : 0.0;
+  }
+  __syncthreads();
+  // w = Linv * b : warp per row (16 rows per warp), lanes over the 128 columns
+  for (int r = warp; r < NB; r += 8) {
+    const double* lr = Linv + r * NB;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = lane + 32 * q;
+      const double a = c <= r ? __ldg(lr + c) : 0.0;
+      s0 += a * sb[0][c];
+      if (NRHS == 2) s1 += a * sb[1][c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      if (NRHS == 2) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane == 0) {
+      sw[0][r] = s0;
+      if (NRHS == 2) sw[1][r] = s1;
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (int i = tid; i < nb; i += 256) {
+      Y[k0 + i] = sw[0][i];
+      if (NRHS == 2) Y[m + k0 + i] = sw[1][i];
+    }
+    return;
+  }
+  // rank-nb update of this CTA's 128 rows: warp per row
+  const int64_t rbase = (int64_t)k0 + nb + (int64_t)(blockIdx.x - 1) * NB;
+  double x0[4], x1[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    x0[q] = sw[0][lane + 32 * q];
+    x1[q] = NRHS == 2 ? sw[1][lane + 32 * q] : 0.0;
+  }
+#pragma unroll 4
+  for (int rr = warp; rr < NB; rr += 8) {
+    const int64_t r = rbase + rr;
+    if (r >= m) break;
+    const double* lr = L + r * ldm + k0;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = lane + 32 * q;
+      const double a = c < nb ? __ldg(lr + c) : 0.0;
+      s0 += a * x0[q];
+      if (NRHS == 2) s1 += a * x1[q];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      if (NRHS == 2) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane == 0) {
+      B[r] -= s0;
+      if (NRHS == 2) B[m + r] -= s1;
+    }
+  }
+}
+
+// Backward step k (L^T x = w):  every CTA computes x_k = inv(L_kk)^T y_k; CTA 0 publishes it to X; CTA j
+// applies y_c -= sum_r L[k0+r][c] x_k[r] to its own 128 columns c of block j-1 (< k).
+template <int NRHS>
+__global__ void __launch_bounds__(256)
+solve_bwd_step_kernel(const double* __restrict__ L, int64_t ldm, const double* __restrict__ Linv, int k0, int nb,
+                      double* __restrict__ Y, double* __restrict__ X, int64_t m) {
+  __shared__ double sy[NRHS][NB];
+  __shared__ double sxk[NRHS][NB];
+  __shared__ double part[NRHS][2][NB];
+  const int tid = threadIdx.x;
+  const int c = tid & (NB - 1), h = tid >> 7;  // 128 columns x 2 row halves
+  for (int i = tid; i < NB; i += 256) {
+    sy[0][i] = i < nb ? Y[k0 + i] : 0.0;
+    if (NRHS == 2) sy[1][i] = i < nb ? Y[m + k0 + i] : 0.0;
+  }
+  __syncthreads();
+  {  // x[c] = sum_{r >= c} Linv[r][c] y[r]  (rows contiguous: coalesced across c)
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+    for (int r = h * 64; r < h * 64 + 64; ++r) {
+      if (r >= c && r < nb) {
+        const double a = __ldg(Linv + r * NB + c);
+        s0 += a * sy[0][r];
+        if (NRHS == 2) s1 += a * sy[1][r];
+      }
+    }
+    part[0][h][c] = s0;
+    if (NRHS == 2) part[1][h][c] = s1;
+  }
+  __syncthreads();
+  if (h == 0) {
+    sxk[0][c] = part[0][0][c] + part[0][1][c];
+    if (NRHS == 2) sxk[1][c] = part[1][0][c] + part[1][1][c];
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    if (h == 0 && c < nb) {
+      X[k0 + c] = sxk[0][c];
+      if (NRHS == 2) X[m + k0 + c] = sxk[1][c];
+    }
+    return;
+  }
+  const int64_t col = (int64_t)(blockIdx.x - 1) * NB + c;  // < k0 always (k0 is a multiple of NB)
+  double s0 = 0.0, s1 = 0.0;
+  const double* lp = L + (int64_t)k0 * ldm + col;
+  const int r_end = (h * 64 + 64) < nb ? (h * 64 + 64) : nb;
+#pragma unroll 8
+  for (int r = h * 64; r < r_end; ++r) {
+    const double a = __ldg(lp + (int64_t)r * ldm);
+    s0 += a * sxk[0][r];
+    if (NRHS == 2) s1 += a * sxk[1][r];
+  }
+  part[0][h][c] = s0;
+  if (NRHS == 2) part[1][h][c] = s1;
+  __syncthreads();
+  if (h == 0) {
+    Y[col] -= part[0][0][c] + part[0][1][c];
+    if (NRHS == 2) Y[m + col] -= part[1][0][c] + part[1][1][c];
+  }
+}
+
 template <typename K>
 int set_smem(K kern, size_t bytes) {
   LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -240,6 +458,7 @@ int set_smem(K kern, size_t bytes) {
 }
 
 constexpr size_t kPotf2Smem = (size_t)(NB * LDS + NB) * sizeof(double);
+constexpr size_t kPotf2InvSmem = (size_t)(NB * LDS + 2 * NB) * sizeof(double);
 constexpr size_t kTrsmSmem = (size_t)((NB + TRSM_ROWS) * LDS) * sizeof(double);
 constexpr size_t kTrsvSmem = (size_t)(NB * LDS + NB + 2 * NB) * sizeof(double);
 
@@ -247,6 +466,7 @@ int configure_once() {
   static bool done = false;
   if (done) return LPB_OK;
   LPB_TRY(set_smem(potf2_kernel, kPotf2Smem));
+  LPB_TRY(set_smem(potf2_inv_kernel, kPotf2InvSmem));
   LPB_TRY(set_smem(trsm_kernel, kTrsmSmem));
   LPB_TRY(set_smem(trsv_diag_kernel<false, 1>, kTrsvSmem));
   LPB_TRY(set_smem(trsv_diag_kernel<false, 2>, kTrsvSmem));
@@ -264,23 +484,67 @@ int configure_once() {
 
 }  // namespace
 
+// Workspace: one dense 128 x 128 inverse per diagonal block + a scratch right-hand side (2 m).
+static int ensure_chol_ws(LaunchCtx& lc, int64_t m) {
+  const int64_t nblk = ceil_div(m, NB);
+  const int64_t need = nblk * NB * NB + 2 * round_up(m, 2);
+  if (lc.chol_ws_cap >= need) return LPB_OK;
+  if (lc.chol_ws) cudaFree(lc.chol_ws);
+  lc.chol_ws = nullptr;
+  lc.chol_ws_cap = 0;
+  void* p = nullptr;
+  LPB_CUDA(cudaMalloc(&p, sizeof(double) * (size_t)need));
+  lc.chol_ws = static_cast<double*>(p);
+  lc.chol_ws_cap = need;
+  return LPB_OK;
+}
+
 int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
   LPB_TRY(configure_once());
+  LPB_TRY(ensure_chol_ws(lc, m));
   LPB_CUDA(cudaMemsetAsync(lc.info_dev, 0, sizeof(int), lc.stream));
   for (int64_t k0 = 0; k0 < m; k0 += NB) {
     const int nb = (int)((m - k0) < NB ? (m - k0) : NB);
-    potf2_kernel<<<1, dim3(32, 16), kPotf2Smem, lc.stream>>>(Mat, ldm, (int)k0, nb, lc.info_dev);
-    LPB_KCHECK(lc);
     const int64_t rem = m - k0 - nb;
+    double* linv = lc.chol_ws + (k0 / NB) * NB * NB;
+    potf2_inv_kernel<<<1, dim3(32, 16), kPotf2InvSmem, lc.stream>>>(Mat, ldm, (int)k0, nb, lc.info_dev, linv);
+    LPB_KCHECK(lc);
     if (rem > 0) {
-      trsm_kernel<<<(unsigned)ceil_div(rem, TRSM_ROWS), dim3(32, 8), kTrsmSmem, lc.stream>>>(Mat, ldm, (int)k0, nb,
-                                                                                             (int)m);
-      LPB_KCHECK(lc);
-      if (syrk_impl == 1)
+      if (syrk_impl == 1) {
+        trsm_kernel<<<(unsigned)ceil_div(rem, TRSM_ROWS), dim3(32, 8), kTrsmSmem, lc.stream>>>(Mat, ldm, (int)k0, nb,
+                                                                                               (int)m);
+        LPB_KCHECK(lc);
         LPB_TRY(k_trailing_update_simple(lc, m, Mat, ldm, k0, nb));
-      else
+      } else {
+        LPB_TRY(k_trsm_dmma(lc, m, Mat, ldm, k0, linv));
         LPB_TRY(k_trailing_update_dmma(lc, m, Mat, ldm, k0, nb));
+      }
     }
+  }
+  lc.linv_valid_m = m;
+  lc.linv_mat = Mat;
+  return LPB_OK;
+}
+
+// Fast path: one launch per 128-block step, using the stored inv(L_kk) blocks of the last k_potrf.
+template <int NRHS>
+static int potrs_fused(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B) {
+  const int nblk = (int)ceil_div(m, NB);
+  double* Y = lc.chol_ws + (int64_t)nblk * NB * NB;  // scratch m x NRHS (column-major, ld m)
+  for (int kb = 0; kb < nblk; ++kb) {                // forward: B -> Y
+    const int64_t k0 = (int64_t)kb * NB;
+    const int nb = (int)((m - k0) < NB ? (m - k0) : NB);
+    const unsigned grid = 1u + (unsigned)ceil_div(m - k0 - nb, NB);
+    solve_fwd_step_kernel<NRHS><<<grid, 256, 0, lc.stream>>>(L, ldm, lc.chol_ws + (int64_t)kb * NB * NB, (int)k0, nb, B,
+                                                             Y, m);
+    LPB_KCHECK(lc);
+  }
+  for (int kb = nblk - 1; kb >= 0; --kb) {           // backward: Y -> B
+    const int64_t k0 = (int64_t)kb * NB;
+    const int nb = (int)((m - k0) < NB ? (m - k0) : NB);
+    solve_bwd_step_kernel<NRHS><<<1u + (unsigned)kb, 256, 0, lc.stream>>>(L, ldm, lc.chol_ws + (int64_t)kb * NB * NB,
+                                                                          (int)k0, nb, Y, B, m);
+    LPB_KCHECK(lc);
   }
   return LPB_OK;
 }
@@ -315,10 +579,15 @@ static int potrs_impl(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, do
   return LPB_OK;
 }
 
-int k_potrs(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B, int nrhs) {
+int k_potrs(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B, int nrhs, bool use_linv) {
   LPB_TRY(configure_once());
-  if (nrhs == 1) return potrs_impl<1>(lc, m, L, ldm, B);
-  if (nrhs == 2) return potrs_impl<2>(lc, m, L, ldm, B);
+  if (use_linv && lc.linv_valid_m == m && lc.linv_mat == L && lc.chol_ws) {
+    if (nrhs == 1) return potrs_fused<1>(lc, m, L, ldm, B);
+    if (nrhs == 2) return potrs_fused<2>(lc, m, L, ldm, B);
+  } else {
+    if (nrhs == 1) return potrs_impl<1>(lc, m, L, ldm, B);
+    if (nrhs == 2) return potrs_impl<2>(lc, m, L, ldm, B);
+  }
   set_last_error("potrs: nrhs must be 1 or 2");
   return LPB_ERR_BAD_ARGUMENT;
 }

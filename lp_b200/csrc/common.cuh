@@ -48,6 +48,10 @@ struct LaunchCtx {
   double* red_host = nullptr;      // pinned, kMaxRedVals
   double* gemv_partials = nullptr; // gemv_t row-chunk partials
   int64_t gemv_partials_cap = 0;   // in doubles
+  double* chol_ws = nullptr;       // inv(L_kk) blocks of the last k_potrf + solve scratch (cholesky.cu)
+  int64_t chol_ws_cap = 0;         // in doubles
+  int64_t linv_valid_m = -1;       // order of the matrix whose block inverses chol_ws holds
+  const double* linv_mat = nullptr; // ... and its address
   int* info_dev = nullptr;         // potrf info flag
   int* info_host = nullptr;        // pinned
 };

@@ -108,11 +108,19 @@ struct LoadCursor {
   uint32_t phase;
 };
 
-// SCALE: multiply the B operand by d[k].  ACCUM: C -= A B^T (Cholesky trailing update) else C = A B^T.
-template <bool SCALE, bool ACCUM>
+// MODE_SYRK   : C = A diag(d) A^T (d optional), lower-triangular tile list, K = [k_begin, k_begin + 16 nkb).
+// MODE_UPDATE : C -= P P^T (Cholesky trailing update): accumulators start from C, the B fragment is
+//               negated, so the epilogue is store-only.
+// MODE_TRSM   : C[:, col_origin + 0..127] = A B^T with B = inv(L_kk) (128 x 128, its own tensor map):
+//               the panel TRSM X L_kk^T = P expressed as a GEMM; rectangular tile list (ntr x 1),
+//               in place (a CTA reads all K-blocks of its own rows before it stores them).
+enum { MODE_SYRK = 0, MODE_UPDATE = 1, MODE_TRSM = 2 };
+
+template <int MODE, bool SCALE>
 __global__ void __maxnreg__(255)
-syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
-                 double* __restrict__ C, int64_t ldc, int m_total, int tile0, int ntr, int k_begin, int nkb) {
+syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 double* __restrict__ C, int64_t ldc, int m_total, int tile0, int ntr, int k_begin, int nkb,
+                 int col_origin) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base + kSmemA, sB = smem_base + kSmemB, sD = smem_base + kSmemD;
@@ -128,9 +136,18 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   __syncthreads();
 
-  const int ntiles = ntr * (ntr + 1) / 2;
+  const int ntiles = MODE == MODE_TRSM ? ntr : ntr * (ntr + 1) / 2;
   const bool is_producer = threadIdx.x == 0;
   constexpr uint32_t kBytes = 2 * kTileBytes + (SCALE ? kDBytes : 0);
+
+  auto decode = [&](int L, int* ti, int* tj) {
+    if (MODE == MODE_TRSM) {
+      *ti = L;
+      *tj = 0;
+    } else {
+      tri_decode(L, ti, tj);
+    }
+  };
 
   LoadCursor pc;
   pc.L = blockIdx.x;
@@ -141,9 +158,9 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto cursor_tile = [&]() {
     if (pc.L < ntiles) {
       int ti, tj;
-      tri_decode(pc.L, &ti, &tj);
+      decode(pc.L, &ti, &tj);
       pc.row_i = (tile0 + ti) * BM;
-      pc.row_j = (tile0 + tj) * BN;
+      pc.row_j = MODE == MODE_TRSM ? 0 : (tile0 + tj) * BN;
     }
   };
   // issue the TMA loads of the cursor's iteration (if any is left) and advance it
@@ -154,8 +171,11 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_expect_tx(full, kBytes);
     const int k = k_begin + pc.kb * BK;
     tma_load_2d(sA + pc.stage * kTileBytes, &tmA, k, pc.row_i, full);
-    tma_load_2d(sB + pc.stage * kTileBytes, &tmA, k, pc.row_j, full);
-    if (SCALE) tma_load_2d(sD + pc.stage * kDBytes, &tmD, k, 0, full);
+    if (MODE == MODE_TRSM)
+      tma_load_2d(sB + pc.stage * kTileBytes, &tmB, pc.kb * BK, 0, full);
+    else
+      tma_load_2d(sB + pc.stage * kTileBytes, &tmA, k, pc.row_j, full);
+    if (SCALE) tma_load_2d(sD + pc.stage * kDBytes, &tmB, k, 0, full);
     if (++pc.stage == kStages) {
       pc.stage = 0;
       pc.phase ^= 1u;
@@ -183,12 +203,32 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
     int ti, tj;
-    tri_decode(L, &ti, &tj);
+    decode(L, &ti, &tj);
+    const int row0 = (tile0 + ti) * BM + wm * 64 + g;
+    const int col0 = (MODE == MODE_TRSM ? col_origin : (tile0 + tj) * BN) + wn * 32 + 2 * t;
+    const int col_limit = MODE == MODE_TRSM ? col_origin + BN : m_total;
     double acc[8][4][2];
+    if (MODE == MODE_UPDATE) {
+      // start from C: the loads overlap the wait for the first operand stages
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+      for (int mi = 0; mi < 8; ++mi) {
+        const int r = row0 + mi * 8;
+        const double* crow = C + static_cast<int64_t>(r) * ldc;
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int ni = 0; ni < 4; ++ni) {
+          const int c = col0 + ni * 8;
+          double2 v = make_double2(0.0, 0.0);
+          if (r < m_total && c < col_limit) v = *reinterpret_cast<const double2*>(crow + c);
+          acc[mi][ni][0] = v.x;
+          acc[mi][ni][1] = v.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    }
 
     for (int kb = 0; kb < nkb; ++kb) {
       // keep the ring kLead iterations ahead: the stage being refilled was released kStages - kLead
@@ -211,6 +251,13 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             b[ni].y *= d.y;
           }
         }
+        if (MODE == MODE_UPDATE) {
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            b[ni].x = -b[ni].x;
+            b[ni].y = -b[ni].y;
+          }
+        }
         double2 a[8];
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi) a[mi] = lds_v2(a_base + mi * 1024 + sw[P]);
@@ -231,9 +278,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
 
-    // ------------------------------------------------------------ epilogue (each warp its own slab)
-    const int row0 = (tile0 + ti) * BM + wm * 64 + g;
-    const int col0 = (tile0 + tj) * BN + wn * 32 + 2 * t;
+    // ------------------------------------------------------------ epilogue: store-only, each warp its own slab
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi) {
       const int r = row0 + mi * 8;
@@ -242,19 +287,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
           const int c = col0 + ni * 8;
-          if (c < m_total) {
-            double2* p = reinterpret_cast<double2*>(crow + c);
-            double2 v;
-            if (ACCUM) {
-              const double2 old = *p;
-              v.x = old.x - acc[mi][ni][0];
-              v.y = old.y - acc[mi][ni][1];
-            } else {
-              v.x = acc[mi][ni][0];
-              v.y = acc[mi][ni][1];
-            }
-            *p = v;
-          }
+          if (c < col_limit) *reinterpret_cast<double2*>(crow + c) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         }
       }
     }
@@ -302,18 +335,18 @@ int make_tmap(CUtensorMap* tm, const double* base, uint64_t rows, uint64_t cols,
   return LPB_OK;
 }
 
-template <bool SCALE, bool ACCUM>
-int launch_dmma(LaunchCtx& lc, const CUtensorMap& tmA, const CUtensorMap& tmD, double* C, int64_t ldc, int m_total,
-                int tile0, int ntr, int k_begin, int nkb) {
+template <int MODE, bool SCALE>
+int launch_dmma(LaunchCtx& lc, const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int m_total,
+                int tile0, int ntr, int k_begin, int nkb, int col_origin) {
   static bool configured = false;
-  auto kern = syrk_dmma_kernel<SCALE, ACCUM>;
+  auto kern = syrk_dmma_kernel<MODE, SCALE>;
   if (!configured) {
     LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAlloc));
     configured = true;
   }
-  const int ntiles = ntr * (ntr + 1) / 2;
+  const int ntiles = MODE == MODE_TRSM ? ntr : ntr * (ntr + 1) / 2;
   const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
-  kern<<<grid, kThreads, kSmemAlloc, lc.stream>>>(tmA, tmD, C, ldc, m_total, tile0, ntr, k_begin, nkb);
+  kern<<<grid, kThreads, kSmemAlloc, lc.stream>>>(tmA, tmB, C, ldc, m_total, tile0, ntr, k_begin, nkb, col_origin);
   lc.launches++;
   LPB_CUDA(cudaGetLastError());
   return LPB_OK;
@@ -337,8 +370,8 @@ int k_syrk_dmma(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t ld
     tmD = tmA;
   const int ntr = (int)ceil_div(m, BM);
   const int nkb = (int)ceil_div(n, BK);
-  if (d) return launch_dmma<true, false>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb);
-  return launch_dmma<false, false>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb);
+  if (d) return launch_dmma<MODE_SYRK, true>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, 0);
+  return launch_dmma<MODE_SYRK, false>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, 0);
 }
 
 int k_trailing_update_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb) {
@@ -351,7 +384,24 @@ int k_trailing_update_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, i
   CUtensorMap tm;
   LPB_TRY(make_tmap(&tm, Mat, (uint64_t)m, (uint64_t)m, (uint64_t)ldm, BM, BK, true));
   const int ntr = (int)ceil_div(m - row0, BM);
-  return launch_dmma<false, true>(lc, tm, tm, Mat, ldm, (int)m, (int)(row0 / BM), ntr, (int)k0, (int)(kb / BK));
+  return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, (int)(row0 / BM), ntr, (int)k0, (int)(kb / BK),
+                                         0);
+}
+
+// Panel TRSM as a GEMM: Mat[row0.., k0..k0+128) <- Mat[row0.., k0..k0+128) * Linv^T, row0 = k0 + 128,
+// Linv = inv(L_kk) stored dense 128 x 128 (ld 128, upper triangle zero).
+int k_trsm_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, const double* Linv) {
+  const int64_t row0 = k0 + BN;
+  if (row0 >= m) return LPB_OK;
+  if ((row0 % BM) || (ldm & 1) || (reinterpret_cast<uintptr_t>(Mat) & 15) || (reinterpret_cast<uintptr_t>(Linv) & 15)) {
+    set_last_error("trsm_dmma: panel origin must be a multiple of %d", BM);
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  CUtensorMap tm, tl;
+  LPB_TRY(make_tmap(&tm, Mat, (uint64_t)m, (uint64_t)m, (uint64_t)ldm, BM, BK, true));
+  LPB_TRY(make_tmap(&tl, Linv, (uint64_t)BN, (uint64_t)BN, (uint64_t)BN, BN, BK, true));
+  const int ntr = (int)ceil_div(m - row0, BM);
+  return launch_dmma<MODE_TRSM, false>(lc, tm, tl, Mat, ldm, (int)m, (int)(row0 / BM), ntr, (int)k0, BN / BK, (int)k0);
 }
 
 // ------------------------------------------------------------------ plain DFMA reference kernel

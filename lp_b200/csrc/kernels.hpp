@@ -74,6 +74,8 @@ int k_sym_back(LaunchCtx& lc, int64_t n, int nchunks, int with_pq, const double*
 int k_syrk_dmma(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* d, double* Cmat,
                 int64_t ldc);
 int k_trailing_update_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb);
+// panel TRSM as a DMMA GEMM with the inverted 128 x 128 diagonal block (dense, ld 128)
+int k_trsm_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, const double* Linv);
 // plain DFMA reference kernels (tests / bisecting only)
 int k_syrk_simple(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* d, double* Cmat,
                   int64_t ldc);
@@ -82,8 +84,9 @@ int k_trailing_update_simple(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm,
 // ---------------------------------------------------------------- K2 / K3 (cholesky.cu)
 // In-place blocked right-looking lower Cholesky; info (device int) = 0 or first bad pivot + 1.
 int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl);
-// Solve L L^T X = B in place; B column-major m x nrhs.
-int k_potrs(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B, int nrhs);
+// Solve L L^T X = B in place; B column-major m x nrhs.  use_linv: use the inverted diagonal blocks the
+// last k_potrf on this context left behind (L must be that factor); otherwise plain substitution.
+int k_potrs(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B, int nrhs, bool use_linv);
 
 // ---------------------------------------------------------------- synthetic shard fill (vec_kernels.cu)
 int k_fill_normal(LaunchCtx& lc, double* A, int64_t rows, int64_t cols, int64_t lda, int64_t row0, int64_t col0,

@@ -238,7 +238,7 @@ struct CudaDev {
     }
     {
       PhaseTimer tm(c, PH_SOLVE);
-      LPB_TRY(k_potrs(c->lc, c->m, c->M, c->ldm, c->W, nrhs));
+      LPB_TRY(k_potrs(c->lc, c->m, c->M, c->ldm, c->W, nrhs, c->syrk_impl == 0));
     }
     RedSpec spec;
     spec.nvals = 6;
@@ -387,6 +387,7 @@ void ctx_free(lpb_ctx* c) {
   }
   for (auto e : c->ev_free) cudaEventDestroy(e);
   for (void* p : c->allocs) cudaFree(p);
+  if (c->lc.chol_ws) cudaFree(c->lc.chol_ws);
   if (c->lc.red_host) cudaFreeHost(c->lc.red_host);
   if (c->lc.info_host) cudaFreeHost(c->lc.info_host);
   if (c->own_stream && c->lc.stream) cudaStreamDestroy(c->lc.stream);
@@ -711,7 +712,7 @@ int lpb_k_potrf(lpb_ctx* c, int64_t m, double* dM, int64_t ldm, int32_t* info_ho
 
 int lpb_k_potrs(lpb_ctx* c, int64_t m, const double* dL, int64_t ldm, double* dB, int64_t nrhs) {
   if (!c || !dL || !dB) return LPB_ERR_BAD_ARGUMENT;
-  LPB_TRY(k_potrs(c->lc, m, dL, ldm, dB, (int)nrhs));
+  LPB_TRY(k_potrs(c->lc, m, dL, ldm, dB, (int)nrhs, c->syrk_impl == 0));
   LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
   return LPB_OK;
 }

@@ -114,3 +114,27 @@ def test_gemv_sweeps_match_numpy(m, n):
         ok(ctx.lib.lpb_k_gemv_t(ctx.h, m, n, dA.data_ptr(), lda, dv.data_ptr(), o_t.data_ptr()))
     assert (np.abs(o_n.cpu().numpy() - A @ w) / (np.abs(A) @ np.abs(w))).max() < 1e-13
     assert (np.abs(o_t.cpu().numpy() - A.T @ v) / (np.abs(A.T) @ np.abs(v))).max() < 1e-13
+
+
+@pytest.mark.parametrize("nrhs", [1, 2])
+@pytest.mark.parametrize("m", [64, 128, 200, 640, 1537])
+def test_potrf_then_fused_potrs(m, nrhs):
+    """K2 + K3 fast path: factor on the device, then solve with the stored inverted diagonal blocks;
+    residual ||M x - b|| / (||M|| ||x||) < 1e-13 and x close to LAPACK's."""
+    from scipy.linalg import cho_factor, cho_solve
+    rng = np.random.default_rng(3 * m + nrhs)
+    Bm = rng.standard_normal((m, m + 8))
+    M = Bm @ Bm.T + 0.5 * np.eye(m)
+    Mp, ldm = pad_cols(M)
+    rhs = rng.standard_normal((nrhs, m))
+    dM, dB = to_dev(Mp), to_dev(rhs)
+    info = C.c_int32(-1)
+    with BareCtx(m, m) as ctx:
+        ok(ctx.lib.lpb_k_potrf(ctx.h, m, dM.data_ptr(), ldm, C.byref(info)))
+        assert info.value == 0
+        ok(ctx.lib.lpb_k_potrs(ctx.h, m, dM.data_ptr(), ldm, dB.data_ptr(), nrhs))
+    X = dB.cpu().numpy()
+    ref = cho_solve(cho_factor(M, lower=True), rhs.T).T
+    assert np.abs(X - ref).max() / np.abs(ref).max() < 1e-9
+    for k in range(nrhs):
+        assert np.linalg.norm(M @ X[k] - rhs[k]) / (np.linalg.norm(M) * np.linalg.norm(X[k])) < 1e-13
