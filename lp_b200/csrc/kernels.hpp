@@ -91,5 +91,9 @@ int k_potrs(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B, i
 // ---------------------------------------------------------------- synthetic shard fill (vec_kernels.cu)
 int k_fill_normal(LaunchCtx& lc, double* A, int64_t rows, int64_t cols, int64_t lda, int64_t row0, int64_t col0,
                   uint64_t seed);
+int k_fill_vec(LaunchCtx& lc, double* v, int64_t count, int64_t idx0, uint64_t seed, int kind, double lo, double hi,
+               int64_t neg_below);
+int k_slack_identity(LaunchCtx& lc, double* A, int64_t rows, int64_t cols, int64_t lda, int64_t col0, int64_t n0);
+int k_add_vec(LaunchCtx& lc, double* out, const double* a, const double* b, int64_t count, int64_t count_b);
 
 }  // namespace lpb

@@ -595,12 +595,55 @@ int lpb_create_sharded(lpb_ctx** out, int64_t m, int64_t n_global, int64_t col0,
   return LPB_OK;
 }
 
+// Device-side instance of the SURVEY 8(d) generator for column shards (config C5: A never exists on
+// the host).  User columns [0, n0), n0 = n_global - m/2, are i.i.d. N(0,1) keyed by (seed, row, column);
+// slack columns are [I; 0].  b = A0 x0 (+ s0 on the inequality rows) needs the one all-reduce;
+// c = A0^T y0 + z0 is local to each shard.  Strictly primal- and dual-feasible by construction.
 int lpb_create_sharded_synthetic(lpb_ctx** out, int64_t m, int64_t n_global, int64_t col0, int64_t n_local,
                                  uint64_t seed, int rank, int world, const void* nccl_unique_id, void* stream) {
-  (void)out; (void)m; (void)n_global; (void)col0; (void)n_local; (void)seed; (void)rank; (void)world;
-  (void)nccl_unique_id; (void)stream;
-  set_last_error("create_sharded_synthetic: not implemented yet");
-  return LPB_ERR_UNSUPPORTED;
+  if ((m & 1) || n_global <= m / 2) {
+    set_last_error("create_sharded_synthetic: needs even m and n_global > m/2");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  lpb_ctx* c = nullptr;
+  LPB_TRY(lpb_create_sharded(&c, m, n_global, col0, n_local, nullptr, 0, nullptr, nullptr, 0.0, LPB_MEM_DEVICE, rank,
+                             world, nccl_unique_id, stream));
+  const int64_t mh = m / 2, n0 = n_global - mh;
+  const int64_t n_user = std::max<int64_t>(0, std::min(n0, col0 + n_local) - col0);  // user columns in this shard
+  int rc = LPB_OK;
+  auto run = [&]() -> int {
+    LPB_TRY(k_fill_normal(c->lc, c->A, m, n_user, c->lda, 0, col0, seed));
+    LPB_TRY(k_slack_identity(c->lc, c->A, m, n_local, c->lda, col0, n0));
+    // x0 (user columns of this shard) -> xs ; y0 -> y ; z0 -> rD ; s0 -> rP (scratch use of iterate buffers)
+    LPB_TRY(k_fill(c->lc, c->xs, n_local, 0.0));
+    LPB_TRY(k_fill_vec(c->lc, c->xs, n_user, col0, seed + 1, 0, 0.5, 1.5, 0));
+    LPB_TRY(k_fill_vec(c->lc, c->y, m, 0, seed + 2, 2, 0.0, 0.0, mh));
+    LPB_TRY(k_fill(c->lc, c->rD, n_local, 0.0));
+    LPB_TRY(k_fill_vec(c->lc, c->rD, n_user, col0, seed + 3, 0, 0.5, 1.5, 0));
+    LPB_TRY(k_fill_vec(c->lc, c->rP, mh, 0, seed + 4, 0, 0.5, 1.5, 0));
+    // b = sum_k A_k x0_k + [s0; 0]   (slack columns contribute nothing: x0 is zero there)
+    LPB_TRY(k_gemv_n(c->lc, m, n_local, c->A, c->lda, nullptr, c->xs, nullptr, c->t, nullptr, 1));
+    LPB_TRY(allreduce(c, c->t, m, ncclSum));
+    LPB_TRY(k_add_vec(c->lc, c->b, c->t, c->rP, m, mh));
+    // c = A^T y0 + z0 on user columns, 0 on slack columns
+    int nchunks = 0;
+    LPB_TRY(k_gemv_t_partials(c->lc, m, n_local, c->A, c->lda, c->y, nullptr, 1, &nchunks));
+    LPB_TRY(k_gemv_t_raw(c->lc, n_local, nchunks, 1, c->u, nullptr));
+    LPB_TRY(k_add_vec(c->lc, c->c, c->u, c->rD, n_local, n_local));
+    if (n_user < n_local) LPB_TRY(k_fill(c->lc, c->c + n_user, n_local - n_user, 0.0));
+    LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+    return LPB_OK;
+  };
+  rc = run();
+  if (rc != LPB_OK) {
+    ctx_free(c);
+    return rc;
+  }
+  c->c0 = 0.0;
+  c->has_problem = true;
+  c->have_pq = false;
+  *out = c;
+  return LPB_OK;
 }
 
 // ---------------------------------------------------------------- phases

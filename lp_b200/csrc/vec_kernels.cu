@@ -594,6 +594,66 @@ __device__ __forceinline__ double counter_normal(uint64_t seed, uint64_t row, ui
   const double u2 = (b >> 11) * (1.0 / 9007199254740992.0);          // [0,1)
   return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
+__device__ __forceinline__ double counter_uniform(uint64_t seed, uint64_t idx, double lo, double hi) {
+  const uint64_t a = splitmix64(seed ^ splitmix64(idx + 0x5851F42D4C957F2Dull));
+  return lo + (hi - lo) * ((a >> 11) * (1.0 / 9007199254740992.0));
+}
+
+// kind 0: U(lo, hi);  kind 1: N(0,1);  kind 2: -|N(0,1)| for idx < neg_below, N(0,1) above (the y0 of
+// the SURVEY 8(d) generator: dual-feasible multipliers, non-positive on the inequality rows).
+__global__ void fill_vec_kernel(double* __restrict__ v, int64_t count, int64_t idx0, uint64_t seed, int kind, double lo,
+                                double hi, int64_t neg_below) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t gi = (uint64_t)(idx0 + i);
+    double r;
+    if (kind == 0) {
+      r = counter_uniform(seed, gi, lo, hi);
+    } else {
+      r = counter_normal(seed, gi, 0x7777ull);
+      if (kind == 2 && (int64_t)gi < neg_below) r = -fabs(r);
+    }
+    v[i] = r;
+  }
+}
+int k_fill_vec(LaunchCtx& lc, double* v, int64_t count, int64_t idx0, uint64_t seed, int kind, double lo, double hi,
+               int64_t neg_below) {
+  if (count <= 0) return LPB_OK;
+  fill_vec_kernel<<<vec_blocks(count), kVecThreads, 0, lc.stream>>>(v, count, idx0, seed, kind, lo, hi, neg_below);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+// slack columns of the slack form: A[r][c] = 1 if (global column) == n0 + r else 0, for global columns >= n0
+__global__ void slack_identity_kernel(double* __restrict__ A, int64_t rows, int64_t cols, int64_t lda, int64_t col0,
+                                      int64_t n0) {
+  const int64_t total = rows * cols;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / cols, c = idx - r * cols;
+    const int64_t gc = col0 + c;
+    if (gc >= n0) A[r * lda + c] = (gc - n0 == r) ? 1.0 : 0.0;
+  }
+}
+int k_slack_identity(LaunchCtx& lc, double* A, int64_t rows, int64_t cols, int64_t lda, int64_t col0, int64_t n0) {
+  if (rows <= 0 || cols <= 0) return LPB_OK;
+  slack_identity_kernel<<<kNumSMs * 8, 256, 0, lc.stream>>>(A, rows, cols, lda, col0, n0);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+// out[i] = a[i] + (b ? b[i] : 0) for i < count_b, a[i] beyond (count_b <= count)
+__global__ void add_vec_kernel(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b,
+                               int64_t count, int64_t count_b) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = a[i] + (i < count_b ? b[i] : 0.0);
+}
+int k_add_vec(LaunchCtx& lc, double* out, const double* a, const double* b, int64_t count, int64_t count_b) {
+  if (count <= 0) return LPB_OK;
+  add_vec_kernel<<<vec_blocks(count), kVecThreads, 0, lc.stream>>>(out, a, b, count, count_b);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
 __global__ void fill_normal_kernel(double* __restrict__ A, int64_t rows, int64_t cols, int64_t lda, int64_t row0,
                                    int64_t col0, uint64_t seed) {
   const int64_t total = rows * cols;
