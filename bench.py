@@ -35,11 +35,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {  # slack-form (m, n); BASELINE.json configs[0..2]
+WORKLOADS = {  # slack-form (m, n); BASELINE.json configs[0..4]
     "C1": (512, 1024),
     "C2": (4096, 8192),
     "C3": (16384, 32768),
+    "C4": (64, 128),        # batched: 8192 independent LPs, one CTA per problem, batch sharded over ranks
+    "C5": (32768, 131072),  # A generated on the device per column shard (never on the host)
 }
+C4_BATCH = 8192
 DEFAULT_WORKLOAD = "C3"
 NOMINAL_FP64_TFLOPS = 40.0  # B200 FP64 (tensor == vector), NVIDIA HGX B200 spec sheet
 
@@ -202,6 +205,238 @@ def run_reference_arm(args, m, n):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------- shared pieces of the product arm
+def _sync_max_ms(torch, dist, ms):
+    if dist is None:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _roofline(prof_sum, m, n_loc):
+    f_syrk = float(m) * (m + 1) * n_loc
+    f_chol = float(m) ** 3 / 3.0
+    syrk_ms = prof_sum.get("syrk_ms", 0.0) / max(1, prof_sum.get("syrk_launches", 1))
+    potrf_ms = prof_sum.get("potrf_ms", 0.0) / max(1, prof_sum.get("potrf_launches", 1))
+    achieved = f_syrk / (syrk_ms * 1e-3) * 1e-12 if syrk_ms > 0 else None
+    return {
+        "bound": "tensor", "kernel": "syrk_dmma_kernel (K1, A.diag(x/z).A^T, FP64 DMMA)",
+        "achieved": achieved, "peak": NOMINAL_FP64_TFLOPS, "unit": "TFLOP/s",
+        "frac": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None, "traffic": SYRK_TRAFFIC.get((m, n_loc)),
+        "peak_source": "nominal B200 FP64 (MEASURED_PEAKS.json has no FP64 entry; measured on this pool: DMMA issue "
+                       "peak 36.95, cuBLAS DGEMM 35.4 TFLOP/s, profiles/fp64_peaks_r01.json)",
+        "flop_per_launch": f_syrk, "ms_per_launch": syrk_ms,
+        "phase_syrk_plus_cholesky_tflops": ((f_syrk + f_chol) / ((syrk_ms + potrf_ms) * 1e-3) * 1e-12
+                                            if syrk_ms + potrf_ms > 0 else None),
+        "potrf_ms_per_launch": potrf_ms,
+        "potrf_tflops": (f_chol / (potrf_ms * 1e-3) * 1e-12) if potrf_ms > 0 else None,
+    }
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE syrk_dmma_kernel launch, from the committed
+# `ncu --set full` captures (profiles/); keyed by (m, n_local).
+SYRK_TRAFFIC = {}
+
+
+def _timed_solves(args, torch, dist, solver, rp, local_rank):
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        solver.solve_resident(rp)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_sum, launches, total_iters, res = {}, 0, 0, None
+    sampler.start()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        res = solver.solve_resident(rp)
+        total_iters += res.iteration()
+        p = rp.profile()
+        launches += p["launches"]
+        for k, v in p.items():
+            prof_sum[k] = prof_sum.get(k, 0) + v
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = _sync_max_ms(torch, dist, e0.elapsed_time(e1))
+    return ms, total_iters, launches, prof_sum, clocks, res
+
+
+def run_device_synthetic(args, torch, dist, rank, local_rank, world, stream, m, n):
+    """C5 (and any size with --device-synthetic): A is generated per column shard on the device."""
+    import lp_b200
+    from lp_b200.api import SyntheticShardedProblem
+    solver = lp_b200.InteriorPoint.default()
+    t0 = time.perf_counter()
+    rp = SyntheticShardedProblem(m, n, args.seed, rank, world, dist, stream=stream)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    ms, total_iters, launches, prof_sum, clocks, res = _timed_solves(args, torch, dist, solver, rp, local_rank)
+    value = total_iters / (ms * 1e-3)
+    rp.close()
+    # e2e: context creation + on-device generation of the shard + solve + D2H / gather of x
+    e2e = None
+    if not args.no_e2e:
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        it_e2e = 0
+        for _ in range(args.steps):
+            with SyntheticShardedProblem(m, n, args.seed, rank, world, dist, stream=stream) as sp:
+                it_e2e += solver.solve_resident(sp).iteration()
+        torch.cuda.synchronize()
+        dt = _sync_max_ms(torch, dist, (time.perf_counter() - t0) * 1e3) * 1e-3
+        e2e = {"value": it_e2e / dt, "unit": "iterations/s", "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": int(rp.n * 8 + 16), "ms_per_step": dt / args.steps * 1e3,
+               "note": "inputs are generated on the device (the %.1f GB matrix never exists on the host); "
+                       "the timed region covers generation + solve + D2H of x" % (m * n * 8 / 1e9)}
+    if rank == 0:
+        n_loc = rp.n
+        steps = args.steps
+        phases = {k: prof_sum.get(k, 0.0) / steps for k in
+                  ("total_ms", "syrk_ms", "potrf_ms", "solve_ms", "sweep_ms", "vector_ms", "comm_ms")}
+        line = {
+            "metric": "ipm_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s dense LP slack-form m=%d n=%d seed=%d, generated on the device per column "
+                                   "shard (counter-based N(0,1), SURVEY 8d construction)" % (args.workload, m, n, args.seed),
+                       "iterations_per_solve": total_iters / args.steps, "objective": res.fun(),
+                       "l2": "inputs larger than L2 (A shard = %.0f MB)" % (m * n_loc * 8 / 1e6),
+                       "parallelism": "1 GPU" if world == 1 else
+                       "A column-sharded over %d GPUs, NCCL all-reduce of M" % world,
+                       "device_generation_s": gen_s},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": _roofline(prof_sum, m, n_loc),
+            "phases_ms_per_solve": phases, "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_batched(args, torch, dist, rank, local_rank, world, stream):
+    """C4: `batch` independent 64x128 LPs, one CTA per problem; the batch is sharded over the ranks
+    with no collective on the data path."""
+    import lp_b200
+    from lp_b200 import _ffi
+    lib = _ffi.load()
+    m, n = WORKLOADS["C4"]
+    batch = args.batch
+    per = -(-batch // world)
+    lo, hi = min(batch, rank * per), min(batch, (rank + 1) * per)
+    nb = hi - lo
+    t0 = time.perf_counter()
+    A = np.zeros((nb, m, n))
+    b = np.zeros((nb, m))
+    c = np.zeros((nb, n))
+    for i in range(nb):  # SURVEY 8(d): seeds 1000 + i
+        cc, A_ub, b_ub, A_eq, b_eq = synthetic_lp(m, n, 1000 + lo + i)
+        pb = lp_b200.Problem.target(cc).ub(A_ub, b_ub).eq(A_eq, b_eq).build()
+        A[i], b[i], c[i] = pb.A(), pb.b(), pb.c()
+    gen_s = time.perf_counter() - t0
+    solver = lp_b200.InteriorPoint.default()
+    dA, db, dc = torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(c).cuda()
+    dx = torch.zeros((nb, n), dtype=torch.float64, device="cuda")
+    dfun = torch.zeros(nb, dtype=torch.float64, device="cuda")
+    dit = torch.zeros(nb, dtype=torch.int64, device="cuda")
+    dst = torch.zeros(nb, dtype=torch.int32, device="cuda")
+
+    def resident():
+        rc = lib.lpb_solve_batched(nb, m, n, dA.data_ptr(), db.data_ptr(), dc.data_ptr(), C.byref(solver._o),
+                                   dx.data_ptr(), dfun.data_ptr(), dit.data_ptr(), dst.data_ptr(),
+                                   _ffi.LPB_MEM_DEVICE, C.c_void_p(stream))
+        assert rc == 0, _ffi.last_error()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        resident()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = _sync_max_ms(torch, dist, e0.elapsed_time(e1))
+    its = dit.sum().to(torch.float64).reshape(1)
+    n_ok = (dst == 0).sum().to(torch.float64).reshape(1)
+    if dist is not None:
+        dist.all_reduce(its)
+        dist.all_reduce(n_ok)
+    total_iters = float(its.item())
+    value = total_iters * args.steps / (ms * 1e-3)
+    # e2e: host arrays in, host arrays out through lp_b200.solve_batched (H2D of A, b, c + D2H of x, fun, ...)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = lp_b200.solve_batched(A, b, c, n_slack=m // 2, solver=solver, stream=stream)
+    torch.cuda.synchronize()
+    dt = _sync_max_ms(torch, dist, (time.perf_counter() - t0) * 1e3) * 1e-3
+    e2e = {"value": total_iters * args.steps / dt, "unit": "iterations/s",
+           "h2d_bytes_per_step": int((A.size + b.size + c.size) * 8), "d2h_bytes_per_step": int(nb * (n * 8 + 8 + 8 + 4)),
+           "ms_per_step": dt / args.steps * 1e3}
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import ipm_oracle as o
+            k = min(nb, 256)
+            t0 = time.perf_counter()
+            it_cpu = 0
+            for i in range(k):
+                it_cpu += o.InteriorPoint().solve(o.Problem(A[i], b[i], c[i], 0.0, m // 2)).iteration
+            dtc = time.perf_counter() - t0
+            cpu = {"value": it_cpu / dtc, "unit": "iterations/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": "oracle looped over the first %d of the %d LPs" % (k, batch)}
+        # one-time load of each LP into shared memory is the only HBM traffic of the kernel
+        bytes_per_lp = (m * n + m + n) * 8 + n * 8 + 24
+        line = {
+            "metric": "ipm_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 batched: %d independent dense LPs slack-form m=%d n=%d, seeds 1000+i, one CTA "
+                                   "per problem" % (batch, m, n),
+                       "lps_per_s": batch * args.steps / (ms * 1e-3), "optimal": int(n_ok.item()),
+                       "iterations_per_lp": total_iters / batch,
+                       "l2": "whole batch (%.0f MB) larger than L2" % (batch * bytes_per_lp / 1e6),
+                       "parallelism": "batch sharded over %d GPU(s), no collective" % world,
+                       "host_generation_s": gen_s},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(args.steps),
+            "roofline": {"bound": "hbm", "kernel": "batched_ipm_kernel (K6): latency / shared-memory bound; HBM only "
+                                                   "for the one-time load of each LP",
+                         "achieved": batch * bytes_per_lp / (ms / args.steps * 1e-3) / 1e9 / world, "peak": _hbm_peak(),
+                         "unit": "GB/s", "frac": batch * bytes_per_lp / (ms / args.steps * 1e-3) / 1e9 / world / _hbm_peak(),
+                         "traffic": None},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0  # B200_PROFILING.md fallback
+
+
 # --------------------------------------------------------------------------- product arm
 def main():
     ap = argparse.ArgumentParser()
@@ -213,6 +448,9 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--device-synthetic", action="store_true",
+                    help="generate the LP on the device per column shard (always on for C5)")
+    ap.add_argument("--batch", type=int, default=C4_BATCH)
     args = ap.parse_args()
     m, n = WORKLOADS[args.workload]
 
@@ -239,6 +477,13 @@ def main():
 
     lib = _ffi.load()
     stream = torch.cuda.current_stream().cuda_stream
+
+    if args.workload == "C4":
+        run_batched(args, torch, dist, rank, local_rank, world, stream)
+        return
+    if args.workload == "C5" or args.device_synthetic:
+        run_device_synthetic(args, torch, dist, rank, local_rank, world, stream, m, n)
+        return
 
     # ---- build the workload on the host (identical bits on every rank)
     t0 = time.perf_counter()
@@ -291,6 +536,7 @@ def main():
         ms = float(t.item())
     value = total_iters / (ms * 1e-3)
     fun = res.fun()
+    n_loc_rank = rp.n
 
     # ---- e2e through the public API (host buffers, H2D + D2H inside the timed region)
     e2e = None
@@ -328,26 +574,7 @@ def main():
                "d2h_bytes_per_step": int((n // world) * 8 + 16), "ms_per_step": dt / args.steps * 1e3}
 
     if rank == 0:
-        # ---- roofline of the dominant kernel (K1 DMMA SYRK) and of the SYRK+Cholesky phase
-        n_loc = n // world if world > 1 else n
-        f_syrk = float(m) * (m + 1) * n_loc
-        f_chol = float(m) ** 3 / 3.0
-        syrk_launches = max(1, prof_sum.get("syrk_launches", 1))
-        syrk_ms = prof_sum.get("syrk_ms", 0.0) / syrk_launches
-        potrf_ms = prof_sum.get("potrf_ms", 0.0) / max(1, prof_sum.get("potrf_launches", 1))
-        achieved = f_syrk / (syrk_ms * 1e-3) * 1e-12 if syrk_ms > 0 else None
-        roofline = {
-            "bound": "tensor", "kernel": "syrk_dmma_kernel (K1, A.diag(x/z).A^T, FP64 DMMA)",
-            "achieved": achieved, "peak": NOMINAL_FP64_TFLOPS, "unit": "TFLOP/s",
-            "frac": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None, "traffic": None,
-            "peak_source": "nominal B200 FP64 (MEASURED_PEAKS.json has no FP64 entry; measured DMMA/cuBLAS "
-                           "DGEMM rates are in profiles/fp64_peaks_r01.json)",
-            "flop_per_launch": f_syrk, "ms_per_launch": syrk_ms,
-            "phase_syrk_plus_cholesky_tflops": ((f_syrk + f_chol) / ((syrk_ms + potrf_ms) * 1e-3) * 1e-12
-                                                if syrk_ms + potrf_ms > 0 else None),
-            "potrf_ms_per_launch": potrf_ms,
-            "potrf_tflops": (f_chol / (potrf_ms * 1e-3) * 1e-12) if potrf_ms > 0 else None,
-        }
+        roofline = _roofline(prof_sum, m, n_loc_rank)
         steps = args.steps
         phases = {k: prof_sum.get(k, 0.0) / steps for k in
                   ("total_ms", "syrk_ms", "potrf_ms", "solve_ms", "sweep_ms", "vector_ms", "comm_ms")}

@@ -130,6 +130,11 @@ int lpb_create_sharded_synthetic(lpb_ctx** ctx, int64_t m, int64_t n_global, int
                                  int64_t n_local, uint64_t seed, int rank, int world,
                                  const void* nccl_unique_id, void* stream);
 
+/* Copy this context's (shard of the) slack-form problem back to the host: A_out m x n_local
+ * (leading dimension lda_out >= n_local), b_out m, c_out n_local; any pointer may be NULL.
+ * (Accessors Problem::A()/b()/c(), linear_program.rs:42-54, for device-generated shards.) */
+int lpb_download_problem(lpb_ctx* ctx, double* A_out, int64_t lda_out, double* b_out, double* c_out);
+
 /* ------------------------------------------------------------------ whole solve
  * Solver::solve + solve_normal_form (interior_point/mod.rs:161-169,199-240).
  * x_out: n doubles, x/tau in SLACK form (caller drops the last n_slack entries,
@@ -232,9 +237,16 @@ typedef struct lpb_profile {
 int lpb_get_profile(lpb_ctx* ctx, lpb_profile* out);
 /* Kernels launched by this library on this context since creation (all entry points). */
 int64_t lpb_launch_count(lpb_ctx* ctx);
-/* Tuning / debug knobs ("syrk_impl": 0 = DMMA+TMA, 1 = plain DFMA reference kernel used by the
- * parity tests to bisect; "profile": 1 = record per-phase events). Unknown key -> BAD_ARGUMENT. */
+/* Tuning / debug knobs.  "syrk_impl": 0 = DMMA+TMA, 1 = plain DFMA reference kernels (parity tests
+ * bisect with it); "solve_impl": 0 = pipelined single-launch solve, 1 = one launch per 128-block
+ * step; "solve_grid_cap": > 0 caps the pipelined solve's grid (tests: several block rows per CTA);
+ * "profile": 1 = record per-phase events.  Unknown key -> BAD_ARGUMENT. */
 int lpb_set_option(lpb_ctx* ctx, const char* key, int64_t value);
+
+/* Copy a named device buffer to the host (debugging / parity tests): "M" (m x ldm), n-vectors
+ * "x" "z" "c" "rD" "dinv" "dx" "dz" "p" "u", m-vectors "b" "y" "rP" "dy", "t" / "W" (2 m).  Returns the
+ * number of doubles the buffer holds (-1: unknown name) and copies min(count, that) of them. */
+int64_t lpb_debug_read(lpb_ctx* ctx, const char* name, double* out, int64_t count);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

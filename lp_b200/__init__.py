@@ -9,6 +9,7 @@ from .api import (  # noqa: F401
     BatchedResult,
     ResidentProblem,
     ShardedProblem,
+    SyntheticShardedProblem,
     solve_batched,
     EquationSolverType,
     IncompatibleInputDimensions,
@@ -28,7 +29,7 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "BatchedResult", "ResidentProblem", "ShardedProblem", "solve_batched",
+    "BatchedResult", "ResidentProblem", "ShardedProblem", "SyntheticShardedProblem", "solve_batched",
     "EquationSolverType", "IncompatibleInputDimensions", "Infeasible", "InteriorPoint", "InteriorPointBuilder",
     "InvalidParameter", "IterationLimitExceeded", "LinearProgramError", "NumericalProblem", "OptimizeResult",
     "Problem", "ProblemBuilder", "Solver", "Unbounded", "Unconstrained",

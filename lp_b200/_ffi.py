@@ -96,6 +96,7 @@ SIGNATURES = {
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "lpb_create_sharded_synthetic": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                                C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "lpb_download_problem": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "lpb_solve": (C.c_int, [C.c_void_p, C.POINTER(lpb_options), C.c_void_p, c_double_p, c_int64_p]),
     "lpb_trace": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "lpb_blind_start": (C.c_int, [C.c_void_p]),
@@ -118,6 +119,7 @@ SIGNATURES = {
     "lpb_get_profile": (C.c_int, [C.c_void_p, C.POINTER(lpb_profile)]),
     "lpb_launch_count": (C.c_int64, [C.c_void_p]),
     "lpb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "lpb_debug_read": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
 }
 
 _lib = None

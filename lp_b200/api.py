@@ -365,8 +365,18 @@ class ResidentProblem:
         _raise_for(_ffi.load().lpb_get_profile(self.handle, C.byref(p)))
         return {k: getattr(p, k) for k, _ in p._fields_}
 
+    def debug_read(self, name: str) -> np.ndarray:
+        """Host copy of a named device buffer (lpb_debug_read)."""
+        lib = _ffi.load()
+        n = lib.lpb_debug_read(self.handle, name.encode(), None, 0)
+        if n < 0:
+            raise KeyError(name)
+        out = np.empty(n)
+        lib.lpb_debug_read(self.handle, name.encode(), out.ctypes.data, n)
+        return out
+
     def trace(self) -> np.ndarray:
-        rows = np.zeros((max(1, self.last_iterations), _ffi.LPB_TRACE_COLS))
+        rows = np.zeros((max(1, self.last_iterations + 1), _ffi.LPB_TRACE_COLS))
         k = _ffi.load().lpb_trace(self.handle, rows.ctypes.data, rows.shape[0])
         return rows[:k]
 
@@ -491,3 +501,37 @@ class ShardedProblem(ResidentProblem):
 
     def reupload(self, problem: Problem):
         raise NotImplementedError
+
+
+class SyntheticShardedProblem(ShardedProblem):
+    """Column shard of the SURVEY.md 8(d) synthetic LP generated ON THE DEVICE (config C5: the
+    34 GB matrix never exists on the host).  Slack-form m x n_global with m/2 inequality rows; the
+    generator is counter-based, so every (seed, row, column) entry is independent of the sharding and
+    any world size sees the same LP."""
+
+    def __init__(self, m: int, n_global: int, seed: int, rank: int = 0, world: int = 1, dist=None, stream: int = 0):
+        lib = _ffi.load()
+        self.m, self.n_global = int(m), int(n_global)
+        self.n_slack = self.m // 2
+        self.rank, self.world, self._dist = rank, world, dist
+        self.shards = shard_columns(self.n_global, world)
+        self.col0, self.n = self.shards[rank]
+        if self.n <= 0:
+            raise ValueError("more ranks than column blocks")
+        self.last_iterations = 0
+        self._problem = None
+        uid = self._broadcast_unique_id(lib)
+        h = C.c_void_p()
+        rc = lib.lpb_create_sharded_synthetic(C.byref(h), self.m, self.n_global, self.col0, self.n, int(seed), rank,
+                                              world, uid, C.c_void_p(stream))
+        _raise_for(rc)
+        self.handle = h
+
+    def download(self):
+        """(A_local, b, c_local) as host arrays -- parity tests hand these to the CPU oracle."""
+        A = np.empty((self.m, self.n))
+        b = np.empty(self.m)
+        c = np.empty(self.n)
+        _raise_for(_ffi.load().lpb_download_problem(self.handle, A.ctypes.data, self.n, b.ctypes.data,
+                                                    c.ctypes.data))
+        return A, b, c

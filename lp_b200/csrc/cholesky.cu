@@ -59,74 +59,208 @@ potf2_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __restr
     for (int k = tx; k <= i; k += 32) blk[(int64_t)i * ldm + k] = (k == i) ? diag[i] : S[i * LDS + k];
 }
 
-// ------------------------------------------------------------------ potf2 + in-place inverse (one CTA)
-// Factor as above, then X = inv(L_kk): column c is owned by a quad of threads; x_i for i > c is
-//   x_i = -(sum_{l=c}^{i-1} L[i][l] x_l) / L[i][i]
-// with the partial sums split over the quad (2 shuffles).  X^T is kept in the strictly upper triangle
-// of the same shared block (row c holds column c), its diagonal in rdiag.  L goes back to Mat, X to
-// Linv (dense 128 x 128, zero above the diagonal and beyond nb).
+// ------------------------------------------------------------------ potf2 + inverse of the diagonal block (one CTA)
+// This kernel sits on the critical path of every panel, so it is organised to keep the serial part
+// short: the 128 x 128 block is factored in 16-column steps; per step ONE warp factors the 16 x 16
+// diagonal sub-block entirely in registers (lane i = row i, pivots broadcast by shuffle) and inverts
+// it, then all 16 warps apply X = inv(L_dd) to the rows below (a 16-wide GEMM, no substitution chain)
+// and the rank-16 update to the remaining sub-blocks.  The full inverse X = inv(L_kk) is then built
+// block-diagonal by block-diagonal:  X_ij = -X_ii (sum_{k=j}^{i-1} L_ik X_kj),  all blocks of one
+// diagonal in parallel.  X^T lives in the strictly upper triangle of the same shared block (row c
+// holds column c of X), its diagonal in rdiag.  Rows >= nb of a ragged last panel are padded with the
+// identity so every loop is uniform.  L goes back to Mat, X to Linv (dense 128 x 128, zero above the
+// diagonal and beyond nb).  A non-positive / non-finite pivot sets *info (first one wins) and poisons
+// the block with NaN; there is no early exit.
+constexpr int SB = 16;        // sub-block
+constexpr int NSB = NB / SB;  // 8
+constexpr int XDP = SB + 1;   // pitch of the 16 x 16 inverse of the current diagonal sub-block
+constexpr int TWP = 9;        // pitch of the per-warp 16 x 8 scratch of the block-inverse step
+
 __global__ void __launch_bounds__(512)
 potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __restrict__ info,
                  double* __restrict__ Linv) {
-  extern __shared__ double S[];  // NB*LDS block + NB diag + NB rdiag
-  double* diag = S + NB * LDS;
-  double* rdiag = diag + NB;
-  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+  extern __shared__ double S[];    // NB*LDS block
+  double* rdiag = S + NB * LDS;    // NB: 1 / L[i][i]
+  double* Xd = rdiag + NB;         // SB * XDP
+  double* Tw = Xd + SB * XDP;      // 16 warps * SB * TWP
+  const int tid = threadIdx.y * 32 + threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned full = 0xffffffffu;
   double* blk = Mat + (int64_t)k0 * ldm + k0;
-  for (int i = ty; i < nb; i += 16)
-    for (int k = tx; k <= i; k += 32) S[i * LDS + k] = blk[(int64_t)i * ldm + k];
-  __syncthreads();
-
-  bool failed = false;
-  for (int j = 0; j < nb; ++j) {
-    const double ajj = S[j * LDS + j];
-    if (!(ajj > 0.0) || !isfinite(ajj)) {  // uniform: every thread reads the same shared value
-      if (tid == 0 && *info == 0) *info = k0 + j + 1;
-      for (int i = j + tid; i < nb; i += 512) {
-        diag[i] = __longlong_as_double(0x7ff8000000000000ll);
-        rdiag[i] = diag[i];
-      }
-      failed = true;
-      break;
-    }
-    const double d = sqrt(ajj);
-    const double rd = 1.0 / d;
-    if (tid == 0) {
-      diag[j] = d;
-      rdiag[j] = rd;
-    }
-    if (tid < nb - j - 1) S[(j + 1 + tid) * LDS + j] /= d;
-    __syncthreads();
-    for (int i = j + 1 + ty; i < nb; i += 16) {
-      const double lij = S[i * LDS + j];
-      for (int k = j + 1 + tx; k <= i; k += 32) S[i * LDS + k] -= lij * S[k * LDS + j];
-    }
-    __syncthreads();
+  for (int idx = tid; idx < NB * NB; idx += 512) {
+    const int r = idx >> 7, c = idx & (NB - 1);
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < nb && c <= r) v = blk[(int64_t)r * ldm + c];
+    S[r * LDS + c] = v;
   }
   __syncthreads();
-  for (int i = ty; i < nb; i += 16)
-    for (int k = tx; k <= i; k += 32) blk[(int64_t)i * ldm + k] = (k == i) ? diag[i] : S[i * LDS + k];
 
-  // ---- inverse (skipped values are still written so Linv is always defined)
-  if (!failed) {
-    const int c = tid >> 2, q = tid & 3;
-    const int i_first = (tid >> 5) * 8 + 1;  // smallest c of this warp + 1: keeps the warp's trip count uniform
-    const double xc = c < nb ? rdiag[c] : 0.0;
-    for (int i = i_first; i < nb; ++i) {
-      double s = 0.0;
-      if (c < i) {
-        for (int l = c + q; l < i; l += 4) {
-          const double xl = (l == c) ? xc : S[c * LDS + l];
-          s += S[i * LDS + l] * xl;
+  for (int kb = 0; kb < NSB; ++kb) {
+    const int c0 = kb * SB;
+    if (warp == 0) {
+      // ---- factor the 16 x 16 diagonal sub-block in registers: lane i (and its mirror i + 16) = row i
+      const int i = lane & 15;
+      double a[SB];
+#pragma unroll
+      for (int k = 0; k < SB; ++k) a[k] = (k <= i) ? S[(c0 + i) * LDS + c0 + k] : 0.0;
+      double mydiag = 1.0;
+#pragma unroll
+      for (int j = 0; j < SB; ++j) {
+        const double ajj = __shfl_sync(full, a[j], j);
+        const bool bad = !(ajj > 0.0) || !isfinite(ajj);
+        if (bad && lane == 0 && *info == 0) *info = k0 + c0 + j + 1;
+        const double d = bad ? __longlong_as_double(0x7ff8000000000000ll) : sqrt(ajj);
+        double l = a[j] / d;
+        if (i == j) {
+          l = d;
+          mydiag = d;
+        }
+        a[j] = l;
+#pragma unroll
+        for (int k = 0; k < SB; ++k) {
+          if (k > j) {  // compile-time after unrolling
+            const double lk = __shfl_sync(full, l, k);
+            a[k] -= (i >= k) ? l * lk : 0.0;
+          }
         }
       }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (c < i && q == 0) S[c * LDS + i] = -s * rdiag[i];
+      if (lane < SB) {
+#pragma unroll
+        for (int k = 0; k < SB; ++k)
+          if (k <= i) S[(c0 + i) * LDS + c0 + k] = a[k];
+      }
       __syncwarp();
+      // ---- X = inv(L_dd): lane c owns column c;  x_i = -(sum_{l<i} L[i][l] x_l) / L[i][i]
+      const double rdc = 1.0 / mydiag;
+      double x[SB];
+#pragma unroll
+      for (int r = 0; r < SB; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int l = 0; l < r; ++l) s += S[(c0 + r) * LDS + c0 + l] * x[l];
+        const double rdr = __shfl_sync(full, rdc, r);
+        x[r] = (r == i) ? rdc : ((r > i) ? -s * rdr : 0.0);
+      }
+      if (lane < SB) {
+        rdiag[c0 + i] = rdc;
+#pragma unroll
+        for (int r = 0; r < SB; ++r) {
+          Xd[r * XDP + i] = x[r];                               // X[r][c = i], zero above the diagonal
+          if (r > i) S[(c0 + i) * LDS + c0 + r] = x[r];         // X^T in the upper triangle
+        }
+      }
+    }
+    __syncthreads();
+    // ---- rows below the sub-block: P[r][c] = sum_{l<=c} S[r][c0+l] X[c][l]   (4 columns per thread)
+    {
+      const int r = c0 + SB + (tid >> 2), q = tid & 3;
+      const bool act = r < NB;
+      double out[4] = {0.0, 0.0, 0.0, 0.0};
+      if (act) {
+        double row[SB];
+#pragma unroll
+        for (int l = 0; l < SB; ++l) row[l] = S[r * LDS + c0 + l];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double* xr = Xd + (4 * q + e) * XDP;
+          double s = 0.0;
+#pragma unroll
+          for (int l = 0; l < SB; ++l) s += row[l] * xr[l];
+          out[e] = s;
+        }
+      }
+      __syncwarp();  // the four threads of a row sit in one warp: all reads of the row precede its writes
+      if (act) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) S[r * LDS + c0 + 4 * q + e] = out[e];
+      }
+    }
+    __syncthreads();
+    // ---- rank-16 update of the remaining 16 x 16 sub-blocks (lower triangle), one per warp per round
+    {
+      const int nrem = NSB - 1 - kb;
+      const int T = nrem * (nrem + 1) / 2;
+      const int ii = lane & 15, jh = lane >> 4;
+      for (int t = warp; t < T; t += 16) {
+        int bi = 0;
+        while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+        const int bj = t - bi * (bi + 1) / 2;
+        const int ri = (kb + 1 + bi) * SB + ii;
+        const int cj = (kb + 1 + bj) * SB + 8 * jh;
+        double pr[SB];
+#pragma unroll
+        for (int l = 0; l < SB; ++l) pr[l] = S[ri * LDS + c0 + l];
+        double acc[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const double* pj = S + (cj + jj) * LDS + c0;
+          double s = 0.0;
+#pragma unroll
+          for (int l = 0; l < SB; ++l) s += pr[l] * pj[l];
+          acc[jj] = s;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          if (cj + jj <= ri) S[ri * LDS + cj + jj] -= acc[jj];
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- L back to Mat
+  for (int idx = tid; idx < NB * NB; idx += 512) {
+    const int r = idx >> 7, c = idx & (NB - 1);
+    if (r < nb && c <= r) blk[(int64_t)r * ldm + c] = S[r * LDS + c];
+  }
+
+  // ---- off-diagonal blocks of X, one block diagonal at a time; block (i, j) by a pair of warps
+  {
+    const int b = warp >> 1, h = warp & 1;
+    const int ii = lane & 15, cg = lane >> 4;
+    double* tw = Tw + warp * SB * TWP;
+    for (int d = 1; d < NSB; ++d) {
+      if (b < NSB - d) {
+        const int j = b, i = b + d;
+        const int ccb = 8 * h + 4 * cg;  // first of this lane's 4 columns within block column j
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* lrow = S + (i * SB + ii) * LDS;
+        // k == j: X_jj (lower triangular; transposed in the upper triangle, diagonal in rdiag)
+#pragma unroll
+        for (int l = 0; l < SB; ++l) {
+          const double lv = lrow[j * SB + l];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int cc = ccb + e;
+            const double up = S[(j * SB + cc) * LDS + j * SB + l];
+            const double xv = (l > cc) ? up : ((l == cc) ? rdiag[j * SB + cc] : 0.0);
+            acc[e] += lv * xv;
+          }
+        }
+        for (int k = j + 1; k < i; ++k) {
+#pragma unroll
+          for (int l = 0; l < SB; ++l) {
+            const double lv = lrow[k * SB + l];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] += lv * S[(j * SB + ccb + e) * LDS + k * SB + l];
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) tw[ii * TWP + 4 * cg + e] = acc[e];
+        __syncwarp();
+        // X_ij = -X_ii T
+        double o[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int l = 0; l < SB; ++l) {
+          const double up = S[(i * SB + l) * LDS + i * SB + ii];
+          const double xv = (l < ii) ? up : ((l == ii) ? rdiag[i * SB + ii] : 0.0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] += xv * tw[l * TWP + 4 * cg + e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) S[(j * SB + ccb + e) * LDS + i * SB + ii] = -o[e];
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();
   for (int idx = tid; idx < NB * NB; idx += 512) {
     const int i = idx >> 7, c = idx & (NB - 1);
     double v = 0.0;
@@ -451,6 +585,246 @@ solve_bwd_step_kernel(const double* __restrict__ L, int64_t ldm, const double* _
   }
 }
 
+// ------------------------------------------------------------------ K3 v3: pipelined solve, ONE launch
+// L L^T X = B for 1 or 2 right-hand sides in a single cooperative kernel.  Block row j (128 rows) is
+// owned by CTA j mod gridDim.x; CTAs exchange the 128-entry solution blocks through global memory and
+// per-block flags (release / acquire at gpu scope), so the only serial chain is
+//     w_{j-1} published -> CTA j applies L[j][j-1] w_{j-1}, multiplies by inv(L_jj), publishes w_j
+// (~3 us per block instead of one kernel launch per block), while every other block product
+// L[j][k] w_k, k < j-1, is consumed as soon as w_k exists -- each CTA runs ahead of the chain.
+// Warps are autonomous inside the sweep over k (each polls the flag itself: no CTA barrier per block).
+// Forward:  warp = 16 rows, lane = 4 columns; per-lane partial sums are kept over ALL k and folded
+//           across lanes once per block row (multi-value butterfly: 16 shuffles for 16 rows).
+// Backward: the same loads of L[k][j] (rows of block k, columns of block j), accumulated per column;
+//           the 8 warps are folded through shared memory.
+// Co-residency of all CTAs is what makes the flag waits safe: the launch is cooperative and the grid
+// is capped at the number of CTAs the device can hold.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Bounded: a lost flag traps after ~2 s instead of hanging the GPU.
+// `relaxed` pollers (blocks that are not next in the chain) back off so that up to ~1000 warps
+// spinning on one L2 line do not delay the release store they are waiting for.
+__device__ __forceinline__ void wait_flag(const int* flag, int epoch, bool relaxed = false) {
+  if (ld_acquire_gpu(flag) == epoch) return;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(flag) != epoch) {
+    if (relaxed) __nanosleep(256);
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+// Per-lane partials of 16 rows -> total of row (lane >> 1) in every lane (pairs hold copies).
+__device__ __forceinline__ double fold16(double (&v)[16], int lane) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int w = 8; w >= 1; w >>= 1) {
+    const bool up = (lane & (2 * w)) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const double send = up ? v[i] : v[i + w];
+      const double keep = up ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(full, send, 2 * w);
+    }
+  }
+  return v[0] + __shfl_xor_sync(full, v[0], 1);
+}
+
+constexpr int kSolveThreads = 256;
+constexpr size_t kSolveSmem = (size_t)(NB * NB + 2 * 2 * NB + 8 * 2 * NB) * sizeof(double);
+
+template <int NRHS>
+__global__ void __launch_bounds__(kSolveThreads, 1)
+solve_pipelined_kernel(const double* __restrict__ L, int64_t ldm, const double* __restrict__ Linv_all, int64_t m,
+                       int nblk, double* B, double* Y, int64_t ldy, int* flags_f, int* flags_b, int epoch) {
+  extern __shared__ __align__(16) double sm[];
+  double* sLinv = sm;                 // 128 x 128, ld 128
+  double* sc = sLinv + NB * NB;       // [2][128] reduced right-hand side of the current block
+  double* sx = sc + 2 * NB;           // [2][128] solution of the current block
+  double* sred = sx + 2 * NB;         // [8 warps][2][128] backward cross-warp fold
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c4 = 4 * lane;            // this lane's 4 columns inside a 128-wide block
+
+  // ============================================================ forward: L w = b
+  for (int j = blockIdx.x; j < nblk; j += gridDim.x) {
+    const int64_t r0 = (int64_t)j * NB;
+    const int nbj = (int)((m - r0) < NB ? (m - r0) : NB);
+    {  // inv(L_jj) -> shared (needed only after the sweep: its latency hides behind it)
+      const double2* src = reinterpret_cast<const double2*>(Linv_all + (int64_t)j * NB * NB);
+      double2* dst = reinterpret_cast<double2*>(sLinv);
+      for (int idx = tid; idx < NB * NB / 2; idx += kSolveThreads) dst[idx] = __ldg(src + idx);
+    }
+    double acc[NRHS][16];
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[q][i] = 0.0;
+    const int64_t rw = r0 + warp * 16;  // first row of this warp
+    for (int k = 0; k < j; ++k) {
+      const int64_t k0 = (int64_t)k * NB;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        double2 la[8], lb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t r = rw + half * 8 + i;
+          la[i] = lb[i] = make_double2(0.0, 0.0);
+          if (r < m) {
+            const double2* p = reinterpret_cast<const double2*>(L + r * ldm + k0 + c4);
+            la[i] = __ldg(p);
+            lb[i] = __ldg(p + 1);
+          }
+        }
+        if (half == 0) wait_flag(flags_f + k, epoch, k + 1 < j);
+        double2 wa[NRHS], wb[NRHS];
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q) {
+          const double2* p = reinterpret_cast<const double2*>(Y + (int64_t)q * ldy + k0 + c4);
+          wa[q] = __ldcg(p);
+          wb[q] = __ldcg(p + 1);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int q = 0; q < NRHS; ++q)
+            acc[q][half * 8 + i] += la[i].x * wa[q].x + la[i].y * wa[q].y + lb[i].x * wb[q].x + lb[i].y * wb[q].y;
+      }
+    }
+    // fold across lanes; c = b - sum
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q) {
+      const double tot = fold16(acc[q], lane);
+      const int rr = warp * 16 + (lane >> 1);
+      if ((lane & 1) == 0) sc[q * NB + rr] = (rr < nbj) ? B[(int64_t)q * m + r0 + rr] - tot : 0.0;
+    }
+    __syncthreads();
+    // w = inv(L_jj) c  (rows of this warp, lanes over columns)
+    {
+      double part[NRHS][16];
+      double4 cv[NRHS];
+#pragma unroll
+      for (int q = 0; q < NRHS; ++q) cv[q] = *reinterpret_cast<const double4*>(sc + q * NB + c4);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const double4 lv = *reinterpret_cast<const double4*>(sLinv + (warp * 16 + i) * NB + c4);
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q)
+          part[q][i] = lv.x * cv[q].x + lv.y * cv[q].y + lv.z * cv[q].z + lv.w * cv[q].w;
+      }
+#pragma unroll
+      for (int q = 0; q < NRHS; ++q) {
+        const double tot = fold16(part[q], lane);
+        const int rr = warp * 16 + (lane >> 1);
+        if ((lane & 1) == 0 && rr < nbj) Y[(int64_t)q * ldy + r0 + rr] = tot;
+      }
+    }
+    __syncthreads();  // all of w_j written (and sLinv / sc free for the next block row)
+    if (tid == 0) {
+      __threadfence();
+      st_release_gpu(flags_f + j, epoch);
+    }
+  }
+
+  // ============================================================ backward: L^T x = w
+  for (int j = nblk - 1 - blockIdx.x; j >= 0; j -= gridDim.x) {
+    const int64_t j0 = (int64_t)j * NB;
+    const int nbj = (int)((m - j0) < NB ? (m - j0) : NB);
+    __syncthreads();  // previous users of sLinv / sred are done
+    {
+      const double2* src = reinterpret_cast<const double2*>(Linv_all + (int64_t)j * NB * NB);
+      double2* dst = reinterpret_cast<double2*>(sLinv);
+      for (int idx = tid; idx < NB * NB / 2; idx += kSolveThreads) dst[idx] = __ldg(src + idx);
+    }
+    double acc[NRHS][4];
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
+    for (int k = nblk - 1; k > j; --k) {
+      const int64_t k0 = (int64_t)k * NB;
+      const int64_t rw = k0 + warp * 16;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        double2 la[8], lb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t r = rw + half * 8 + i;
+          la[i] = lb[i] = make_double2(0.0, 0.0);
+          if (r < m) {
+            const double2* p = reinterpret_cast<const double2*>(L + r * ldm + j0 + c4);
+            la[i] = __ldg(p);
+            lb[i] = __ldg(p + 1);
+          }
+        }
+        if (half == 0) wait_flag(flags_b + k, epoch, k - 1 > j);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t r = rw + half * 8 + i;
+#pragma unroll
+          for (int q = 0; q < NRHS; ++q) {
+            const double xv = (r < m) ? __ldcg(B + (int64_t)q * m + r) : 0.0;
+            acc[q][0] += la[i].x * xv;
+            acc[q][1] += la[i].y * xv;
+            acc[q][2] += lb[i].x * xv;
+            acc[q][3] += lb[i].y * xv;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q)
+      *reinterpret_cast<double4*>(sred + (warp * 2 + q) * NB + c4) = make_double4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+    __syncthreads();
+    if (tid < NRHS * NB) {  // c = w_j - sum over the 8 warps
+      wait_flag(flags_f + j, epoch);  // w_j may come from another CTA (forward owner j mod G)
+      const int q = tid >> 7, c = tid & (NB - 1);
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += sred[(w * 2 + q) * NB + c];
+      sc[q * NB + c] = (c < nbj) ? __ldcg(Y + (int64_t)q * ldy + j0 + c) - s : 0.0;
+    }
+    __syncthreads();
+    // x = inv(L_jj)^T c : x[c] = sum_r Linv[r][c] c[r]; warp = 16 rows, lane = 4 columns
+    {
+      double xa[NRHS][4];
+#pragma unroll
+      for (int q = 0; q < NRHS; ++q) xa[q][0] = xa[q][1] = xa[q][2] = xa[q][3] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = warp * 16 + i;
+        const double4 lv = *reinterpret_cast<const double4*>(sLinv + r * NB + c4);
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q) {
+          const double cr = sc[q * NB + r];
+          xa[q][0] += lv.x * cr;
+          xa[q][1] += lv.y * cr;
+          xa[q][2] += lv.z * cr;
+          xa[q][3] += lv.w * cr;
+        }
+      }
+      __syncthreads();  // sred is re-used
+#pragma unroll
+      for (int q = 0; q < NRHS; ++q)
+        *reinterpret_cast<double4*>(sred + (warp * 2 + q) * NB + c4) = make_double4(xa[q][0], xa[q][1], xa[q][2], xa[q][3]);
+    }
+    __syncthreads();
+    if (tid < NRHS * NB) {
+      const int q = tid >> 7, c = tid & (NB - 1);
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += sred[(w * 2 + q) * NB + c];
+      if (c < nbj) B[(int64_t)q * m + j0 + c] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      st_release_gpu(flags_b + j, epoch);
+    }
+  }
+}
+
 template <typename K>
 int set_smem(K kern, size_t bytes) {
   LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -458,7 +832,7 @@ int set_smem(K kern, size_t bytes) {
 }
 
 constexpr size_t kPotf2Smem = (size_t)(NB * LDS + NB) * sizeof(double);
-constexpr size_t kPotf2InvSmem = (size_t)(NB * LDS + 2 * NB) * sizeof(double);
+constexpr size_t kPotf2InvSmem = (size_t)(NB * LDS + NB + SB * XDP + 16 * SB * TWP) * sizeof(double);
 constexpr size_t kTrsmSmem = (size_t)((NB + TRSM_ROWS) * LDS) * sizeof(double);
 constexpr size_t kTrsvSmem = (size_t)(NB * LDS + NB + 2 * NB) * sizeof(double);
 
@@ -487,13 +861,14 @@ int configure_once() {
 // Workspace: one dense 128 x 128 inverse per diagonal block + a scratch right-hand side (2 m).
 static int ensure_chol_ws(LaunchCtx& lc, int64_t m) {
   const int64_t nblk = ceil_div(m, NB);
-  const int64_t need = nblk * NB * NB + 2 * round_up(m, 2);
+  const int64_t need = nblk * NB * NB + 2 * round_up(m, 2) + nblk;  // + 2 nblk int flags of the pipelined solve
   if (lc.chol_ws_cap >= need) return LPB_OK;
   if (lc.chol_ws) cudaFree(lc.chol_ws);
   lc.chol_ws = nullptr;
   lc.chol_ws_cap = 0;
   void* p = nullptr;
   LPB_CUDA(cudaMalloc(&p, sizeof(double) * (size_t)need));
+  LPB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * (size_t)need, lc.stream));  // flags start below any epoch
   lc.chol_ws = static_cast<double*>(p);
   lc.chol_ws_cap = need;
   return LPB_OK;
@@ -549,6 +924,39 @@ static int potrs_fused(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, d
   return LPB_OK;
 }
 
+// One cooperative launch for the whole solve (see solve_pipelined_kernel).
+template <int NRHS>
+static int potrs_pipelined(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B) {
+  static int max_ctas = 0;
+  auto kern = solve_pipelined_kernel<NRHS>;
+  if (max_ctas == 0) {
+    LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmem));
+    int dev = 0, sms = 0, per_sm = 0;
+    LPB_CUDA(cudaGetDevice(&dev));
+    LPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    LPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSolveThreads, kSolveSmem));
+    if (per_sm < 1) {
+      set_last_error("solve_pipelined_kernel does not fit on this device");
+      return LPB_ERR_CUDA;
+    }
+    max_ctas = sms * per_sm;
+  }
+  int nblk = (int)ceil_div(m, NB);
+  double* Y = lc.chol_ws + (int64_t)nblk * NB * NB;
+  int64_t ldy = round_up(m, 2);
+  int* flags_f = reinterpret_cast<int*>(Y + 2 * ldy);
+  int* flags_b = flags_f + nblk;
+  int epoch = ++lc.solve_epoch;
+  const double* linv = lc.chol_ws;
+  void* args[] = {(void*)&L, (void*)&ldm, (void*)&linv, (void*)&m, (void*)&nblk, (void*)&B,
+                  (void*)&Y, (void*)&ldy, (void*)&flags_f, (void*)&flags_b, (void*)&epoch};
+  int grid = nblk < max_ctas ? nblk : max_ctas;
+  if (lc.solve_grid_cap > 0 && grid > lc.solve_grid_cap) grid = lc.solve_grid_cap;
+  LPB_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kSolveThreads), args, kSolveSmem, lc.stream));
+  lc.launches++;
+  return LPB_OK;
+}
+
 template <int NRHS>
 static int potrs_impl(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B) {
   const int nblk = (int)ceil_div(m, NB);
@@ -582,8 +990,13 @@ static int potrs_impl(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, do
 int k_potrs(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B, int nrhs, bool use_linv) {
   LPB_TRY(configure_once());
   if (use_linv && lc.linv_valid_m == m && lc.linv_mat == L && lc.chol_ws) {
-    if (nrhs == 1) return potrs_fused<1>(lc, m, L, ldm, B);
-    if (nrhs == 2) return potrs_fused<2>(lc, m, L, ldm, B);
+    if (lc.solve_impl == 1) {  // one launch per 128-block step (kept for bisecting)
+      if (nrhs == 1) return potrs_fused<1>(lc, m, L, ldm, B);
+      if (nrhs == 2) return potrs_fused<2>(lc, m, L, ldm, B);
+    } else {
+      if (nrhs == 1) return potrs_pipelined<1>(lc, m, L, ldm, B);
+      if (nrhs == 2) return potrs_pipelined<2>(lc, m, L, ldm, B);
+    }
   } else {
     if (nrhs == 1) return potrs_impl<1>(lc, m, L, ldm, B);
     if (nrhs == 2) return potrs_impl<2>(lc, m, L, ldm, B);

@@ -52,6 +52,9 @@ struct LaunchCtx {
   int64_t chol_ws_cap = 0;         // in doubles
   int64_t linv_valid_m = -1;       // order of the matrix whose block inverses chol_ws holds
   const double* linv_mat = nullptr; // ... and its address
+  int solve_epoch = 0;             // flag value of the next pipelined solve (cholesky.cu)
+  int solve_impl = 0;              // 0 = pipelined single launch, 1 = one launch per block step
+  int solve_grid_cap = 0;          // > 0: cap the pipelined solve's grid (tests: several block rows per CTA)
   int* info_dev = nullptr;         // potrf info flag
   int* info_host = nullptr;        // pinned
 };

@@ -95,5 +95,8 @@ int k_fill_vec(LaunchCtx& lc, double* v, int64_t count, int64_t idx0, uint64_t s
                int64_t neg_below);
 int k_slack_identity(LaunchCtx& lc, double* A, int64_t rows, int64_t cols, int64_t lda, int64_t col0, int64_t n0);
 int k_add_vec(LaunchCtx& lc, double* out, const double* a, const double* b, int64_t count, int64_t count_b);
+// order-independent bit checksum of a matrix block (replica-agreement checks of the sharded path)
+int k_checksum(LaunchCtx& lc, const double* v, int64_t rows, int64_t cols, int64_t ld, int lower_only,
+               unsigned long long* out_dev);
 
 }  // namespace lpb

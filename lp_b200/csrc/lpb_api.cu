@@ -50,6 +50,9 @@ struct lpb_ctx {
   bool profile = true;
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
+  bool check_replicas = false;          // debug: compare checksums of replicated buffers across ranks
+  unsigned long long* chk_dev = nullptr;  // 2 words: {checksum, ~checksum}
+  unsigned long long* chk_host = nullptr; // pinned
   SolveOutput last;
   lpb_profile prof;
   std::vector<cudaEvent_t> ev_free;
@@ -138,6 +141,27 @@ int allreduce(lpb_ctx* c, double* buf, int64_t count, ncclRedOp_t op) {
   return LPB_OK;
 }
 
+// Debug (option "check_replicas"): every rank must hold the same bits of a replicated buffer.  All
+// ranks learn the verdict from the same all-reduce, so a divergence is reported on every rank at once
+// instead of dead-locking the ranks that carry on.
+int check_replicated(lpb_ctx* c, const char* what, const double* v, int64_t rows, int64_t cols, int64_t ld, int lower) {
+  if (c->world <= 1 || !c->check_replicas) return LPB_OK;
+  LPB_TRY(k_checksum(c->lc, v, rows, cols, ld, lower, c->chk_dev));
+  LPB_CUDA(cudaMemcpyAsync(c->chk_dev + 1, c->chk_dev, sizeof(unsigned long long), cudaMemcpyDeviceToDevice,
+                           c->lc.stream));
+  LPB_NCCL(ncclAllReduce(c->chk_dev, c->chk_dev, 1, ncclUint64, ncclMin, c->comm, c->lc.stream));
+  LPB_NCCL(ncclAllReduce(c->chk_dev + 1, c->chk_dev + 1, 1, ncclUint64, ncclMax, c->comm, c->lc.stream));
+  LPB_CUDA(cudaMemcpyAsync(c->chk_host, c->chk_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                           c->lc.stream));
+  LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+  if (c->chk_host[0] != c->chk_host[1]) {
+    set_last_error("replicas diverged: %s differs between ranks (iteration %lld)", what,
+                   (long long)c->prof.syrk_launches);
+    return LPB_ERR_NCCL;
+  }
+  return LPB_OK;
+}
+
 // Fold partials, all-reduce the first `n_sharded` values (they are sums / mins over this rank's
 // columns), fetch all `nvals` to the host.
 int finish_scalars(lpb_ctx* c, const RedSpec& spec, int n_sharded, ncclRedOp_t op) {
@@ -168,6 +192,8 @@ struct CudaDev {
       LPB_TRY(k_gemv_n(c->lc, c->m, c->n, c->A, c->lda, nullptr, c->x, nullptr, c->t, nullptr, 1));
     }
     LPB_TRY(allreduce(c, c->t, c->m, ncclSum));
+    LPB_TRY(check_replicated(c, "A x after the all-reduce", c->t, 1, c->m, c->m, 0));
+    LPB_TRY(check_replicated(c, "y", c->y, 1, c->m, c->m, 0));
     {
       PhaseTimer tm(c, PH_SWEEP);
       LPB_TRY(k_resid_p(c->lc, c->m, tau, c->b, c->t, c->y, c->rP, 3, &nb_m));
@@ -200,10 +226,16 @@ struct CudaDev {
       c->prof.syrk_launches++;
     }
     LPB_TRY(allreduce(c, c->M, c->m * c->ldm, ncclSum));
+    LPB_TRY(check_replicated(c, "M after the all-reduce", c->M, c->m, c->m, c->ldm, 1));
     {
       PhaseTimer tm(c, PH_POTRF);
       LPB_TRY(k_potrf(c->lc, c->m, c->M, c->ldm, c->syrk_impl));
       c->prof.potrf_launches++;
+    }
+    LPB_TRY(check_replicated(c, "the Cholesky factor", c->M, c->m, c->m, c->ldm, 1));
+    if (c->world > 1) {  // every rank must take the same branch on a failed factorisation
+      PhaseTimer tm(c, PH_COMM);
+      LPB_NCCL(ncclAllReduce(c->lc.info_dev, c->lc.info_dev, 1, ncclInt32, ncclMax, c->comm, c->lc.stream));
     }
     LPB_CUDA(cudaMemcpyAsync(c->lc.info_host, c->lc.info_dev, sizeof(int), cudaMemcpyDeviceToHost, c->lc.stream));
     LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
@@ -232,6 +264,7 @@ struct CudaDev {
       LPB_TRY(k_gemv_n(c->lc, c->m, c->n, c->A, c->lda, c->dinv, c->r1, c->c, c->t, c->t + c->m, nrhs));
     }
     LPB_TRY(allreduce(c, c->t, c->m * nrhs, ncclSum));
+    LPB_TRY(check_replicated(c, "A (Dinv r1) after the all-reduce", c->t, 1, c->m * nrhs, c->m * nrhs, 0));
     {
       PhaseTimer tm(c, PH_VEC);
       LPB_TRY(k_sym_fwd_rhs(c->lc, c->m, in.eta, c->rP, c->b, c->t, c->t + c->m, W0, W1, with_pq));
@@ -240,6 +273,7 @@ struct CudaDev {
       PhaseTimer tm(c, PH_SOLVE);
       LPB_TRY(k_potrs(c->lc, c->m, c->M, c->ldm, c->W, nrhs, c->syrk_impl == 0));
     }
+    LPB_TRY(check_replicated(c, "the solve output (v, q)", c->W, 1, c->m * nrhs, c->m * nrhs, 0));
     RedSpec spec;
     spec.nvals = 6;
     int nchunks = 0, nb_n = 0, nb_m = 0;
@@ -333,6 +367,10 @@ int ctx_base_init(lpb_ctx* c, void* stream) {
   LPB_CUDA(cudaMalloc(&q, sizeof(int)));
   c->allocs.push_back(q);
   c->lc.info_dev = static_cast<int*>(q);
+  LPB_CUDA(cudaMalloc(&q, 2 * sizeof(unsigned long long)));
+  c->allocs.push_back(q);
+  c->chk_dev = static_cast<unsigned long long*>(q);
+  LPB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->chk_host), 2 * sizeof(unsigned long long)));
   std::memset(&c->prof, 0, sizeof(c->prof));
   return LPB_OK;
 }
@@ -390,6 +428,7 @@ void ctx_free(lpb_ctx* c) {
   if (c->lc.chol_ws) cudaFree(c->lc.chol_ws);
   if (c->lc.red_host) cudaFreeHost(c->lc.red_host);
   if (c->lc.info_host) cudaFreeHost(c->lc.info_host);
+  if (c->chk_host) cudaFreeHost(c->chk_host);
   if (c->own_stream && c->lc.stream) cudaStreamDestroy(c->lc.stream);
   delete c;
 }
@@ -646,6 +685,51 @@ int lpb_create_sharded_synthetic(lpb_ctx** out, int64_t m, int64_t n_global, int
   return LPB_OK;
 }
 
+// Copy this context's (shard of the) problem back to host memory: A_out m x n_local (leading
+// dimension lda_out), b_out m, c_out n_local.  Any pointer may be NULL.  Parity tests use it to hand
+// the device-generated synthetic shards to the CPU oracle.
+int lpb_download_problem(lpb_ctx* c, double* A_out, int64_t lda_out, double* b_out, double* c_out) {
+  LPB_TRY(need_problem(c));
+  if (A_out && lda_out < c->n) {
+    set_last_error("download_problem: lda_out < n_local");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  if (A_out)
+    LPB_CUDA(cudaMemcpy2DAsync(A_out, sizeof(double) * lda_out, c->A, sizeof(double) * c->lda, sizeof(double) * c->n,
+                               c->m, cudaMemcpyDeviceToHost, c->lc.stream));
+  if (b_out) LPB_CUDA(cudaMemcpyAsync(b_out, c->b, sizeof(double) * c->m, cudaMemcpyDeviceToHost, c->lc.stream));
+  if (c_out) LPB_CUDA(cudaMemcpyAsync(c_out, c->c, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->lc.stream));
+  LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+  return LPB_OK;
+}
+
+// Copy a named device buffer of the context to the host (debugging / parity tests): "M" (m x ldm,
+// the normal matrix or its factor), the n-vectors x z c rD dinv dx dz p u and the m-vectors b y rP dy.
+// Returns the number of doubles the buffer holds; copies min(count, that) of them.
+int64_t lpb_debug_read(lpb_ctx* c, const char* name, double* out, int64_t count) {
+  if (!c || !name || !c->A) return -1;
+  const std::string k(name);
+  struct Ent { const char* n; const double* p; int64_t len; };
+  const Ent tab[] = {{"M", c->M, c->m * c->ldm}, {"x", c->x, c->n}, {"z", c->z, c->n}, {"c", c->c, c->n},
+                     {"rD", c->rD, c->n}, {"dinv", c->dinv, c->n}, {"dx", c->dx, c->n}, {"dz", c->dz, c->n},
+                     {"p", c->p, c->n}, {"u", c->u, c->n}, {"b", c->b, c->m}, {"y", c->y, c->m},
+                     {"rP", c->rP, c->m}, {"dy", c->dy, c->m}, {"t", c->t, 2 * c->m}, {"W", c->W, 2 * c->m}};
+  for (const Ent& e : tab) {
+    if (k != e.n) continue;
+    const int64_t cnt = std::min(count, e.len);
+    if (out && cnt > 0) {
+      if (cudaMemcpyAsync(out, e.p, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, c->lc.stream) != cudaSuccess ||
+          cudaStreamSynchronize(c->lc.stream) != cudaSuccess) {
+        set_last_error("debug_read: copy failed");
+        return -1;
+      }
+    }
+    return e.len;
+  }
+  set_last_error("debug_read: unknown buffer '%s'", name);
+  return -1;
+}
+
 // ---------------------------------------------------------------- phases
 int lpb_blind_start(lpb_ctx* c) {
   LPB_TRY(need_problem(c));
@@ -858,6 +942,20 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
   if (k == "syrk_impl") {
     if (value != 0 && value != 1) return LPB_ERR_BAD_ARGUMENT;
     c->syrk_impl = (int)value;
+    return LPB_OK;
+  }
+  if (k == "solve_impl") {
+    if (value != 0 && value != 1) return LPB_ERR_BAD_ARGUMENT;
+    c->lc.solve_impl = (int)value;
+    return LPB_OK;
+  }
+  if (k == "solve_grid_cap") {
+    if (value < 0) return LPB_ERR_BAD_ARGUMENT;
+    c->lc.solve_grid_cap = (int)value;
+    return LPB_OK;
+  }
+  if (k == "check_replicas") {
+    c->check_replicas = value != 0;
     return LPB_OK;
   }
   if (k == "profile") {

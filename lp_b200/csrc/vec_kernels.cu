@@ -671,4 +671,31 @@ int k_fill_normal(LaunchCtx& lc, double* A, int64_t rows, int64_t cols, int64_t 
   return LPB_OK;
 }
 
+
+// Order-independent 64-bit checksum of a (rows x cols, leading dimension ld) block of doubles: sum over
+// entries of bits * (odd multiplier of the position), wrapping.  Integer atomics, so the value does not
+// depend on scheduling; replicas of the sharded path compare it to prove they hold identical bits.
+__global__ void checksum_kernel(const double* __restrict__ v, int64_t rows, int64_t cols, int64_t ld, int lower_only,
+                                unsigned long long* __restrict__ out) {
+  unsigned long long h = 0;
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    if (lower_only && c > r) continue;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v[r * ld + c]);
+    h += bits * (2ull * (unsigned long long)i + 0x9E3779B97F4A7C15ull);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, h);
+}
+int k_checksum(LaunchCtx& lc, const double* v, int64_t rows, int64_t cols, int64_t ld, int lower_only,
+               unsigned long long* out_dev) {
+  LPB_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(unsigned long long), lc.stream));
+  if (rows <= 0 || cols <= 0) return LPB_OK;
+  checksum_kernel<<<kNumSMs * 8, 256, 0, lc.stream>>>(v, rows, cols, ld, lower_only, out_dev);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
 }  // namespace lpb

@@ -44,7 +44,7 @@ def test_syrk_adat_matches_numpy(m, n, impl, scaled):
 
 
 @pytest.mark.parametrize("impl", [0, 1])
-@pytest.mark.parametrize("m", [5, 64, 128, 129, 200, 384, 1000, 1536])
+@pytest.mark.parametrize("m", [1, 5, 16, 17, 64, 128, 129, 200, 384, 1000, 1536])
 def test_potrf_matches_lapack(m, impl):
     """K2 vs numpy.linalg.cholesky (LAPACK potrf); ||L L^T - M|| / ||M|| < 1e-13 and L close to LAPACK's."""
     rng = np.random.default_rng(m)
@@ -116,11 +116,13 @@ def test_gemv_sweeps_match_numpy(m, n):
     assert (np.abs(o_t.cpu().numpy() - A.T @ v) / (np.abs(A.T) @ np.abs(v))).max() < 1e-13
 
 
+@pytest.mark.parametrize("solve_impl,grid_cap", [(0, 0), (0, 3), (0, 1), (1, 0)])
 @pytest.mark.parametrize("nrhs", [1, 2])
-@pytest.mark.parametrize("m", [64, 128, 200, 640, 1537])
-def test_potrf_then_fused_potrs(m, nrhs):
-    """K2 + K3 fast path: factor on the device, then solve with the stored inverted diagonal blocks;
-    residual ||M x - b|| / (||M|| ||x||) < 1e-13 and x close to LAPACK's."""
+@pytest.mark.parametrize("m", [1, 17, 64, 128, 200, 640, 1537, 2305])
+def test_potrf_then_fused_potrs(m, nrhs, solve_impl, grid_cap):
+    """K2 + K3 fast path: factor on the device, then solve with the stored inverted diagonal blocks
+    (pipelined single-launch kernel, also with its grid capped so one CTA owns several block rows, and
+    the one-launch-per-block variant); residual ||M x - b|| / (||M|| ||x||) < 1e-13, x close to LAPACK's."""
     from scipy.linalg import cho_factor, cho_solve
     rng = np.random.default_rng(3 * m + nrhs)
     Bm = rng.standard_normal((m, m + 8))
@@ -130,9 +132,15 @@ def test_potrf_then_fused_potrs(m, nrhs):
     dM, dB = to_dev(Mp), to_dev(rhs)
     info = C.c_int32(-1)
     with BareCtx(m, m) as ctx:
+        ctx.set("solve_impl", solve_impl)
+        ctx.set("solve_grid_cap", grid_cap)
         ok(ctx.lib.lpb_k_potrf(ctx.h, m, dM.data_ptr(), ldm, C.byref(info)))
         assert info.value == 0
         ok(ctx.lib.lpb_k_potrs(ctx.h, m, dM.data_ptr(), ldm, dB.data_ptr(), nrhs))
+        if solve_impl == 0:  # a second solve on the same context: the flag epoch advances
+            dB2 = to_dev(rhs)
+            ok(ctx.lib.lpb_k_potrs(ctx.h, m, dM.data_ptr(), ldm, dB2.data_ptr(), nrhs))
+            assert np.array_equal(dB2.cpu().numpy(), dB.cpu().numpy())
     X = dB.cpu().numpy()
     ref = cho_solve(cho_factor(M, lower=True), rhs.T).T
     assert np.abs(X - ref).max() / np.abs(ref).max() < 1e-9

@@ -160,7 +160,8 @@ def test_host_driven_phase_calls_equal_lpb_solve():
             axz = (C.c_double * 2)()
             assert lib.lpb_assemble_delta(h, d_tau, axz) == 0
             alpha = step(axz, d_tau, d_kappa, 1.0)
-            gamma = 10.0 if ip else (1 - alpha) ** 2 * min(0.1, 1 - alpha)
+            one_m = 1.0 - alpha  # (one_m * one_m), not pow(): libm's pow is not correctly rounded
+            gamma = 10.0 if ip else (one_m * one_m) * min(0.1, one_m)
             eta = 1.0 if ip else 1.0 - gamma
             if ip:
                 tk = (1.0 - alpha) * gamma * mu - tau * kappa - alpha * alpha * d_tau * d_kappa
