@@ -144,8 +144,9 @@ int lpb_download_problem(lpb_ctx* ctx, double* A_out, int64_t lda_out, double* b
 int lpb_solve(lpb_ctx* ctx, const lpb_options* opts, double* x_out, double* fun, int64_t* iterations);
 
 /* Per-iteration trace of the last lpb_solve (the `disp` columns of indicators.rs:25-33 plus tau,
- * kappa): rows of LPB_TRACE_COLS doubles {alpha, rho_p, rho_d, rho_A, rho_g, rho_mu, obj, bty, tau, kappa}. */
-#define LPB_TRACE_COLS 10
+ * kappa and the scalars of the corrector's Delta::compute, delta.rs:29-38): rows of LPB_TRACE_COLS
+ * doubles {alpha, rho_p, rho_d, rho_A, rho_g, rho_mu, obj, bty, tau, kappa, c.p, b.q, c.u, b.v, d_tau, d_kappa}. */
+#define LPB_TRACE_COLS 16
 int64_t lpb_trace(lpb_ctx* ctx, double* rows, int64_t max_rows);
 
 /* ------------------------------------------------------------------ phase calls

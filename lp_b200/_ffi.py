@@ -31,7 +31,7 @@ LPB_SOLVER_LEAST_SQUARES = 2
 
 LPB_MEM_HOST = 0
 LPB_MEM_DEVICE = 1
-LPB_TRACE_COLS = 10
+LPB_TRACE_COLS = 16
 
 c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)

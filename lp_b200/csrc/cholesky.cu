@@ -312,6 +312,96 @@ trsm_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int m) {
     for (int k = tx; k < nb; k += 32) pan[(int64_t)r * ldm + k] = SB[r * LDS + k];
 }
 
+// ------------------------------------------------------------------ panel TRSM, blocked substitution
+// X L_kk^T = P for 64 panel rows per CTA.  L_kk is applied as 8 sub-block steps of 16 columns:
+//     P[:, s] = T[:, s] inv(L_ss)^T ,   T[:, j] -= P[:, s] L[j][s]^T  for the later sub-blocks j,
+// i.e. substitution between the 16-column sub-blocks and a 16 x 16 explicit inverse (the diagonal
+// blocks of Linv, by-products of potf2_inv_kernel) inside each.  A GEMM with the full 128 x 128 inverse
+// is faster on paper but NOT backward stable: late in the interior-point iteration, when M is very
+// ill-conditioned, it perturbed d_tau enough to cost 3-4 extra iterations against the CPU oracle
+// (C3: 28 instead of 24); with this form the trajectory follows the oracle's.  Plain DFMA: the whole
+// TRSM is 128 m flop per panel column, ~1 % of the factorisation.
+constexpr int TBR = 64;            // panel rows per CTA
+constexpr int LDP = NB + 2;        // even pitch: 16-byte aligned double2 rows, conflict-free for 4-row groups
+constexpr size_t kTrsmBlockedSmem = (size_t)((NB + TBR) * LDP + NSB * SB * XDP) * sizeof(double);
+
+__global__ void __launch_bounds__(256)
+trsm_blocked_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int m, const double* __restrict__ Linv) {
+  extern __shared__ __align__(16) double sm[];
+  double* SL = sm;                      // NB * LDP : L_kk (lower triangle incl. diagonal)
+  double* SP = SL + NB * LDP;           // TBR * LDP: panel rows
+  double* SX = SP + TBR * LDP;          // NSB * SB * XDP: inv(L_ss), s = 0..7
+  const int tid = threadIdx.x;
+  const int64_t r0 = (int64_t)k0 + NB + (int64_t)blockIdx.x * TBR;
+  const double* lkk = Mat + (int64_t)k0 * ldm + k0;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int i = idx >> 7, c = idx & (NB - 1);
+    if (c <= i) SL[i * LDP + c] = lkk[(int64_t)i * ldm + c];
+  }
+  for (int idx = tid; idx < NSB * SB * SB; idx += 256) {
+    const int sblk = idx >> 8, i = (idx >> 4) & 15, l = idx & 15;
+    SX[(sblk * SB + i) * XDP + l] = Linv[(sblk * SB + i) * NB + sblk * SB + l];
+  }
+  for (int idx = tid; idx < TBR * NB; idx += 256) {
+    const int r = idx >> 7, c = idx & (NB - 1);
+    SP[r * LDP + c] = (r0 + r < m) ? Mat[(r0 + r) * ldm + k0 + c] : 0.0;
+  }
+  __syncthreads();
+
+  const int r = tid >> 2, q = tid & 3;  // the four threads of a row sit in one warp: only __syncwarp below
+  double* prow = SP + r * LDP;
+#pragma unroll 1
+  for (int kb = 0; kb < NSB; ++kb) {
+    const int c0 = kb * SB;
+    double row[SB];
+#pragma unroll
+    for (int l = 0; l < SB; l += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(prow + c0 + l);
+      row[l] = v.x;
+      row[l + 1] = v.y;
+    }
+    double out[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const double* xr = SX + (kb * SB + 4 * q + e) * XDP;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int l = 0; l < SB; l += 2) {
+        s0 += row[l] * xr[l];
+        s1 += row[l + 1] * xr[l + 1];
+      }
+      out[e] = s0 + s1;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 4; ++e) prow[c0 + 4 * q + e] = out[e];
+    __syncwarp();
+#pragma unroll
+    for (int l = 0; l < SB; l += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(prow + c0 + l);
+      row[l] = v.x;
+      row[l + 1] = v.y;
+    }
+    for (int j = c0 + SB + q; j < NB; j += 4) {
+      const double* lj = SL + j * LDP + c0;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int l = 0; l < SB; l += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(lj + l);
+        s0 += row[l] * v.x;
+        s1 += row[l + 1] * v.y;
+      }
+      prow[j] -= s0 + s1;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int idx = tid; idx < TBR * NB; idx += 256) {
+    const int rr = idx >> 7, c = idx & (NB - 1);
+    if (r0 + rr < m) Mat[(r0 + rr) * ldm + k0 + c] = SP[rr * LDP + c];
+  }
+}
+
 // ------------------------------------------------------------------ K3: diagonal-block solve (one CTA)
 // UPPER == false: L_kk w = b (forward).  UPPER == true: L_kk^T x = b (backward).
 // Thread i owns row i of the block; reciprocal diagonals keep the division off the critical path.
@@ -635,29 +725,113 @@ __device__ __forceinline__ double fold16(double (&v)[16], int lane) {
 }
 
 constexpr int kSolveThreads = 256;
-constexpr size_t kSolveSmem = (size_t)(NB * NB + 2 * 2 * NB + 8 * 2 * NB) * sizeof(double);
+constexpr size_t kSolveSmem = (size_t)(NB * LDP + NSB * SB * XDP + 2 * 2 * NB + 8 * 2 * NB) * sizeof(double);
+
+// Stage L_jj (lower triangle, rows beyond m left out) and the 8 inverted 16 x 16 diagonal sub-blocks.
+__device__ __forceinline__ void solve_stage_diag(const double* __restrict__ L, int64_t ldm, const double* __restrict__ Linv_j,
+                                                 int64_t j0, int64_t m, double* sL, double* sX, int tid) {
+  for (int idx = tid; idx < NB * NB / 2; idx += kSolveThreads) {
+    const int i = idx >> 6, c = (idx & 63) * 2;
+    if (c <= i) {  // c + 1 may be i + 1: one entry above the diagonal, never read
+      double2 v = make_double2(0.0, 0.0);  // rows beyond m (ragged last block) are zero, not stale
+      if (j0 + i < m) v = __ldg(reinterpret_cast<const double2*>(L + (j0 + i) * ldm + j0 + c));
+      *reinterpret_cast<double2*>(sL + i * LDP + c) = v;
+    }
+  }
+  for (int idx = tid; idx < NSB * SB * SB; idx += kSolveThreads) {
+    const int sblk = idx >> 8, i = (idx >> 4) & 15, l = idx & 15;
+    sX[(sblk * SB + i) * XDP + l] = __ldg(Linv_j + (sblk * SB + i) * NB + sblk * SB + l);
+  }
+}
+
+// w = inv(L_jj) c, in place in sc (forward) -- blocked substitution over the 16-column sub-blocks with the
+// 16 x 16 inverses inside (see trsm_blocked_kernel for why not one GEMV with the full inverse).
+template <int NRHS>
+__device__ __forceinline__ void solve_diag_fwd(const double* sL, const double* sX, double* sc, double* sw, int tid) {
+  const int r = tid & (NB - 1), q = tid >> 7;
+#pragma unroll 1
+  for (int s = 0; s < NSB; ++s) {
+    const int c0 = s * SB;
+    if (tid < SB * NRHS) {
+      const int i = tid & 15, qq = tid >> 4;
+      const double* xr = sX + (c0 + i) * XDP;
+      const double* cs = sc + qq * NB + c0;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int l = 0; l < SB; l += 2) {  // X is zero above its diagonal
+        a0 += xr[l] * cs[l];
+        a1 += xr[l + 1] * cs[l + 1];
+      }
+      sw[qq * NB + c0 + i] = a0 + a1;
+    }
+    __syncthreads();
+    if (q < NRHS && r >= c0 + SB) {
+      const double* lr = sL + r * LDP + c0;
+      const double* ws = sw + q * NB + c0;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int l = 0; l < SB; l += 2) {
+        a0 += lr[l] * ws[l];
+        a1 += lr[l + 1] * ws[l + 1];
+      }
+      sc[q * NB + r] -= a0 + a1;
+    }
+    __syncthreads();
+  }
+}
+
+// x = inv(L_jj)^T c (backward)
+template <int NRHS>
+__device__ __forceinline__ void solve_diag_bwd(const double* sL, const double* sX, double* sc, double* sw, int tid) {
+  const int c = tid & (NB - 1), q = tid >> 7;
+#pragma unroll 1
+  for (int s = NSB - 1; s >= 0; --s) {
+    const int c0 = s * SB;
+    if (tid < SB * NRHS) {
+      const int i = tid & 15, qq = tid >> 4;
+      const double* cs = sc + qq * NB + c0;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int l = 0; l < SB; l += 2) {  // x_i = sum_l X[l][i] c_l ; X[l][i] = 0 for l < i
+        a0 += sX[(c0 + l) * XDP + i] * cs[l];
+        a1 += sX[(c0 + l + 1) * XDP + i] * cs[l + 1];
+      }
+      sw[qq * NB + c0 + i] = a0 + a1;
+    }
+    __syncthreads();
+    if (q < NRHS && c < c0) {
+      const double* xs = sw + q * NB + c0;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int l = 0; l < SB; l += 2) {
+        a0 += sL[(c0 + l) * LDP + c] * xs[l];
+        a1 += sL[(c0 + l + 1) * LDP + c] * xs[l + 1];
+      }
+      sc[q * NB + c] -= a0 + a1;
+    }
+    __syncthreads();
+  }
+}
 
 template <int NRHS>
 __global__ void __launch_bounds__(kSolveThreads, 1)
 solve_pipelined_kernel(const double* __restrict__ L, int64_t ldm, const double* __restrict__ Linv_all, int64_t m,
                        int nblk, double* B, double* Y, int64_t ldy, int* flags_f, int* flags_b, int epoch) {
   extern __shared__ __align__(16) double sm[];
-  double* sLinv = sm;                 // 128 x 128, ld 128
-  double* sc = sLinv + NB * NB;       // [2][128] reduced right-hand side of the current block
-  double* sx = sc + 2 * NB;           // [2][128] solution of the current block
-  double* sred = sx + 2 * NB;         // [8 warps][2][128] backward cross-warp fold
+  double* sL = sm;                        // 128 x LDP: L_jj
+  double* sX = sL + NB * LDP;             // 8 x 16 x XDP: inv of its 16 x 16 diagonal sub-blocks
+  double* sc = sX + NSB * SB * XDP;       // [2][128] right-hand side of the current block
+  double* sw = sc + 2 * NB;               // [2][128] solution of the current block
+  double* sred = sw + 2 * NB;             // [8 warps][2][128] backward cross-warp fold
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int c4 = 4 * lane;            // this lane's 4 columns inside a 128-wide block
+  const int c4 = 4 * lane;                // this lane's 4 columns inside a 128-wide block
 
   // ============================================================ forward: L w = b
   for (int j = blockIdx.x; j < nblk; j += gridDim.x) {
     const int64_t r0 = (int64_t)j * NB;
     const int nbj = (int)((m - r0) < NB ? (m - r0) : NB);
-    {  // inv(L_jj) -> shared (needed only after the sweep: its latency hides behind it)
-      const double2* src = reinterpret_cast<const double2*>(Linv_all + (int64_t)j * NB * NB);
-      double2* dst = reinterpret_cast<double2*>(sLinv);
-      for (int idx = tid; idx < NB * NB / 2; idx += kSolveThreads) dst[idx] = __ldg(src + idx);
-    }
+    __syncthreads();  // the previous block row is done with sL / sX / sc / sw
+    solve_stage_diag(L, ldm, Linv_all + (int64_t)j * NB * NB, r0, m, sL, sX, tid);  // latency hides behind the sweep
     double acc[NRHS][16];
 #pragma unroll
     for (int q = 0; q < NRHS; ++q)
@@ -702,27 +876,12 @@ solve_pipelined_kernel(const double* __restrict__ L, int64_t ldm, const double* 
       if ((lane & 1) == 0) sc[q * NB + rr] = (rr < nbj) ? B[(int64_t)q * m + r0 + rr] - tot : 0.0;
     }
     __syncthreads();
-    // w = inv(L_jj) c  (rows of this warp, lanes over columns)
-    {
-      double part[NRHS][16];
-      double4 cv[NRHS];
-#pragma unroll
-      for (int q = 0; q < NRHS; ++q) cv[q] = *reinterpret_cast<const double4*>(sc + q * NB + c4);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const double4 lv = *reinterpret_cast<const double4*>(sLinv + (warp * 16 + i) * NB + c4);
-#pragma unroll
-        for (int q = 0; q < NRHS; ++q)
-          part[q][i] = lv.x * cv[q].x + lv.y * cv[q].y + lv.z * cv[q].z + lv.w * cv[q].w;
-      }
-#pragma unroll
-      for (int q = 0; q < NRHS; ++q) {
-        const double tot = fold16(part[q], lane);
-        const int rr = warp * 16 + (lane >> 1);
-        if ((lane & 1) == 0 && rr < nbj) Y[(int64_t)q * ldy + r0 + rr] = tot;
-      }
+    solve_diag_fwd<NRHS>(sL, sX, sc, sw, tid);
+    if (tid < NRHS * NB) {
+      const int q = tid >> 7, rr = tid & (NB - 1);
+      if (rr < nbj) Y[(int64_t)q * ldy + r0 + rr] = sw[q * NB + rr];
     }
-    __syncthreads();  // all of w_j written (and sLinv / sc free for the next block row)
+    __syncthreads();  // all of w_j written
     if (tid == 0) {
       __threadfence();
       st_release_gpu(flags_f + j, epoch);
@@ -733,12 +892,8 @@ solve_pipelined_kernel(const double* __restrict__ L, int64_t ldm, const double* 
   for (int j = nblk - 1 - blockIdx.x; j >= 0; j -= gridDim.x) {
     const int64_t j0 = (int64_t)j * NB;
     const int nbj = (int)((m - j0) < NB ? (m - j0) : NB);
-    __syncthreads();  // previous users of sLinv / sred are done
-    {
-      const double2* src = reinterpret_cast<const double2*>(Linv_all + (int64_t)j * NB * NB);
-      double2* dst = reinterpret_cast<double2*>(sLinv);
-      for (int idx = tid; idx < NB * NB / 2; idx += kSolveThreads) dst[idx] = __ldg(src + idx);
-    }
+    __syncthreads();  // previous users of sL / sX / sc / sw / sred are done
+    solve_stage_diag(L, ldm, Linv_all + (int64_t)j * NB * NB, j0, m, sL, sX, tid);
     double acc[NRHS][4];
 #pragma unroll
     for (int q = 0; q < NRHS; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
@@ -775,47 +930,22 @@ solve_pipelined_kernel(const double* __restrict__ L, int64_t ldm, const double* 
     }
 #pragma unroll
     for (int q = 0; q < NRHS; ++q)
-      *reinterpret_cast<double4*>(sred + (warp * 2 + q) * NB + c4) = make_double4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+      *reinterpret_cast<double2*>(sred + (warp * 2 + q) * NB + c4) = make_double2(acc[q][0], acc[q][1]),
+      *reinterpret_cast<double2*>(sred + (warp * 2 + q) * NB + c4 + 2) = make_double2(acc[q][2], acc[q][3]);
     __syncthreads();
     if (tid < NRHS * NB) {  // c = w_j - sum over the 8 warps
       wait_flag(flags_f + j, epoch);  // w_j may come from another CTA (forward owner j mod G)
       const int q = tid >> 7, c = tid & (NB - 1);
-      double s = 0.0;
+      double sum = 0.0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += sred[(w * 2 + q) * NB + c];
-      sc[q * NB + c] = (c < nbj) ? __ldcg(Y + (int64_t)q * ldy + j0 + c) - s : 0.0;
+      for (int w = 0; w < 8; ++w) sum += sred[(w * 2 + q) * NB + c];
+      sc[q * NB + c] = (c < nbj) ? __ldcg(Y + (int64_t)q * ldy + j0 + c) - sum : 0.0;
     }
     __syncthreads();
-    // x = inv(L_jj)^T c : x[c] = sum_r Linv[r][c] c[r]; warp = 16 rows, lane = 4 columns
-    {
-      double xa[NRHS][4];
-#pragma unroll
-      for (int q = 0; q < NRHS; ++q) xa[q][0] = xa[q][1] = xa[q][2] = xa[q][3] = 0.0;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int r = warp * 16 + i;
-        const double4 lv = *reinterpret_cast<const double4*>(sLinv + r * NB + c4);
-#pragma unroll
-        for (int q = 0; q < NRHS; ++q) {
-          const double cr = sc[q * NB + r];
-          xa[q][0] += lv.x * cr;
-          xa[q][1] += lv.y * cr;
-          xa[q][2] += lv.z * cr;
-          xa[q][3] += lv.w * cr;
-        }
-      }
-      __syncthreads();  // sred is re-used
-#pragma unroll
-      for (int q = 0; q < NRHS; ++q)
-        *reinterpret_cast<double4*>(sred + (warp * 2 + q) * NB + c4) = make_double4(xa[q][0], xa[q][1], xa[q][2], xa[q][3]);
-    }
-    __syncthreads();
+    solve_diag_bwd<NRHS>(sL, sX, sc, sw, tid);
     if (tid < NRHS * NB) {
       const int q = tid >> 7, c = tid & (NB - 1);
-      double s = 0.0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) s += sred[(w * 2 + q) * NB + c];
-      if (c < nbj) B[(int64_t)q * m + j0 + c] = s;
+      if (c < nbj) B[(int64_t)q * m + j0 + c] = sw[q * NB + c];
     }
     __syncthreads();
     if (tid == 0) {
@@ -842,6 +972,7 @@ int configure_once() {
   LPB_TRY(set_smem(potf2_kernel, kPotf2Smem));
   LPB_TRY(set_smem(potf2_inv_kernel, kPotf2InvSmem));
   LPB_TRY(set_smem(trsm_kernel, kTrsmSmem));
+  LPB_TRY(set_smem(trsm_blocked_kernel, kTrsmBlockedSmem));
   LPB_TRY(set_smem(trsv_diag_kernel<false, 1>, kTrsvSmem));
   LPB_TRY(set_smem(trsv_diag_kernel<false, 2>, kTrsvSmem));
   LPB_TRY(set_smem(trsv_diag_kernel<true, 1>, kTrsvSmem));
@@ -884,16 +1015,25 @@ int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
     double* linv = lc.chol_ws + (k0 / NB) * NB * NB;
     potf2_inv_kernel<<<1, dim3(32, 16), kPotf2InvSmem, lc.stream>>>(Mat, ldm, (int)k0, nb, lc.info_dev, linv);
     LPB_KCHECK(lc);
+    if (lc.sync_each_launch) LPB_CUDA(cudaStreamSynchronize(lc.stream));
     if (rem > 0) {
-      if (syrk_impl == 1) {
+      if (syrk_impl == 1 || lc.trsm_impl == 1) {  // column-by-column substitution (reference path)
         trsm_kernel<<<(unsigned)ceil_div(rem, TRSM_ROWS), dim3(32, 8), kTrsmSmem, lc.stream>>>(Mat, ldm, (int)k0, nb,
                                                                                                (int)m);
         LPB_KCHECK(lc);
-        LPB_TRY(k_trailing_update_simple(lc, m, Mat, ldm, k0, nb));
-      } else {
+      } else if (lc.trsm_impl == 2) {             // GEMM with the full 128 x 128 inverse (not backward stable)
         LPB_TRY(k_trsm_dmma(lc, m, Mat, ldm, k0, linv));
-        LPB_TRY(k_trailing_update_dmma(lc, m, Mat, ldm, k0, nb));
+      } else {                                    // rem > 0 implies nb == NB
+        trsm_blocked_kernel<<<(unsigned)ceil_div(rem, TBR), 256, kTrsmBlockedSmem, lc.stream>>>(Mat, ldm, (int)k0,
+                                                                                               (int)m, linv);
+        LPB_KCHECK(lc);
       }
+      if (lc.sync_each_launch) LPB_CUDA(cudaStreamSynchronize(lc.stream));
+      if (syrk_impl == 1 || lc.update_impl == 1)
+        LPB_TRY(k_trailing_update_simple(lc, m, Mat, ldm, k0, nb));
+      else
+        LPB_TRY(k_trailing_update_dmma(lc, m, Mat, ldm, k0, nb));
+      if (lc.sync_each_launch) LPB_CUDA(cudaStreamSynchronize(lc.stream));
     }
   }
   lc.linv_valid_m = m;
@@ -989,7 +1129,8 @@ static int potrs_impl(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, do
 
 int k_potrs(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B, int nrhs, bool use_linv) {
   LPB_TRY(configure_once());
-  if (use_linv && lc.linv_valid_m == m && lc.linv_mat == L && lc.chol_ws) {
+  const bool aligned = !(ldm & 1) && !(reinterpret_cast<uintptr_t>(L) & 15);  // double2 loads of L
+  if (use_linv && aligned && lc.solve_impl != 2 && lc.linv_valid_m == m && lc.linv_mat == L && lc.chol_ws) {
     if (lc.solve_impl == 1) {  // one launch per 128-block step (kept for bisecting)
       if (nrhs == 1) return potrs_fused<1>(lc, m, L, ldm, B);
       if (nrhs == 2) return potrs_fused<2>(lc, m, L, ldm, B);

@@ -54,6 +54,8 @@ struct LaunchCtx {
   const double* linv_mat = nullptr; // ... and its address
   int solve_epoch = 0;             // flag value of the next pipelined solve (cholesky.cu)
   int solve_impl = 0;              // 0 = pipelined single launch, 1 = one launch per block step
+  int sync_each_launch = 0;        // debug: stream-synchronise after every launch of k_potrf
+  int trsm_impl = 0, update_impl = 0;  // bisecting knobs of k_potrf: 1 = plain DFMA kernel for that step
   int solve_grid_cap = 0;          // > 0: cap the pipelined solve's grid (tests: several block rows per CTA)
   int* info_dev = nullptr;         // potrf info flag
   int* info_host = nullptr;        // pinned

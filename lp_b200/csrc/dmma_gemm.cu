@@ -54,6 +54,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Release of a ring stage by a consumer warp.  The stage is overwritten by TMA as soon as the eighth
+// arrive lands, so every ld.shared of the iteration must have COMPLETED, not merely been issued,
+// before it: ptxas places SYNCS.ARRIVE directly behind the last LDS without waiting on its scoreboard,
+// and under store back-pressure (the epilogues of the other warps at a tile boundary) an issued LDS
+// was observed to read the stage after its refill (bit-wrong rows in ~1e-6 of the tiles, found by
+// factoring the same matrix twice).  `dep` is a word of the last fragment loaded in the iteration
+// (shared loads of a warp complete in order) and `zero` a run-time zero the compiler cannot fold: the barrier address now depends on
+// the loaded data, which forces the scoreboard wait.  The fragment loads are ld.volatile so that the last
+// one in program order is also the last one issued.
+__device__ __forceinline__ void mbar_arrive_after_loads(uint32_t bar, uint32_t dep, uint32_t zero) {
+  asm volatile(
+      "{\n\t.reg .b32 t;\n\t"
+      "mad.lo.u32 t, %1, %2, %0;\n\t"
+      "mbarrier.arrive.shared::cta.b64 _, [t];\n\t}" ::"r"(bar),
+      "r"(dep), "r"(zero)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -82,7 +99,8 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
 }
 __device__ __forceinline__ double2 lds_v2(uint32_t addr) {
   double2 v;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  // volatile: ptxas keeps these loads in program order among themselves (see mbar_arrive_after_loads)
+  asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -116,7 +134,10 @@ struct LoadCursor {
 //               in place (a CTA reads all K-blocks of its own rows before it stores them).
 enum { MODE_SYRK = 0, MODE_UPDATE = 1, MODE_TRSM = 2 };
 
-template <int MODE, bool SCALE>
+// VAR (experiments on the trailing update): bit 0 = accumulate from zero and read-modify-write C in
+// the epilogue instead of initialising the accumulators from C; bit 1 = CTA barrier at every tile end;
+// bit 2 = legacy stage release (plain arrive right behind the last LDS: reproduces the race, control only).
+template <int MODE, bool SCALE, int VAR = 0>
 __global__ void __maxnreg__(255)
 syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  double* __restrict__ C, int64_t ldc, int m_total, int tile0, int ntr, int k_begin, int nkb,
@@ -201,6 +222,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t sw[2] = {static_cast<uint32_t>(((2 * t + 0) ^ g) << 4), static_cast<uint32_t>(((2 * t + 1) ^ g) << 4)};
   const uint32_t dof[2] = {static_cast<uint32_t>((2 * t + 0) << 4), static_cast<uint32_t>((2 * t + 1) << 4)};
 
+  const uint32_t rt_zero = static_cast<uint32_t>(static_cast<uint64_t>(ldc) >> 62);  // 0 at run time, opaque to the compiler
   for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
     int ti, tj;
     decode(L, &ti, &tj);
@@ -208,7 +230,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int col0 = (MODE == MODE_TRSM ? col_origin : (tile0 + tj) * BN) + wn * 32 + 2 * t;
     const int col_limit = MODE == MODE_TRSM ? col_origin + BN : m_total;
     double acc[8][4][2];
-    if (MODE == MODE_UPDATE) {
+    if (MODE == MODE_UPDATE && !(VAR & 1)) {
       // start from C: the loads overlap the wait for the first operand stages
 #pragma unroll
       for (int mi = 0; mi < 8; ++mi) {
@@ -238,6 +260,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t a_base = sA + stage * kTileBytes + offA;
       const uint32_t b_base = sB + stage * kTileBytes + offB;
       const uint32_t d_base = sD + stage * kDBytes;
+      uint32_t dep = 0;
 #pragma unroll
       for (int P = 0; P < 2; ++P) {
         double2 b[4];
@@ -261,6 +284,8 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         double2 a[8];
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi) a[mi] = lds_v2(a_base + mi * 1024 + sw[P]);
+        // the last ld.shared of the iteration in program order (shared loads of a warp complete in order)
+        if (P == 1) dep = static_cast<uint32_t>(__double2hiint(a[7].y));
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
@@ -271,7 +296,12 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty + stage * 8);
+      if (lane == 0) {
+        if (VAR & 4)
+          mbar_arrive(bar_empty + stage * 8);
+        else
+          mbar_arrive_after_loads(bar_empty + stage * 8, dep, rt_zero);
+      }
       if (++stage == kStages) {
         stage = 0;
         phase ^= 1u;
@@ -287,10 +317,19 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
           const int c = col0 + ni * 8;
-          if (c < col_limit) *reinterpret_cast<double2*>(crow + c) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+          if (c < col_limit) {
+            double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            if (MODE == MODE_UPDATE && (VAR & 1)) {
+              const double2 o = *reinterpret_cast<const double2*>(crow + c);
+              v.x += o.x;
+              v.y += o.y;
+            }
+            *reinterpret_cast<double2*>(crow + c) = v;
+          }
         }
       }
     }
+    if (VAR & 2) __syncthreads();
   }
 }
 
@@ -335,11 +374,11 @@ int make_tmap(CUtensorMap* tm, const double* base, uint64_t rows, uint64_t cols,
   return LPB_OK;
 }
 
-template <int MODE, bool SCALE>
+template <int MODE, bool SCALE, int VAR = 0>
 int launch_dmma(LaunchCtx& lc, const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int m_total,
                 int tile0, int ntr, int k_begin, int nkb, int col_origin) {
   static bool configured = false;
-  auto kern = syrk_dmma_kernel<MODE, SCALE>;
+  auto kern = syrk_dmma_kernel<MODE, SCALE, VAR>;
   if (!configured) {
     LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAlloc));
     configured = true;
@@ -384,6 +423,18 @@ int k_trailing_update_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, i
   CUtensorMap tm;
   LPB_TRY(make_tmap(&tm, Mat, (uint64_t)m, (uint64_t)m, (uint64_t)ldm, BM, BK, true));
   const int ntr = (int)ceil_div(m - row0, BM);
+  if (lc.update_impl == 2)
+    return launch_dmma<MODE_UPDATE, false, 1>(lc, tm, tm, Mat, ldm, (int)m, (int)(row0 / BM), ntr, (int)k0,
+                                              (int)(kb / BK), 0);
+  if (lc.update_impl == 3)
+    return launch_dmma<MODE_UPDATE, false, 2>(lc, tm, tm, Mat, ldm, (int)m, (int)(row0 / BM), ntr, (int)k0,
+                                              (int)(kb / BK), 0);
+  if (lc.update_impl == 4)
+    return launch_dmma<MODE_UPDATE, false, 4>(lc, tm, tm, Mat, ldm, (int)m, (int)(row0 / BM), ntr, (int)k0,
+                                              (int)(kb / BK), 0);
+  if (lc.update_impl == 5)
+    return launch_dmma<MODE_UPDATE, false, 6>(lc, tm, tm, Mat, ldm, (int)m, (int)(row0 / BM), ntr, (int)k0,
+                                              (int)(kb / BK), 0);
   return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, (int)(row0 / BM), ntr, (int)k0, (int)(kb / BK),
                                          0);
 }

@@ -110,10 +110,11 @@ struct HostRecorder {
     std::printf("alpha     \trho_p     \trho_d     \trho_g     \trho_mu    \tobj       \n");
     std::printf("1.00000000\t%.8f\t%.8f\t%.8f\t%.8f\t%8.3f\n", i.rho_p, i.rho_d, i.rho_g, i.rho_mu, i.obj);
   }
-  void iteration(double alpha, const Indicators& i, double tau, double kappa) {
+  void iteration(double alpha, const Indicators& i, double tau, double kappa, const double dbg[6]) {
     if (disp) std::printf("%.8f\t%.8f\t%.8f\t%.8f\t%.8f\t%8.3f\n", alpha, i.rho_p, i.rho_d, i.rho_g, i.rho_mu, i.obj);
     if (trace) {
-      TraceRow row = {{alpha, i.rho_p, i.rho_d, i.rho_A, i.rho_g, i.rho_mu, i.obj, i.bty, tau, kappa}};
+      TraceRow row = {{alpha, i.rho_p, i.rho_d, i.rho_A, i.rho_g, i.rho_mu, i.obj, i.bty, tau, kappa, dbg[0], dbg[1],
+                       dbg[2], dbg[3], dbg[4], dbg[5]}};
       trace->push_back(row);
     }
   }
@@ -122,7 +123,7 @@ struct HostRecorder {
 // Device recorder (batched kernel): nothing to record.
 struct NullRecorder {
   LPB_HD void start(const Indicators&) {}
-  LPB_HD void iteration(double, const Indicators&, double, double) {}
+  LPB_HD void iteration(double, const Indicators&, double, double, const double*) {}
 };
 
 // One Delta::compute worth of host scalars (delta.rs:29-32, :38).
@@ -220,7 +221,10 @@ LPB_HD int solve_normal_form_rec(Dev& dev, const lpb_options& o, int64_t n_total
     // ---- indicators (mod.rs:225-235)
     if ((rc = dev.residuals(tau, kappa, &rs)) != LPB_OK) return rc;
     ind = make_indicators(rs, ini, tau, kappa, n_total, c0);
-    rec.iteration(alpha, ind, tau, kappa);
+    {  // parity-debugging scalars of the corrector: where two backends first part ways
+      const double dbg[6] = {dout.cp, dout.bq, dout.cu, dout.bv, d_tau, d_kappa};
+      rec.iteration(alpha, ind, tau, kappa, dbg);
+    }
     out->iterations = iteration;
     out->tau = tau;
     out->kappa = kappa;

@@ -46,6 +46,10 @@ int k_resid_p(LaunchCtx& lc, int64_t m, double tau, const double* b, const doubl
 // rhs0 = rP*eta + t0 ; (with_pq) rhs1 = b + t1          (newton_equations.rs:220)
 int k_sym_fwd_rhs(LaunchCtx& lc, int64_t m, double eta, const double* rP, const double* b, const double* t0,
                   const double* t1, double* rhs0, double* rhs1, int with_pq);
+// refinement residuals rho0 = rP*eta - A u ; (with_pq) rho1 = b - A p ;  and y += x
+int k_refine_rhs(LaunchCtx& lc, int64_t m, double eta, const double* rP, const double* b, const double* au,
+                 const double* ap, double* rho0, double* rho1, int with_pq);
+int k_add_inplace(LaunchCtx& lc, int64_t count, const double* x, double* y);
 // partials: b.v -> val_base ; (with_pq) b.q -> val_base+1, #NaN(q) -> val_base+2
 int k_dots_m(LaunchCtx& lc, int64_t m, const double* b, const double* v, const double* q, int with_pq, int val_base,
              int* nblocks);
@@ -96,6 +100,8 @@ int k_fill_vec(LaunchCtx& lc, double* v, int64_t count, int64_t idx0, uint64_t s
 int k_slack_identity(LaunchCtx& lc, double* A, int64_t rows, int64_t cols, int64_t lda, int64_t col0, int64_t n0);
 int k_add_vec(LaunchCtx& lc, double* out, const double* a, const double* b, int64_t count, int64_t count_b);
 // order-independent bit checksum of a matrix block (replica-agreement checks of the sharded path)
+int k_diff(LaunchCtx& lc, const double* a, const double* b, int64_t rows, int64_t cols, int64_t ld, int lower_only,
+           unsigned long long* out_dev3);
 int k_checksum(LaunchCtx& lc, const double* v, int64_t rows, int64_t cols, int64_t ld, int lower_only,
                unsigned long long* out_dev);
 

@@ -40,7 +40,8 @@ struct lpb_ctx {
   int64_t m = 0, n = 0, n_global = 0, col0 = 0, lda = 0, ldm = 0;
   double c0 = 0.0;
   double *A = nullptr, *M = nullptr;
-  double *b = nullptr, *y = nullptr, *rP = nullptr, *dy = nullptr, *t = nullptr, *W = nullptr;
+  double *b = nullptr, *y = nullptr, *rP = nullptr, *dy = nullptr, *t = nullptr, *W = nullptr, *R = nullptr;
+  int refine = 1;  // iterative-refinement steps per sym_solve (0 = the plain factor-and-solve of the reference)
   double *c = nullptr, *x = nullptr, *z = nullptr, *rD = nullptr, *dinv = nullptr, *xs = nullptr, *r1 = nullptr,
          *p = nullptr, *u = nullptr, *dx = nullptr, *dz = nullptr, *xo = nullptr;
   bool have_pq = false;
@@ -50,6 +51,9 @@ struct lpb_ctx {
   bool profile = true;
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
+  int potrf_verify = 0;                 // debug: factor every M twice and compare the two factors bit for bit
+  double *vfy1 = nullptr, *vfy2 = nullptr;
+  int64_t vfy_mismatch = 0, vfy_runs = 0;
   bool check_replicas = false;          // debug: compare checksums of replicated buffers across ranks
   unsigned long long* chk_dev = nullptr;  // 2 words: {checksum, ~checksum}
   unsigned long long* chk_host = nullptr; // pinned
@@ -227,10 +231,39 @@ struct CudaDev {
     }
     LPB_TRY(allreduce(c, c->M, c->m * c->ldm, ncclSum));
     LPB_TRY(check_replicated(c, "M after the all-reduce", c->M, c->m, c->m, c->ldm, 1));
+    const size_t mbytes = sizeof(double) * (size_t)(c->m * c->ldm);
+    if (c->potrf_verify) {
+      if (!c->vfy1) {
+        LPB_TRY(dev_alloc(c, &c->vfy1, c->m * c->ldm));
+        LPB_TRY(dev_alloc(c, &c->vfy2, c->m * c->ldm));
+      }
+      LPB_CUDA(cudaMemcpyAsync(c->vfy1, c->M, mbytes, cudaMemcpyDeviceToDevice, c->lc.stream));
+    }
     {
       PhaseTimer tm(c, PH_POTRF);
       LPB_TRY(k_potrf(c->lc, c->m, c->M, c->ldm, c->syrk_impl));
       c->prof.potrf_launches++;
+    }
+    if (c->potrf_verify) {  // same input, second run: any bit that differs is a race
+      LPB_CUDA(cudaMemcpyAsync(c->vfy2, c->M, mbytes, cudaMemcpyDeviceToDevice, c->lc.stream));
+      LPB_CUDA(cudaMemcpyAsync(c->M, c->vfy1, mbytes, cudaMemcpyDeviceToDevice, c->lc.stream));
+      const int saved = c->lc.sync_each_launch;
+      if (c->potrf_verify == 2) c->lc.sync_each_launch = 1;
+      LPB_TRY(k_potrf(c->lc, c->m, c->M, c->ldm, c->syrk_impl));
+      c->lc.sync_each_launch = saved;
+      unsigned long long* d3 = nullptr;
+      LPB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d3), 3 * sizeof(unsigned long long)));
+      LPB_TRY(k_diff(c->lc, c->M, c->vfy2, c->m, c->m, c->ldm, 1, d3));
+      unsigned long long h3[3];
+      LPB_CUDA(cudaMemcpyAsync(h3, d3, sizeof(h3), cudaMemcpyDeviceToHost, c->lc.stream));
+      LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+      cudaFree(d3);
+      c->vfy_runs++;
+      if (h3[0]) {
+        c->vfy_mismatch++;
+        std::fprintf(stderr, "[potrf_verify] factorisation %lld: %llu entries differ between two runs on the same M; "
+                     "first column %llu, first row %llu\n", (long long)c->vfy_runs, h3[0], h3[1], h3[2]);
+      }
     }
     LPB_TRY(check_replicated(c, "the Cholesky factor", c->M, c->m, c->m, c->ldm, 1));
     if (c->world > 1) {  // every rank must take the same branch on a failed factorisation
@@ -281,6 +314,41 @@ struct CudaDev {
       PhaseTimer tm(c, PH_SWEEP);
       LPB_TRY(k_gemv_t_partials(c->lc, c->m, c->n, c->A, c->lda, W0, W1, nrhs, &nchunks));
       LPB_TRY(k_sym_back(c->lc, c->n, nchunks, with_pq, c->dinv, c->r1, c->c, c->u, c->p, 0, &nb_n));
+    }
+    // Iterative refinement against the OPERATOR A Dinv A^T (not the stored M): the residual of
+    //   M v = r2 + A Dinv r1   is   r2 - A u   with u = Dinv (A^T v - r1),   i.e.  rP*eta - A u  and  b - A p,
+    // one more sweep each way and one more solve.  It removes the rounding error of the SYRK accumulation
+    // and of the factorisation from (u, v, p, q): without it -c.p + b.q (a difference of two numbers ~ the
+    // objective that must come out as p' Dinv^-1 p >= 0, delta.rs:32) was 20x noisier than with LAPACK late
+    // in the iteration, and d_tau went wild (C3: 27-28 iterations instead of the oracle's 24).
+    for (int step = 0; step < c->refine; ++step) {
+      double* R0 = c->R;
+      double* R1 = c->R + c->m;
+      {
+        PhaseTimer tm(c, PH_SWEEP);
+        LPB_TRY(k_gemv_n(c->lc, c->m, c->n, c->A, c->lda, nullptr, c->u, c->p, c->t, c->t + c->m, nrhs));
+      }
+      LPB_TRY(allreduce(c, c->t, c->m * nrhs, ncclSum));
+      {
+        PhaseTimer tm(c, PH_VEC);
+        LPB_TRY(k_refine_rhs(c->lc, c->m, in.eta, c->rP, c->b, c->t, c->t + c->m, R0, R1, with_pq));
+      }
+      {
+        PhaseTimer tm(c, PH_SOLVE);
+        LPB_TRY(k_potrs(c->lc, c->m, c->M, c->ldm, c->R, nrhs, c->syrk_impl == 0));
+      }
+      {
+        PhaseTimer tm(c, PH_VEC);
+        LPB_TRY(k_add_inplace(c->lc, c->m * nrhs, c->R, c->W));
+      }
+      {
+        PhaseTimer tm(c, PH_SWEEP);
+        LPB_TRY(k_gemv_t_partials(c->lc, c->m, c->n, c->A, c->lda, W0, W1, nrhs, &nchunks));
+        LPB_TRY(k_sym_back(c->lc, c->n, nchunks, with_pq, c->dinv, c->r1, c->c, c->u, c->p, 0, &nb_n));
+      }
+    }
+    {
+      PhaseTimer tm(c, PH_SWEEP);
       LPB_TRY(k_dots_m(c->lc, c->m, c->b, W0, W1, with_pq, 3, &nb_m));
     }
     spec.nblocks[0] = spec.nblocks[1] = spec.nblocks[2] = nb_n;
@@ -389,6 +457,7 @@ int ctx_alloc_vectors(lpb_ctx* c, int64_t m, int64_t n, bool with_matrices) {
   for (auto p : mv) LPB_TRY(dev_alloc(c, p, m));
   LPB_TRY(dev_alloc(c, &c->t, 2 * m));
   LPB_TRY(dev_alloc(c, &c->W, 2 * m));
+  LPB_TRY(dev_alloc(c, &c->R, 2 * m));
   double** nv[] = {&c->c, &c->x, &c->z, &c->rD, &c->dinv, &c->xs, &c->r1, &c->p, &c->u, &c->dx, &c->dz, &c->xo};
   for (auto p : nv) LPB_TRY(dev_alloc(c, p, round_up(n, 2)));
   LPB_CUDA(cudaMemsetAsync(c->A, 0, sizeof(double) * (size_t)(m * c->lda), c->lc.stream));
@@ -945,13 +1014,31 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
     return LPB_OK;
   }
   if (k == "solve_impl") {
-    if (value != 0 && value != 1) return LPB_ERR_BAD_ARGUMENT;
+    if (value < 0 || value > 2) return LPB_ERR_BAD_ARGUMENT;
     c->lc.solve_impl = (int)value;
+    return LPB_OK;
+  }
+  if (k == "trsm_impl" || k == "update_impl") {
+    if (value < 0 || value > 5) return LPB_ERR_BAD_ARGUMENT;
+    (k == "trsm_impl" ? c->lc.trsm_impl : c->lc.update_impl) = (int)value;
     return LPB_OK;
   }
   if (k == "solve_grid_cap") {
     if (value < 0) return LPB_ERR_BAD_ARGUMENT;
     c->lc.solve_grid_cap = (int)value;
+    return LPB_OK;
+  }
+  if (k == "refine") {
+    if (value < 0 || value > 4) return LPB_ERR_BAD_ARGUMENT;
+    c->refine = (int)value;
+    return LPB_OK;
+  }
+  if (k == "potrf_verify") {
+    c->potrf_verify = (int)value;
+    return LPB_OK;
+  }
+  if (k == "sync_each_launch") {
+    c->lc.sync_each_launch = (int)value;
     return LPB_OK;
   }
   if (k == "check_replicas") {

@@ -280,6 +280,34 @@ __global__ void sym_fwd_rhs_kernel(int64_t m, double eta, const double* __restri
     if (with_pq) rhs1[i] = b[i] + t1[i];     // r2 = b
   }
 }
+// Iterative refinement of the sym_solve (see CudaDev::direction): residuals of the normal equations
+// written with the already computed u = Dinv(A^T v - r1):  rho0 = rP*eta - A u,  rho1 = b - A p.
+__global__ void refine_rhs_kernel(int64_t m, double eta, const double* __restrict__ rP, const double* __restrict__ b,
+                                  const double* __restrict__ au, const double* __restrict__ ap,
+                                  double* __restrict__ rho0, double* __restrict__ rho1, int with_pq) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    rho0[i] = rP[i] * eta - au[i];
+    if (with_pq) rho1[i] = b[i] - ap[i];
+  }
+}
+int k_refine_rhs(LaunchCtx& lc, int64_t m, double eta, const double* rP, const double* b, const double* au,
+                 const double* ap, double* rho0, double* rho1, int with_pq) {
+  refine_rhs_kernel<<<vec_blocks(m), kVecThreads, 0, lc.stream>>>(m, eta, rP, b, au, ap, rho0, rho1, with_pq);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+// y += x
+__global__ void axpy1_kernel(int64_t count, const double* __restrict__ x, double* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] += x[i];
+}
+int k_add_inplace(LaunchCtx& lc, int64_t count, const double* x, double* y) {
+  if (count <= 0) return LPB_OK;
+  axpy1_kernel<<<vec_blocks(count), kVecThreads, 0, lc.stream>>>(count, x, y);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
 int k_sym_fwd_rhs(LaunchCtx& lc, int64_t m, double eta, const double* rP, const double* b, const double* t0,
                   const double* t1, double* rhs0, double* rhs1, int with_pq) {
   sym_fwd_rhs_kernel<<<vec_blocks(m), kVecThreads, 0, lc.stream>>>(m, eta, rP, b, t0, t1, rhs0, rhs1, with_pq);
@@ -694,6 +722,31 @@ int k_checksum(LaunchCtx& lc, const double* v, int64_t rows, int64_t cols, int64
   LPB_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(unsigned long long), lc.stream));
   if (rows <= 0 || cols <= 0) return LPB_OK;
   checksum_kernel<<<kNumSMs * 8, 256, 0, lc.stream>>>(v, rows, cols, ld, lower_only, out_dev);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+
+// Debug: compare two matrices bit for bit (lower triangle if lower_only); out = {count, min col, min row}.
+__global__ void diff_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t rows, int64_t cols,
+                            int64_t ld, int lower_only, unsigned long long* __restrict__ out) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    if (lower_only && c > r) continue;
+    if (__double_as_longlong(a[r * ld + c]) != __double_as_longlong(b[r * ld + c])) {
+      atomicAdd(out, 1ull);
+      atomicMin(out + 1, (unsigned long long)c);
+      atomicMin(out + 2, (unsigned long long)r);
+    }
+  }
+}
+int k_diff(LaunchCtx& lc, const double* a, const double* b, int64_t rows, int64_t cols, int64_t ld, int lower_only,
+           unsigned long long* out_dev3) {
+  const unsigned long long init[3] = {0ull, ~0ull, ~0ull};
+  LPB_CUDA(cudaMemcpyAsync(out_dev3, init, sizeof(init), cudaMemcpyHostToDevice, lc.stream));
+  LPB_CUDA(cudaStreamSynchronize(lc.stream));
+  diff_kernel<<<kNumSMs * 8, 256, 0, lc.stream>>>(a, b, rows, cols, ld, lower_only, out_dev3);
   LPB_LAUNCH_CHECK(lc);
   return LPB_OK;
 }

@@ -330,15 +330,20 @@ def _backward_sub_t(L, w):
     return v
 
 
+DEBUG_SCALARS: dict = {}  # scalars of the most recent Delta::compute (parity debugging; copied into the trace)
+
+
 def delta_compute(pt: FeasiblePoint, rhat: Rhat, pb: Problem, solver: EquationsSolver) -> Delta:
     """Delta::compute, delta.rs:21-49."""
     p, q, u, v = solver.solve_newton_equations(pb, pt.x, rhat)  # :27
-    d_tau = ((rhat.g + 1.0 / pt.tau * rhat.tk - (-float(pb.c.dot(u)) + float(pb.b.dot(v))))
-             / (1.0 / pt.tau * pt.kappa + (-float(pb.c.dot(p)) + float(pb.b.dot(q)))))  # :29-32
+    cu, bv, cp, bq = float(pb.c.dot(u)), float(pb.b.dot(v)), float(pb.c.dot(p)), float(pb.b.dot(q))
+    d_tau = ((rhat.g + 1.0 / pt.tau * rhat.tk - (-cu + bv))
+             / (1.0 / pt.tau * pt.kappa + (-cp + bq)))  # :29-32
     d_x = u + p * d_tau  # :33
     d_y = v + q * d_tau  # :34
     d_z = (rhat.xs - pt.z * d_x) / pt.x  # :37
     d_kappa = 1.0 / pt.tau * (rhat.tk - pt.kappa * d_tau)  # :38
+    DEBUG_SCALARS.update(cp=cp, bq=bq, cu=cu, bv=bv, d_tau=d_tau, d_kappa=d_kappa)  # last call = the corrector
     return Delta(d_x, d_y, d_z, d_tau, d_kappa)
 
 
@@ -461,7 +466,7 @@ class InteriorPoint:
                 print("%.8f\t%s" % (alpha, ind.display()))
             if trace is not None:
                 trace.append(dict(iteration=iteration, alpha=alpha, tau=pt.tau, kappa=pt.kappa,
-                                  **dataclasses.asdict(ind)))
+                                  **dataclasses.asdict(ind), **DEBUG_SCALARS))
             st = ind.status(pt.tau, pt.kappa, self.tol)  # :230-235
             if st == "Optimal":
                 return pt.x / pt.tau, iteration

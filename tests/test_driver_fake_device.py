@@ -77,7 +77,7 @@ def test_driver_matches_oracle_per_iteration(fake, m, n, seed, ip):
         r = tr[k]
         want = [r["alpha"], r["rho_p"], r["rho_d"], r["rho_A"], r["rho_g"], r["rho_mu"], r["obj"], r["bty"],
                 r["tau"], r["kappa"]]
-        np.testing.assert_allclose(trace[k], want, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(trace[k][:10], want, rtol=1e-6, atol=1e-9)
 
 
 def test_driver_status_paths(fake):

@@ -73,7 +73,7 @@ def test_synthetic_parity_with_oracle(m, n, seed, ip, impl):
         r = tr[k]
         want = [r["alpha"], r["rho_p"], r["rho_d"], r["rho_A"], r["rho_g"], r["rho_mu"], r["obj"], r["bty"],
                 r["tau"], r["kappa"]]
-        np.testing.assert_allclose(trace[k], want, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(trace[k][:10], want, rtol=1e-6, atol=1e-9)
 
 
 def test_status_paths():
@@ -190,3 +190,22 @@ def test_host_driven_phase_calls_equal_lpb_solve():
     assert it == res.iteration()
     np.testing.assert_array_equal(x[: len(res.x())], res.x())
     assert fun.value == res.fun()
+
+
+@pytest.mark.parametrize("workload,m,n", [("C1", 512, 1024), ("C2", 4096, 8192), ("C3", 16384, 32768)])
+def test_full_size_configs_match_committed_oracle_fixture(workload, m, n):
+    """BASELINE.json configs C1..C3 at full size against the oracle's outcome committed under tests/golden/
+    (generated by tools/oracle_full_size.py; C3 takes the CPU oracle ~30 min, the GPU ~8 s): same status,
+    iterations within +-1, objective within 1e-8 relative, x within 1e-6 (head entries, sum and 2-norm)."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "oracle_%s_seed0.json" % workload)
+    gold = json.load(open(path))
+    assert gold["status"] == "Optimal" and (gold["m"], gold["n"]) == (m, n)
+    res = lp_b200.InteriorPoint.default().solve(build(*o.synthetic_lp(m, n, 0)))
+    assert abs(res.iteration() - gold["iterations"]) <= 1
+    assert abs(res.fun() - gold["fun"]) <= 1e-8 * abs(gold["fun"])
+    x = res.x()
+    assert np.abs(x[:16] - np.array(gold["x_head"])).max() <= 1e-6
+    assert abs(x.sum() - gold["x_sum"]) <= 1e-6 * len(x)
+    assert abs(np.linalg.norm(x) - gold["x_norm2"]) <= 1e-6 * np.sqrt(len(x))
