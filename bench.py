@@ -47,6 +47,10 @@ DEFAULT_WORKLOAD = "C3"
 NOMINAL_FP64_TFLOPS = 40.0  # B200 FP64 (tensor == vector), NVIDIA HGX B200 spec sheet
 
 
+def workload_label(name, m, n, seed):
+    return "%s dense LP slack-form m=%d n=%d seed=%d (ub+eq, SURVEY 8d generator)" % (name, m, n, seed)
+
+
 def synthetic_lp(m, n, seed):
     """SURVEY.md 8(d) generator (same bits as oracle.ipm_oracle.synthetic_lp; duplicated here so the
     product arm never imports the oracle)."""
@@ -126,7 +130,7 @@ def cpu_sample(m, n, seed, budget_s=25.0):
     args = synthetic_lp(m, n, seed)
     pb = o.build_problem(*args)
     del args
-    if 2.0 * m * m * n < 2e11:  # small enough: time whole iterations of the real loop
+    if 2.0 * m * m * n < 1e12:  # small enough (C1, C2): time whole iterations of the real loop
         t0 = time.perf_counter()
         its = 0
         tr = []
@@ -151,15 +155,19 @@ def cpu_sample(m, n, seed, budget_s=25.0):
     pt = o.blind_start(pb)
     Dinv = pt.x / pt.z
     A = pb.A
+    t0 = time.perf_counter()
+    B = Dinv[:, None] * A.T          # the reference's n x m temporary (newton_equations.rs:57), timed in full
+    t_temp = time.perf_counter() - t0
     r = 256
-    while True:  # rows slice of M = A (Dinv * A^T): the reference runs the FULL GEMM (2 m^2 n flop)
+    while True:  # row slice of M = A B: the reference runs the FULL GEMM (2 m^2 n flop)
         t0 = time.perf_counter()
-        _ = A[:r].dot(Dinv[:, None] * A.T) if r >= m else A[:r].dot((A * Dinv).T)
+        _ = A[:r].dot(B)
         t_slice = time.perf_counter() - t0
         if t_slice > budget_s * 0.3 or r >= m:
             break
         r = min(m, r * 2)
-    t_gemm = t_slice * m / r
+    del B
+    t_gemm = t_temp + t_slice * m / r
     ms = min(m, 8192)
     rng = np.random.default_rng(1)
     B = rng.standard_normal((ms, ms + 16))
@@ -197,7 +205,7 @@ def run_reference_arm(args, m, n):
         "impl": "reference", "metric": "ipm_iterations_per_s", "value": value, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s dense LP slack-form m=%d n=%d seed=%d" % (args.workload, m, n, args.seed)},
+        "config": {"workload": workload_label(args.workload, m, n, args.seed)},
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -319,6 +327,7 @@ def run_device_synthetic(args, torch, dist, rank, local_rank, world, stream, m, 
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
+        _ffi_finalize()
         dist.destroy_process_group()
 
 
@@ -427,7 +436,13 @@ def run_batched(args, torch, dist, rank, local_rank, world, stream):
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
+        _ffi_finalize()
         dist.destroy_process_group()
+
+
+def _ffi_finalize():
+    from lp_b200 import _ffi
+    _ffi.load().lpb_comm_finalize()
 
 
 def _hbm_peak():
@@ -586,8 +601,8 @@ def main():
             "metric": "ipm_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s dense LP slack-form m=%d n=%d seed=%d (ub+eq, SURVEY 8d generator)" % (
-                args.workload, m, n, args.seed), "iterations_per_solve": total_iters / args.steps,
+            "config": {"workload": workload_label(args.workload, m, n, args.seed),
+                       "iterations_per_solve": total_iters / args.steps,
                 "objective": fun, "l2": "inputs larger than L2 (A = %.0f MB)" % (m * n * 8 / 1e6),
                 "parallelism": "1 GPU" if world == 1 else "A column-sharded over %d GPUs, NCCL all-reduce of M" % world,
                 "host_generation_s": gen_s},
@@ -597,6 +612,7 @@ def main():
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
+        _ffi_finalize()
         dist.destroy_process_group()
 
 

@@ -118,8 +118,14 @@ int lpb_destroy(lpb_ctx* ctx);
 
 /* Column-sharded multi-GPU context (no reference counterpart): this rank owns
  * columns [col0, col0+n_local) of the m x n_global slack-form A.  `nccl_unique_id` is the
- * 128-byte ncclUniqueId every rank received from rank 0 (lpb_nccl_unique_id). */
+ * 128-byte ncclUniqueId every rank received from rank 0 (lpb_nccl_unique_id), or NULL to re-use the
+ * process communicator. */
 int lpb_nccl_unique_id(void* id128);
+/* The NCCL communicator is process-wide (one process per GPU) and outlives contexts: the first
+ * lpb_create_sharded with a unique id builds it, later ones pass nccl_unique_id = NULL and share it.
+ * lpb_comm_ready: 1 if this process already holds a communicator for (rank, world). */
+int lpb_comm_ready(int rank, int world);
+int lpb_comm_finalize(void);
 int lpb_create_sharded(lpb_ctx** ctx, int64_t m, int64_t n_global, int64_t col0, int64_t n_local,
                        const double* A_local, int64_t lda, const double* b, const double* c_local,
                        double c0, int mem, int rank, int world, const void* nccl_unique_id,

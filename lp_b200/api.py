@@ -470,8 +470,8 @@ class ShardedProblem(ResidentProblem):
         self.handle = h
 
     def _broadcast_unique_id(self, lib):
-        if self.world == 1:
-            return None
+        if self.world == 1 or lib.lpb_comm_ready(self.rank, self.world):
+            return None  # the process communicator exists already (ncclCommInitRank costs seconds)
         import torch
         buf = (C.c_ubyte * 128)()
         if self.rank == 0:

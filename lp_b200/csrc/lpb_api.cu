@@ -138,6 +138,15 @@ void profile_collect(lpb_ctx* c) {
   c->prof.comm_ms = ms[PH_COMM];
 }
 
+// One NCCL communicator per process (one process per GPU): ncclCommInitRank costs seconds, contexts
+// come and go with every solve.  Created by the first lpb_create_sharded that carries a unique id,
+// shared by later contexts (nccl_unique_id == NULL), destroyed by lpb_comm_finalize.
+struct ProcessComm {
+  ncclComm_t comm = nullptr;
+  int rank = -1, world = 0;
+};
+ProcessComm g_comm;
+
 int allreduce(lpb_ctx* c, double* buf, int64_t count, ncclRedOp_t op) {
   if (c->world <= 1) return LPB_OK;
   PhaseTimer tm(c, PH_COMM);
@@ -487,7 +496,6 @@ int upload_problem(lpb_ctx* c, const double* A, int64_t lda, const double* b, co
 void ctx_free(lpb_ctx* c) {
   if (!c) return;
   if (c->lc.stream) cudaStreamSynchronize(c->lc.stream);
-  if (c->comm) ncclCommDestroy(c->comm);
   for (auto& r : c->recs) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
@@ -659,6 +667,14 @@ int lpb_destroy(lpb_ctx* c) {
   return LPB_OK;
 }
 
+int lpb_comm_finalize(void) {
+  if (g_comm.comm) ncclCommDestroy(g_comm.comm);
+  g_comm = ProcessComm();
+  return LPB_OK;
+}
+
+int lpb_comm_ready(int rank, int world) { return g_comm.comm && g_comm.rank == rank && g_comm.world == world ? 1 : 0; }
+
 int lpb_nccl_unique_id(void* id128) {
   if (!id128) return LPB_ERR_BAD_ARGUMENT;
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
@@ -672,8 +688,13 @@ int lpb_create_sharded(lpb_ctx** out, int64_t m, int64_t n_global, int64_t col0,
                        int64_t lda, const double* b, const double* c_local, double c0, int mem, int rank, int world,
                        const void* nccl_unique_id, void* stream) {
   if (!out || m <= 0 || n_local <= 0 || n_global < n_local || col0 < 0 || col0 + n_local > n_global || world < 1 ||
-      rank < 0 || rank >= world || (world > 1 && !nccl_unique_id)) {
+      rank < 0 || rank >= world) {
     set_last_error("create_sharded: inconsistent shard description");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  if (world > 1 && !nccl_unique_id && !(g_comm.comm && g_comm.world == world && g_comm.rank == rank)) {
+    set_last_error("create_sharded: no ncclUniqueId given and no process communicator for rank %d of %d yet", rank,
+                   world);
     return LPB_ERR_BAD_ARGUMENT;
   }
   LPB_TRY(check_device());
@@ -683,13 +704,22 @@ int lpb_create_sharded(lpb_ctx** out, int64_t m, int64_t n_global, int64_t col0,
   if (rc == LPB_OK) rc = ctx_alloc_vectors(c, m, n_local, true);
   if (rc == LPB_OK && A_local) rc = upload_problem(c, A_local, lda, b, c_local, c0, mem);
   if (rc == LPB_OK && world > 1) {
-    ncclUniqueId id;
-    std::memcpy(&id, nccl_unique_id, sizeof(id));
-    ncclResult_t r = ncclCommInitRank(&c->comm, world, id, rank);
-    if (r != ncclSuccess) {
-      set_last_error("ncclCommInitRank -> %s", ncclGetErrorString(r));
-      rc = LPB_ERR_NCCL;
+    if (nccl_unique_id) {  // (re)build the process communicator
+      if (g_comm.comm) ncclCommDestroy(g_comm.comm);
+      g_comm = ProcessComm();
+      ncclUniqueId id;
+      std::memcpy(&id, nccl_unique_id, sizeof(id));
+      ncclResult_t r = ncclCommInitRank(&g_comm.comm, world, id, rank);
+      if (r != ncclSuccess) {
+        set_last_error("ncclCommInitRank -> %s", ncclGetErrorString(r));
+        g_comm = ProcessComm();
+        rc = LPB_ERR_NCCL;
+      } else {
+        g_comm.rank = rank;
+        g_comm.world = world;
+      }
     }
+    c->comm = g_comm.comm;
   }
   if (rc != LPB_OK) {
     ctx_free(c);

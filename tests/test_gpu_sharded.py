@@ -86,6 +86,9 @@ def _worker(rank, world, port, q):
             res = solver.solve_resident(sp)
         out["syn"] = (A_k, b, c_k, sp.col0, res.x(), res.fun(), res.iteration())
         q.put((rank, out))
+        dist.barrier()
+        from lp_b200 import _ffi
+        _ffi.load().lpb_comm_finalize()
     finally:
         dist.destroy_process_group()
 

@@ -196,7 +196,11 @@ def test_host_driven_phase_calls_equal_lpb_solve():
 def test_full_size_configs_match_committed_oracle_fixture(workload, m, n):
     """BASELINE.json configs C1..C3 at full size against the oracle's outcome committed under tests/golden/
     (generated by tools/oracle_full_size.py; C3 takes the CPU oracle ~30 min, the GPU ~8 s): same status,
-    iterations within +-1, objective within 1e-8 relative, x within 1e-6 (head entries, sum and 2-norm)."""
+    iterations within +-1, objective within 1e-8 relative, x within 1e-6 (head entries, mean and rms).
+    At C3 the x tolerance is 1e-4: the reference's own stopping rule (indicators.rs:66-83) only asks for
+    ||b tau - A x|| <= tol * rho_p0 with rho_p0 = ||b - A 1|| ~ 2.3e4 there, i.e. x / tau is determined to
+    ~2e-5 and two correct runs that stop at slightly different tau (6.92297 vs 6.92327) differ by that much
+    while their objectives agree to 1e-13."""
     import json
     import os
     path = os.path.join(os.path.dirname(__file__), "golden", "oracle_%s_seed0.json" % workload)
@@ -206,6 +210,7 @@ def test_full_size_configs_match_committed_oracle_fixture(workload, m, n):
     assert abs(res.iteration() - gold["iterations"]) <= 1
     assert abs(res.fun() - gold["fun"]) <= 1e-8 * abs(gold["fun"])
     x = res.x()
-    assert np.abs(x[:16] - np.array(gold["x_head"])).max() <= 1e-6
-    assert abs(x.sum() - gold["x_sum"]) <= 1e-6 * len(x)
-    assert abs(np.linalg.norm(x) - gold["x_norm2"]) <= 1e-6 * np.sqrt(len(x))
+    x_tol = 1e-4 if workload == "C3" else 1e-6
+    assert np.abs(x[:16] - np.array(gold["x_head"])).max() <= x_tol
+    assert abs(x.sum() - gold["x_sum"]) <= x_tol * len(x)
+    assert abs(np.linalg.norm(x) - gold["x_norm2"]) <= x_tol * np.sqrt(len(x))
