@@ -223,18 +223,28 @@ def _sync_max_ms(torch, dist, ms):
 
 
 def _roofline(prof_sum, m, n_loc):
-    f_syrk = float(m) * (m + 1) * n_loc
+    """K1 roofline.  `achieved` counts the flop the kernel EXECUTES: m(m+1) * syrk_cols, where syrk_cols
+    is n minus the trailing slack columns that liblpb200 folds into the diagonal of M instead of
+    contracting over them (lpb_profile.syrk_cols).  SURVEY 8(d)'s algorithmic figure m(m+1)n -- what a
+    structure-blind SYRK would execute -- divided by the same time is reported beside it."""
+    launches = max(1, prof_sum.get("syrk_launches", 1))
+    solves = max(1, prof_sum.get("solves", 1))
+    n_exec = prof_sum.get("syrk_cols", 0) / solves or n_loc
+    f_alg = float(m) * (m + 1) * n_loc
+    f_syrk = float(m) * (m + 1) * n_exec
     f_chol = float(m) ** 3 / 3.0
-    syrk_ms = prof_sum.get("syrk_ms", 0.0) / max(1, prof_sum.get("syrk_launches", 1))
+    syrk_ms = prof_sum.get("syrk_ms", 0.0) / launches
     potrf_ms = prof_sum.get("potrf_ms", 0.0) / max(1, prof_sum.get("potrf_launches", 1))
     achieved = f_syrk / (syrk_ms * 1e-3) * 1e-12 if syrk_ms > 0 else None
     return {
         "bound": "tensor", "kernel": "syrk_dmma_kernel (K1, A.diag(x/z).A^T, FP64 DMMA)",
         "achieved": achieved, "peak": NOMINAL_FP64_TFLOPS, "unit": "TFLOP/s",
-        "frac": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None, "traffic": SYRK_TRAFFIC.get((m, n_loc)),
+        "frac": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None, "traffic": SYRK_TRAFFIC.get((m, int(n_exec))),
         "peak_source": "nominal B200 FP64 (MEASURED_PEAKS.json has no FP64 entry; measured on this pool: DMMA issue "
                        "peak 36.95, cuBLAS DGEMM 35.4 TFLOP/s, profiles/fp64_peaks_r01.json)",
-        "flop_per_launch": f_syrk, "ms_per_launch": syrk_ms,
+        "flop_per_launch": f_syrk, "ms_per_launch": syrk_ms, "syrk_cols": n_exec,
+        "algorithmic_flop_per_launch": f_alg,
+        "algorithmic_tflops": (f_alg / (syrk_ms * 1e-3) * 1e-12) if syrk_ms > 0 else None,
         "phase_syrk_plus_cholesky_tflops": ((f_syrk + f_chol) / ((syrk_ms + potrf_ms) * 1e-3) * 1e-12
                                             if syrk_ms + potrf_ms > 0 else None),
         "potrf_ms_per_launch": potrf_ms,
@@ -269,6 +279,7 @@ def _timed_solves(args, torch, dist, solver, rp, local_rank):
         launches += p["launches"]
         for k, v in p.items():
             prof_sum[k] = prof_sum.get(k, 0) + v
+        prof_sum["solves"] = prof_sum.get("solves", 0) + 1
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -541,6 +552,7 @@ def main():
         launches += p["launches"]
         for k, v in p.items():
             prof_sum[k] = prof_sum.get(k, 0) + v
+        prof_sum["solves"] = prof_sum.get("solves", 0) + 1
     e1.record()
     barrier()
     clocks = sampler.stop()

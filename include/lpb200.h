@@ -240,6 +240,8 @@ typedef struct lpb_profile {
   int64_t launches;     /* kernels launched by this library during the last solve */
   int64_t iterations;
   int64_t syrk_launches, potrf_launches;
+  int64_t syrk_cols;    /* columns of A the SYRK contracts over: n minus the trailing singleton (slack) columns,
+                           which are folded into the diagonal of M (executed flop = m (m + 1) syrk_cols) */
 } lpb_profile;
 int lpb_get_profile(lpb_ctx* ctx, lpb_profile* out);
 /* Kernels launched by this library on this context since creation (all entry points). */
@@ -247,7 +249,8 @@ int64_t lpb_launch_count(lpb_ctx* ctx);
 /* Tuning / debug knobs.  "syrk_impl": 0 = DMMA+TMA, 1 = plain DFMA reference kernels (parity tests
  * bisect with it); "solve_impl": 0 = pipelined single-launch solve, 1 = one launch per 128-block
  * step; "solve_grid_cap": > 0 caps the pipelined solve's grid (tests: several block rows per CTA);
- * "profile": 1 = record per-phase events.  Unknown key -> BAD_ARGUMENT. */
+ * "profile": 1 = record per-phase events; "structure": 0 = contract the SYRK over every column of A
+ * (default 1: trailing singleton columns -- the slack block -- are folded into the diagonal of M).  Unknown key -> BAD_ARGUMENT. */
 int lpb_set_option(lpb_ctx* ctx, const char* key, int64_t value);
 
 /* Copy a named device buffer to the host (debugging / parity tests): "M" (m x ldm), n-vectors

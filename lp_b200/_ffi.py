@@ -66,7 +66,8 @@ class lpb_profile(C.Structure):
     _fields_ = [("total_ms", C.c_double), ("syrk_ms", C.c_double), ("potrf_ms", C.c_double),
                 ("solve_ms", C.c_double), ("sweep_ms", C.c_double), ("vector_ms", C.c_double),
                 ("comm_ms", C.c_double), ("launches", C.c_int64), ("iterations", C.c_int64),
-                ("syrk_launches", C.c_int64), ("potrf_launches", C.c_int64)]
+                ("syrk_launches", C.c_int64), ("potrf_launches", C.c_int64),
+                ("syrk_cols", C.c_int64)]
 
 
 # name -> (restype, argtypes); must list EVERY symbol include/lpb200.h declares

@@ -431,14 +431,24 @@ def solve_batched(A, b, c, n_slack: int = 0, solver: Optional["InteriorPoint"] =
     return BatchedResult(x[:, : n - n_slack].copy(), x, fun, it, st)
 
 
-def shard_columns(n: int, world: int):
-    """Contiguous column blocks [col0, col0 + n_local) per rank (even widths keep 16-byte alignment)."""
-    per = -(-n // world)
+def shard_columns(n: int, world: int, n_slack: int = 0):
+    """Contiguous column blocks [col0, col0 + n_local) per rank (even widths keep 16-byte alignment).
+
+    The trailing `n_slack` columns of the slack form cost nothing in the SYRK (liblpb200 folds them into
+    the diagonal of M), so only the n - n_slack dense columns are balanced over the ranks; the slack
+    block rides along with the last rank."""
+    n_dense = max(0, n - max(0, int(n_slack)))
+    if n_dense == 0:
+        n_dense = n
+    per = -(-n_dense // world)
     per += per & 1
     out = []
     for r in range(world):
-        c0 = min(n, r * per)
-        out.append((c0, max(0, min(per, n - c0))))
+        c0 = min(n_dense, r * per)
+        nl = max(0, min(per, n_dense - c0))
+        if r == world - 1:
+            nl = n - c0
+        out.append((c0, nl))
     return out
 
 
@@ -453,7 +463,7 @@ class ShardedProblem(ResidentProblem):
         self.n_global = n_global
         self.n_slack = problem.n_slack()
         self.rank, self.world, self._dist = rank, world, dist
-        self.shards = shard_columns(n_global, world)
+        self.shards = shard_columns(n_global, world, self.n_slack)
         self.col0, self.n = self.shards[rank]
         if self.n <= 0:
             raise ValueError("more ranks than column blocks")
@@ -514,7 +524,7 @@ class SyntheticShardedProblem(ShardedProblem):
         self.m, self.n_global = int(m), int(n_global)
         self.n_slack = self.m // 2
         self.rank, self.world, self._dist = rank, world, dist
-        self.shards = shard_columns(self.n_global, world)
+        self.shards = shard_columns(self.n_global, world, self.n_slack)
         self.col0, self.n = self.shards[rank]
         if self.n <= 0:
             raise ValueError("more ranks than column blocks")

@@ -99,6 +99,10 @@ int k_fill_vec(LaunchCtx& lc, double* v, int64_t count, int64_t idx0, uint64_t s
                int64_t neg_below);
 int k_slack_identity(LaunchCtx& lc, double* A, int64_t rows, int64_t cols, int64_t lda, int64_t col0, int64_t n0);
 int k_add_vec(LaunchCtx& lc, double* out, const double* a, const double* b, int64_t count, int64_t count_b);
+// per-column structure of A: nnz count, last non-zero row (-1 if none), value (valid iff nnz == 1)
+int k_col_structure(LaunchCtx& lc, const double* A, int64_t m, int64_t n, int64_t lda, int* nnz, int* row, double* val);
+// M[r][r] += sq[r] * dinv[col[r]] where col[r] >= 0 (singleton columns folded into the diagonal)
+int k_diag_add(LaunchCtx& lc, int64_t m, double* M, int64_t ldm, const int* col, const double* sq, const double* dinv);
 // order-independent bit checksum of a matrix block (replica-agreement checks of the sharded path)
 int k_diff(LaunchCtx& lc, const double* a, const double* b, int64_t rows, int64_t cols, int64_t ld, int lower_only,
            unsigned long long* out_dev3);

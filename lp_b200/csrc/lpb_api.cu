@@ -41,6 +41,12 @@ struct lpb_ctx {
   double c0 = 0.0;
   double *A = nullptr, *M = nullptr;
   double *b = nullptr, *y = nullptr, *rP = nullptr, *dy = nullptr, *t = nullptr, *W = nullptr, *R = nullptr;
+  // Column structure (analyze_structure): columns [n_dense, n) are singleton / zero columns -- the slack block
+  // [I; 0] of linear_program.rs:145-156 -- folded into the diagonal of M instead of being contracted over.
+  int64_t n_dense = 0, n_singleton = 0;
+  int use_structure = 1;
+  int* sgl_col = nullptr;     // m: local column whose only non-zero sits in this row, or -1
+  double* sgl_sq = nullptr;   // m: that entry squared
   int refine = 1;  // iterative-refinement steps per sym_solve (0 = the plain factor-and-solve of the reference)
   double *c = nullptr, *x = nullptr, *z = nullptr, *rD = nullptr, *dinv = nullptr, *xs = nullptr, *r1 = nullptr,
          *p = nullptr, *u = nullptr, *dx = nullptr, *dz = nullptr, *xo = nullptr;
@@ -232,11 +238,15 @@ struct CudaDev {
     }
     {
       PhaseTimer tm(c, PH_SYRK);
-      if (c->syrk_impl == 1)
-        LPB_TRY(k_syrk_simple(c->lc, c->m, c->n, c->A, c->lda, c->dinv, c->M, c->ldm));
+      if (c->n_dense <= 0)  // a shard made of slack columns only
+        LPB_CUDA(cudaMemsetAsync(c->M, 0, sizeof(double) * (size_t)(c->m * c->ldm), c->lc.stream));
+      else if (c->syrk_impl == 1)
+        LPB_TRY(k_syrk_simple(c->lc, c->m, c->n_dense, c->A, c->lda, c->dinv, c->M, c->ldm));
       else
-        LPB_TRY(k_syrk_dmma(c->lc, c->m, c->n, c->A, c->lda, c->dinv, c->M, c->ldm));
+        LPB_TRY(k_syrk_dmma(c->lc, c->m, c->n_dense, c->A, c->lda, c->dinv, c->M, c->ldm));
+      if (c->n_singleton > 0) LPB_TRY(k_diag_add(c->lc, c->m, c->M, c->ldm, c->sgl_col, c->sgl_sq, c->dinv));
       c->prof.syrk_launches++;
+      c->prof.syrk_cols = c->n_dense;
     }
     LPB_TRY(allreduce(c, c->M, c->m * c->ldm, ncclSum));
     LPB_TRY(check_replicated(c, "M after the all-reduce", c->M, c->m, c->m, c->ldm, 1));
@@ -467,12 +477,77 @@ int ctx_alloc_vectors(lpb_ctx* c, int64_t m, int64_t n, bool with_matrices) {
   LPB_TRY(dev_alloc(c, &c->t, 2 * m));
   LPB_TRY(dev_alloc(c, &c->W, 2 * m));
   LPB_TRY(dev_alloc(c, &c->R, 2 * m));
+  LPB_TRY(dev_alloc(c, &c->sgl_sq, m));
+  {
+    void* q = nullptr;
+    LPB_CUDA(cudaMalloc(&q, sizeof(int) * (size_t)m));
+    c->allocs.push_back(q);
+    c->sgl_col = static_cast<int*>(q);
+  }
   double** nv[] = {&c->c, &c->x, &c->z, &c->rD, &c->dinv, &c->xs, &c->r1, &c->p, &c->u, &c->dx, &c->dz, &c->xo};
   for (auto p : nv) LPB_TRY(dev_alloc(c, p, round_up(n, 2)));
   LPB_CUDA(cudaMemsetAsync(c->A, 0, sizeof(double) * (size_t)(m * c->lda), c->lc.stream));
   LPB_CUDA(cudaMemsetAsync(c->M, 0, sizeof(double) * (size_t)(m * c->ldm), c->lc.stream));
   LPB_CUDA(cudaMemsetAsync(c->dx, 0, sizeof(double) * (size_t)round_up(n, 2), c->lc.stream));
   LPB_CUDA(cudaMemsetAsync(c->dz, 0, sizeof(double) * (size_t)round_up(n, 2), c->lc.stream));
+  return LPB_OK;
+}
+
+// Find the trailing run of singleton / zero columns of the resident A (one pass over A on the device, the
+// bookkeeping on the host) and fold it out of the SYRK: see lpb_ctx::n_dense.  The run must map its
+// columns to DISTINCT rows (always true for a slack block), so the diagonal update needs no atomics and
+// stays deterministic; otherwise, or when the run is shorter than one K-block, A is treated as dense.
+int analyze_structure(lpb_ctx* c) {
+  c->n_dense = c->n;
+  c->n_singleton = 0;
+  if (!c->use_structure || !c->A || c->n < 16) return LPB_OK;
+  const int64_t n = c->n, m = c->m;
+  int* d_int = nullptr;
+  double* d_val = nullptr;
+  LPB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_int), sizeof(int) * (size_t)(2 * n)));
+  if (cudaMalloc(reinterpret_cast<void**>(&d_val), sizeof(double) * (size_t)n) != cudaSuccess) {
+    cudaFree(d_int);
+    set_last_error("analyze_structure: out of device memory");
+    return LPB_ERR_CUDA;
+  }
+  std::vector<int> h_int((size_t)(2 * n));
+  std::vector<double> h_val((size_t)n);
+  int rc = k_col_structure(c->lc, c->A, m, n, c->lda, d_int, d_int + n, d_val);
+  if (rc == LPB_OK &&
+      (cudaMemcpyAsync(h_int.data(), d_int, sizeof(int) * (size_t)(2 * n), cudaMemcpyDeviceToHost, c->lc.stream) !=
+           cudaSuccess ||
+       cudaMemcpyAsync(h_val.data(), d_val, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->lc.stream) !=
+           cudaSuccess ||
+       cudaStreamSynchronize(c->lc.stream) != cudaSuccess)) {
+    set_last_error("analyze_structure: copy failed");
+    rc = LPB_ERR_CUDA;
+  }
+  cudaFree(d_int);
+  cudaFree(d_val);
+  LPB_TRY(rc);
+  const int* nnz = h_int.data();
+  const int* row = h_int.data() + n;
+  std::vector<int> col_of_row((size_t)m, -1);
+  std::vector<double> sq((size_t)m, 0.0);
+  int64_t nd = n, nsgl = 0;
+  while (nd > 0) {
+    const int64_t j = nd - 1;
+    if (nnz[j] > 1) break;
+    if (nnz[j] == 1) {
+      const int r = row[j];
+      if (r < 0 || r >= m || col_of_row[r] >= 0) break;
+      col_of_row[r] = (int)j;
+      sq[r] = h_val[j] * h_val[j];
+      ++nsgl;
+    }
+    --nd;
+  }
+  if (n - nd < 16) return LPB_OK;  // not worth a separate pass
+  LPB_CUDA(cudaMemcpyAsync(c->sgl_col, col_of_row.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, c->lc.stream));
+  LPB_CUDA(cudaMemcpyAsync(c->sgl_sq, sq.data(), sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, c->lc.stream));
+  LPB_CUDA(cudaStreamSynchronize(c->lc.stream));  // the host vectors go out of scope
+  c->n_dense = nd;
+  c->n_singleton = nsgl;
   return LPB_OK;
 }
 
@@ -490,7 +565,7 @@ int upload_problem(lpb_ctx* c, const double* A, int64_t lda, const double* b, co
   c->c0 = c0;
   c->has_problem = true;
   c->have_pq = false;
-  return LPB_OK;
+  return analyze_structure(c);
 }
 
 void ctx_free(lpb_ctx* c) {
@@ -780,6 +855,11 @@ int lpb_create_sharded_synthetic(lpb_ctx** out, int64_t m, int64_t n_global, int
   c->c0 = 0.0;
   c->has_problem = true;
   c->have_pq = false;
+  rc = analyze_structure(c);
+  if (rc != LPB_OK) {
+    ctx_free(c);
+    return rc;
+  }
   *out = c;
   return LPB_OK;
 }
@@ -1062,6 +1142,10 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
     if (value < 0 || value > 4) return LPB_ERR_BAD_ARGUMENT;
     c->refine = (int)value;
     return LPB_OK;
+  }
+  if (k == "structure") {  // 0: contract over every column of A (no slack-column shortcut)
+    c->use_structure = value != 0;
+    return c->has_problem ? analyze_structure(c) : LPB_OK;
   }
   if (k == "potrf_verify") {
     c->potrf_verify = (int)value;

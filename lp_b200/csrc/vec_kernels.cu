@@ -727,6 +727,70 @@ int k_checksum(LaunchCtx& lc, const double* v, int64_t rows, int64_t cols, int64
 }
 
 
+// ------------------------------------------------------------------ column structure of A (slack columns)
+// The slack form [[A_ub, I], [A_eq, 0]] (linear_program.rs:145-156) ends in n_slack singleton columns.
+// A singleton column s e_r contributes s^2 d_j to M[r][r] and nothing else, so the SYRK only has to
+// contract over the dense leading columns.  One pass over A: per column the number of non-zeros, the
+// (last) row holding one and its value.  Row chunks run in parallel; the counts meet in atomics, and
+// `val` is only meaningful when the final count is exactly 1 (then exactly one thread stored it).
+__global__ void col_structure_kernel(const double* __restrict__ A, int64_t m, int64_t n, int64_t lda,
+                                     int rows_per_chunk, int* __restrict__ nnz, int* __restrict__ row,
+                                     double* __restrict__ val) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+  int64_t r1 = r0 + rows_per_chunk;
+  if (r1 > m) r1 = m;
+  int cnt = 0, last = -1;
+  double v = 0.0;
+  const double* __restrict__ Ap = A + j;
+#pragma unroll 4
+  for (int64_t r = r0; r < r1; ++r) {
+    const double a = __ldg(Ap + r * lda);
+    if (a != 0.0) {  // NaN counts as a non-zero
+      ++cnt;
+      last = (int)r;
+      v = a;
+    }
+  }
+  if (cnt > 0) {
+    atomicAdd(nnz + j, cnt);
+    atomicMax(row + j, last);
+    if (cnt == 1) val[j] = v;
+  }
+}
+int k_col_structure(LaunchCtx& lc, const double* A, int64_t m, int64_t n, int64_t lda, int* nnz, int* row,
+                    double* val) {
+  if (m <= 0 || n <= 0) return LPB_OK;
+  LPB_CUDA(cudaMemsetAsync(nnz, 0, sizeof(int) * (size_t)n, lc.stream));
+  LPB_CUDA(cudaMemsetAsync(row, 0xff, sizeof(int) * (size_t)n, lc.stream));  // -1
+  LPB_CUDA(cudaMemsetAsync(val, 0, sizeof(double) * (size_t)n, lc.stream));
+  const int cb = (int)ceil_div(n, 128);
+  int64_t chunks = ceil_div((int64_t)kNumSMs * 16, cb);
+  if (chunks > 1024) chunks = 1024;
+  if (chunks > m) chunks = m;
+  const int rpc = (int)ceil_div(m, chunks);
+  col_structure_kernel<<<dim3(cb, (unsigned)ceil_div(m, rpc)), 128, 0, lc.stream>>>(A, m, n, lda, rpc, nnz, row, val);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+// M[r][r] += sq[r] * dinv[col[r]] for the rows that own a singleton column (col[r] >= 0).
+__global__ void diag_add_kernel(int64_t m, double* __restrict__ M, int64_t ldm, const int* __restrict__ col,
+                                const double* __restrict__ sq, const double* __restrict__ dinv) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  const int j = col[r];
+  if (j >= 0) M[r * ldm + r] += sq[r] * dinv[j];
+}
+int k_diag_add(LaunchCtx& lc, int64_t m, double* M, int64_t ldm, const int* col, const double* sq,
+               const double* dinv) {
+  if (m <= 0) return LPB_OK;
+  diag_add_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, lc.stream>>>(m, M, ldm, col, sq, dinv);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
 // Debug: compare two matrices bit for bit (lower triangle if lower_only); out = {count, min col, min row}.
 __global__ void diff_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t rows, int64_t cols,
                             int64_t ld, int lower_only, unsigned long long* __restrict__ out) {

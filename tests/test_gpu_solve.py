@@ -214,3 +214,85 @@ def test_full_size_configs_match_committed_oracle_fixture(workload, m, n):
     assert np.abs(x[:16] - np.array(gold["x_head"])).max() <= x_tol
     assert abs(x.sum() - gold["x_sum"]) <= x_tol * len(x)
     assert abs(np.linalg.norm(x) - gold["x_norm2"]) <= x_tol * np.sqrt(len(x))
+
+
+def _factor_on_device(pb, structure):
+    """form_and_factor at the blind start; returns (lower factor L, lpb_profile.syrk_cols after a solve)."""
+    with ResidentProblem(pb) as rp:
+        rp.set_option("structure", structure)
+        lib = _ffi.load()
+        assert lib.lpb_blind_start(rp.handle) == 0
+        assert lib.lpb_form_and_factor(rp.handle) == 0
+        m = rp.m
+        ldm = (m + 15) // 16 * 16
+        L = np.tril(rp.debug_read("M").reshape(m, ldm)[:, :m])
+        res = lp_b200.InteriorPoint.default().solve_resident(rp)
+        return L, rp.profile()["syrk_cols"], res
+
+
+@pytest.mark.parametrize("m,n,seed", [(64, 128, 0), (130, 301, 2), (512, 1024, 0), (300, 1500, 5)])
+def test_slack_columns_are_folded_into_the_diagonal(m, n, seed):
+    """The slack block [I; 0] of linear_program.rs:145-156 is not contracted over: the SYRK runs on the
+    n - n_slack dense columns and d_slack lands on the diagonal.  Same factor (1e-12 relative), same solve."""
+    args = o.synthetic_lp(m, n, seed)
+    pb = build(*args)
+    L1, cols1, res1 = _factor_on_device(pb, 1)
+    L0, cols0, res0 = _factor_on_device(pb, 0)
+    assert cols0 == n and cols1 == n - pb.n_slack()
+    assert np.abs(L1 - L0).max() <= 1e-12 * np.abs(L0).max()
+    assert res1.iteration() == res0.iteration()
+    assert np.abs(res1.x() - res0.x()).max() <= 1e-9
+    assert abs(res1.fun() - res0.fun()) <= 1e-10 * max(1.0, abs(res0.fun()))
+
+
+def test_structure_detection_edge_cases():
+    """Scaled singleton columns fold as s^2 d; two singleton columns hitting the same row stop the run
+    (the earlier one stays in the dense part); a short run (< 16 columns) is left dense."""
+    rng = np.random.default_rng(11)
+    m, n0 = 40, 60
+    A0 = rng.standard_normal((m, n0))
+    tail = np.zeros((m, 24))
+    for j in range(24):
+        tail[j, j] = 1.0 + 0.25 * j          # scaled unit columns, distinct rows 0..23
+    tail[:, 3] = 0.0                          # an all-zero column inside the run
+    x0 = rng.uniform(0.5, 1.5, n0 + 24)
+    A = np.hstack([A0, tail])
+    b = A @ x0
+    c = A.T @ rng.standard_normal(m) + rng.uniform(0.5, 1.5, n0 + 24)
+    lib = _ffi.load()
+
+    def factor(Amat, structure):
+        bufs = [lp_b200.api._HostBuffer(s) for s in (Amat.shape, b.shape, (Amat.shape[1],))]
+        bufs[0].array[:] = Amat
+        bufs[1].array[:] = b
+        bufs[2].array[:] = c[: Amat.shape[1]]
+        pb = lp_b200.Problem(bufs[0], bufs[1], bufs[2], 0.0, 0)
+        with ResidentProblem(pb) as rp:
+            rp.set_option("structure", structure)
+            assert lib.lpb_blind_start(rp.handle) == 0
+            assert lib.lpb_form_and_factor(rp.handle) == 0
+            ldm = (m + 15) // 16 * 16
+            L = np.tril(rp.debug_read("M").reshape(m, ldm)[:, :m])
+            try:
+                lp_b200.InteriorPoint.custom().max_iter(1).build().solve_resident(rp)
+            except lp_b200.LinearProgramError:
+                pass
+            return L, rp.profile()["syrk_cols"]
+
+    Lref = np.linalg.cholesky(A @ A.T)        # blind start: x = z = 1, Dinv = 1
+    L, cols = factor(A, 1)
+    assert cols == n0
+    assert np.abs(L - Lref).max() <= 1e-11 * np.abs(Lref).max()
+    # collision: the last column repeats row 5 -> only the columns behind the first repeat are folded
+    A2 = A.copy()
+    A2[:, -1] = 0.0
+    A2[5, -1] = 3.0
+    L2, cols2 = factor(A2, 1)
+    Lref2 = np.linalg.cholesky(A2 @ A2.T)
+    assert cols2 == n0 + 6                    # columns n0+6 .. end fold (row 5 is taken by the last one)
+    assert np.abs(L2 - Lref2).max() <= 1e-11 * np.abs(Lref2).max()
+    # short run: 8 singleton columns only -> dense
+    A3 = A[:, : n0 + 8]
+    L3, cols3 = factor(A3, 1)
+    assert cols3 == n0 + 8
+    assert np.abs(L3 - np.linalg.cholesky(A3 @ A3.T)).max() <= 1e-11 * np.abs(Lref).max()

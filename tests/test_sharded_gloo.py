@@ -32,7 +32,7 @@ def _worker(rank, world, port, q):
         out = {}
         for (m, n, seed) in [(32, 80, 0), (64, 128, 3)]:
             pb = o.build_problem(*o.synthetic_lp(m, n, seed))
-            shards = shard_columns(n, world)
+            shards = shard_columns(n, world, m // 2)
             c0, nk = shards[rank]
             st, xk, it = solve_sharded(np.ascontiguousarray(pb.A[:, c0:c0 + nk]), pb.b, pb.c[c0:c0 + nk], n,
                                        TorchComm(dist))
@@ -83,14 +83,20 @@ def test_shard_columns_partition():
     from lp_b200.api import shard_columns
     for n in (1, 7, 128, 1001, 32768, 131072):
         for world in (1, 2, 3, 4, 8):
-            sh = shard_columns(n, world)
-            assert len(sh) == world
-            assert sum(nl for _, nl in sh) == n
-            pos = 0
-            for c0, nl in sh:
-                assert c0 == pos or nl == 0
-                assert c0 % 2 == 0 or nl == 0   # even offsets keep 16-byte alignment of every shard
-                pos += nl
+            for n_slack in (0, n // 4, n // 8 + 1, n):
+                sh = shard_columns(n, world, n_slack)
+                assert len(sh) == world
+                assert sum(nl for _, nl in sh) == n
+                pos = 0
+                for c0, nl in sh:
+                    assert c0 == pos or nl == 0
+                    assert c0 % 2 == 0 or nl == 0   # even offsets keep 16-byte alignment of every shard
+                    pos += nl
+                # the dense columns (everything but the trailing slack block) are balanced to within one pair
+                n_dense = n - n_slack if n_slack < n else n
+                dense = [max(0, min(c0 + nl, n_dense) - c0) for c0, nl in sh]
+                assert sum(dense) == n_dense
+                assert max(dense) <= -(-n_dense // world) + 1
 
 
 def test_local_comm_equals_unsharded():
