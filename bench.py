@@ -122,14 +122,19 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU baseline / reference arm
-def cpu_sample(m, n, seed, budget_s=25.0):
+def cpu_problem(m, n, seed):
+    """The workload LP as the oracle's Problem (built once per process: generation is not what is timed)."""
+    from oracle import ipm_oracle as o
+    return o.build_problem(*synthetic_lp(m, n, seed))
+
+
+def cpu_sample(m, n, seed, budget_s=25.0, pb=None):
     """Time the oracle (the reference's algorithm on host cores, OpenBLAS threads) on a bounded
     sample of the workload.  Returns (iterations_per_s, sample_description, cores)."""
     from oracle import ipm_oracle as o
     cores = os.cpu_count() or 1
-    args = synthetic_lp(m, n, seed)
-    pb = o.build_problem(*args)
-    del args
+    if pb is None:
+        pb = cpu_problem(m, n, seed)
     if 2.0 * m * m * n < 1e12:  # small enough (C1, C2): time whole iterations of the real loop
         t0 = time.perf_counter()
         its = 0
@@ -195,9 +200,10 @@ def run_reference_arm(args, m, n):
         return
     vals = []
     desc, cores = "", 1
+    pb = cpu_problem(m, n, args.seed)
     for i in range(args.warmup + args.steps):
         budget = 20.0 if i >= args.warmup else 5.0
-        v, desc, cores = cpu_sample(m, n, args.seed, budget_s=budget)
+        v, desc, cores = cpu_sample(m, n, args.seed, budget_s=budget, pb=pb)
         if i >= args.warmup:
             vals.append(v)
     value = float(np.mean(vals))
@@ -294,6 +300,7 @@ def run_device_synthetic(args, torch, dist, rank, local_rank, world, stream, m, 
     solver = lp_b200.InteriorPoint.default()
     t0 = time.perf_counter()
     rp = SyntheticShardedProblem(m, n, args.seed, rank, world, dist, stream=stream)
+    rp.set_option("potrf_dist", args.potrf_dist)
     torch.cuda.synchronize()
     gen_s = time.perf_counter() - t0
     ms, total_iters, launches, prof_sum, clocks, res = _timed_solves(args, torch, dist, solver, rp, local_rank)
@@ -330,7 +337,8 @@ def run_device_synthetic(args, torch, dist, rank, local_rank, world, stream, m, 
                        "iterations_per_solve": total_iters / args.steps, "objective": res.fun(),
                        "l2": "inputs larger than L2 (A shard = %.0f MB)" % (m * n_loc * 8 / 1e6),
                        "parallelism": "1 GPU" if world == 1 else
-                       "A column-sharded over %d GPUs, NCCL all-reduce of M" % world,
+                       "A column-sharded over %d GPUs, NCCL all-reduce of M, %s Cholesky" % (
+                           world, "panel-broadcast distributed" if args.potrf_dist else "replicated"),
                        "device_generation_s": gen_s},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": _roofline(prof_sum, m, n_loc),
             "phases_ms_per_solve": phases, "cpu_baseline": None,
@@ -477,6 +485,8 @@ def main():
     ap.add_argument("--device-synthetic", action="store_true",
                     help="generate the LP on the device per column shard (always on for C5)")
     ap.add_argument("--batch", type=int, default=C4_BATCH)
+    ap.add_argument("--potrf-dist", type=int, default=1, choices=[0, 1],
+                    help="N > 1: 1 = distributed panel-broadcast Cholesky (default), 0 = replicated on every rank")
     args = ap.parse_args()
     m, n = WORKLOADS[args.workload]
 
@@ -521,6 +531,7 @@ def main():
 
     if world > 1:
         rp = ShardedProblem(problem, rank, world, dist, stream=stream)
+        rp.set_option("potrf_dist", args.potrf_dist)
     else:
         rp = ResidentProblem(problem, stream=stream)
 
@@ -616,7 +627,8 @@ def main():
             "config": {"workload": workload_label(args.workload, m, n, args.seed),
                        "iterations_per_solve": total_iters / args.steps,
                 "objective": fun, "l2": "inputs larger than L2 (A = %.0f MB)" % (m * n * 8 / 1e6),
-                "parallelism": "1 GPU" if world == 1 else "A column-sharded over %d GPUs, NCCL all-reduce of M" % world,
+                "parallelism": "1 GPU" if world == 1 else "A column-sharded over %d GPUs, NCCL all-reduce of M, %s Cholesky" % (
+                           world, "panel-broadcast distributed" if args.potrf_dist else "replicated"),
                 "host_generation_s": gen_s},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "phases_ms_per_solve": phases, "cpu_baseline": cpu,

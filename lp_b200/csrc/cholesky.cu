@@ -13,6 +13,10 @@
 // in which each CTA forms x_k = inv(L_kk) b_k itself (a 128 x 128 GEMV out of L2) and applies the
 // rank-128 update to its own rows / columns.
 // The substitution-based trsm / trsv kernels below are the plain reference path (syrk_impl = 1).
+#include <nccl.h>
+
+#include <algorithm>
+
 #include "kernels.hpp"
 
 namespace lpb {
@@ -78,11 +82,12 @@ constexpr int TWP = 9;        // pitch of the per-warp 16 x 8 scratch of the blo
 
 __global__ void __launch_bounds__(512)
 potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __restrict__ info,
-                 double* __restrict__ Linv) {
+                 double* __restrict__ Linv, int full_inverse) {
   extern __shared__ double S[];    // NB*LDS block
   double* rdiag = S + NB * LDS;    // NB: 1 / L[i][i]
   double* Xd = rdiag + NB;         // SB * XDP
   double* Tw = Xd + SB * XDP;      // 16 warps * SB * TWP
+  double* cbuf = Tw + 16 * SB * TWP;  // 2 * SB: column j of the diagonal sub-block, double-buffered
   const int tid = threadIdx.y * 32 + threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned full = 0xffffffffu;
   double* blk = Mat + (int64_t)k0 * ldm + k0;
@@ -97,55 +102,58 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
   for (int kb = 0; kb < NSB; ++kb) {
     const int c0 = kb * SB;
     if (warp == 0) {
-      // ---- factor the 16 x 16 diagonal sub-block in registers: lane i (and its mirror i + 16) = row i
+      // ---- the serial heart of the factorisation: ONE warp factors the 16 x 16 diagonal sub-block and inverts
+      // it in the same 16 pivot steps.  Lanes 0..15 hold row i of the sub-block (v[k] = a[i][k]); lanes 16..31
+      // hold the running sums of the forward substitution L x = e_i for column i of X = inv(L_dd)
+      // (v[r] = sum_{l<r} L[r][l] x_l, replaced by x_r at step r).  Both need exactly column j of L at pivot
+      // step j -- broadcast through shared memory -- and then the same FMA  v[k] += mult * L[k][j], k > j.
+      // sqrt and the divisions are one rsqrt plus Newton corrections (results within an ulp of IEEE).
       const int i = lane & 15;
-      double a[SB];
+      const bool inv_lane = lane >= SB;
+      double v[SB];
 #pragma unroll
-      for (int k = 0; k < SB; ++k) a[k] = (k <= i) ? S[(c0 + i) * LDS + c0 + k] : 0.0;
-      double mydiag = 1.0;
+      for (int k = 0; k < SB; ++k) v[k] = (!inv_lane && k <= i) ? S[(c0 + i) * LDS + c0 + k] : 0.0;
+      double myrd = 1.0;
 #pragma unroll
       for (int j = 0; j < SB; ++j) {
-        const double ajj = __shfl_sync(full, a[j], j);
+        const double ajj = __shfl_sync(full, v[j], j);
         const bool bad = !(ajj > 0.0) || !isfinite(ajj);
         if (bad && lane == 0 && *info == 0) *info = k0 + c0 + j + 1;
-        const double d = bad ? __longlong_as_double(0x7ff8000000000000ll) : sqrt(ajj);
-        double l = a[j] / d;
-        if (i == j) {
-          l = d;
-          mydiag = d;
+        double rs = rsqrt(ajj);
+        double d = ajj * rs;
+        d = fma(fma(-d, d, ajj), 0.5 * rs, d);    // sqrt(ajj)
+        rs = fma(fma(-d, rs, 1.0), rs, rs);       // 1 / sqrt(ajj)
+        if (bad) d = rs = __longlong_as_double(0x7ff8000000000000ll);
+        double l;
+        if (!inv_lane) {
+          l = v[j] * rs;
+          l = fma(fma(-l, d, v[j]), rs, l);       // a[i][j] / d
+          if (i == j) l = d;
+        } else {
+          l = ((i == j ? 1.0 : 0.0) - v[j]) * rs;  // x_j of column i
         }
-        a[j] = l;
-#pragma unroll
-        for (int k = 0; k < SB; ++k) {
-          if (k > j) {  // compile-time after unrolling
-            const double lk = __shfl_sync(full, l, k);
-            a[k] -= (i >= k) ? l * lk : 0.0;
-          }
-        }
-      }
-      if (lane < SB) {
+        if (i == j) myrd = rs;
+        v[j] = l;
+        double* cb = cbuf + (j & 1) * SB;
+        if (!inv_lane) cb[i] = l;
+        __syncwarp();
+        const double mult = inv_lane ? l : -l;
 #pragma unroll
         for (int k = 0; k < SB; ++k)
-          if (k <= i) S[(c0 + i) * LDS + c0 + k] = a[k];
+          if (k > j) v[k] = fma(mult, cb[k], v[k]);  // entries above a row's diagonal are garbage, never read
       }
-      __syncwarp();
-      // ---- X = inv(L_dd): lane c owns column c;  x_i = -(sum_{l<i} L[i][l] x_l) / L[i][i]
-      const double rdc = 1.0 / mydiag;
-      double x[SB];
+      if (!inv_lane) {
+        rdiag[c0 + i] = myrd;
 #pragma unroll
-      for (int r = 0; r < SB; ++r) {
-        double s = 0.0;
-#pragma unroll
-        for (int l = 0; l < r; ++l) s += S[(c0 + r) * LDS + c0 + l] * x[l];
-        const double rdr = __shfl_sync(full, rdc, r);
-        x[r] = (r == i) ? rdc : ((r > i) ? -s * rdr : 0.0);
+        for (int k = 0; k < SB; ++k)
+          if (k <= i) S[(c0 + i) * LDS + c0 + k] = v[k];
       }
-      if (lane < SB) {
-        rdiag[c0 + i] = rdc;
+      __syncwarp();  // the factor rows are written before the transposed inverse lands above the diagonal
+      if (inv_lane) {
 #pragma unroll
         for (int r = 0; r < SB; ++r) {
-          Xd[r * XDP + i] = x[r];                               // X[r][c = i], zero above the diagonal
-          if (r > i) S[(c0 + i) * LDS + c0 + r] = x[r];         // X^T in the upper triangle
+          Xd[r * XDP + i] = (r >= i) ? v[r] : 0.0;          // X[r][c = i], zero above the diagonal
+          if (r > i) S[(c0 + i) * LDS + c0 + r] = v[r];     // X^T in the upper triangle
         }
       }
     }
@@ -212,8 +220,10 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
     if (r < nb && c <= r) blk[(int64_t)r * ldm + c] = S[r * LDS + c];
   }
 
-  // ---- off-diagonal blocks of X, one block diagonal at a time; block (i, j) by a pair of warps
-  {
+  // ---- off-diagonal blocks of X, one block diagonal at a time; block (i, j) by a pair of warps.  Only the
+  // full-inverse consumers need them (trsm_impl 2, solve_impl 1); the default TRSM and the pipelined solve
+  // use the 16 x 16 diagonal inverses alone, so this stage is normally skipped (the blocks stay zero).
+  if (full_inverse) {
     const int b = warp >> 1, h = warp & 1;
     const int ii = lane & 15, cg = lane >> 4;
     double* tw = Tw + warp * SB * TWP;
@@ -399,6 +409,97 @@ trsm_blocked_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int m, const 
   for (int idx = tid; idx < TBR * NB; idx += 256) {
     const int rr = idx >> 7, c = idx & (NB - 1);
     if (r0 + rr < m) Mat[(r0 + rr) * ldm + k0 + c] = SP[rr * LDP + c];
+  }
+}
+
+// ------------------------------------------------------------------ panel TRSM, blocked substitution on the DMMA pipe
+// The same algorithm as trsm_blocked_kernel (substitution between the 16-column sub-blocks, the explicit
+// 16 x 16 inverses inside them) with every product on mma.sync.m8n8k4.f64.  A warp owns 8 panel rows and keeps
+// the whole 8 x 128 slab in registers as 16 accumulator fragments c[q] (columns 8q .. 8q+7): sub-block step s
+//     X_s  = T_s inv(L_ss)^T            : 2 fragments x 4 k-groups, B-fragments from the staged inverses
+//     T_q -= X_s L[q-block][s-block]^T  : every later fragment q, 4 k-groups, B-fragments from the staged L_kk
+// The A-operands (T_s, then -X_s) are accumulator fragments re-shaped by two quad shuffles per k-group
+// (accumulator: thread t holds columns 2t, 2t+1 of row g; A-fragment: thread t holds column t).  288 DMMAs per
+// warp instead of ~9000 dependent DFMAs per thread: the panel solve drops from ~44 us to a few us per wave.
+// Shared pitches are = 4 mod 16 doubles so the 64-bit B-fragment loads (row g, column t) are conflict-free.
+constexpr int TLP = NB + 4;   // 132
+constexpr int TXP = SB + 4;   // 20
+constexpr size_t kTrsmDmmaSmem = (size_t)(NB * TLP + NSB * SB * TXP) * sizeof(double);
+
+__device__ __forceinline__ void dmma884(double2& c, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+      : "+d"(c.x), "+d"(c.y)
+      : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256)
+trsm_dmma_blocked_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int m, const double* __restrict__ Linv) {
+  extern __shared__ __align__(16) double sm[];
+  double* SL = sm;               // NB * TLP : L_kk (lower triangle incl. diagonal)
+  double* SX = SL + NB * TLP;    // NSB * SB * TXP : inv(L_ss), s = 0..7 (zero above their diagonals)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const unsigned full = 0xffffffffu;
+  const double* lkk = Mat + (int64_t)k0 * ldm + k0;
+  for (int idx = tid; idx < NB * NB / 2; idx += 256) {
+    const int i = idx >> 6, c = (idx & 63) * 2;
+    if (c <= i)  // c + 1 may be i + 1: one entry above the diagonal, never read
+      *reinterpret_cast<double2*>(SL + i * TLP + c) = __ldg(reinterpret_cast<const double2*>(lkk + (int64_t)i * ldm + c));
+  }
+  for (int idx = tid; idx < NSB * SB * SB; idx += 256) {
+    const int sblk = idx >> 8, i = (idx >> 4) & 15, l = idx & 15;
+    SX[(sblk * SB + i) * TXP + l] = __ldg(Linv + (sblk * SB + i) * NB + sblk * SB + l);
+  }
+  const int64_t r = (int64_t)k0 + NB + (int64_t)blockIdx.x * TBR + warp * 8 + g;
+  double* prow = Mat + r * ldm + k0 + 2 * t;
+  double2 c[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q)
+    c[q] = (r < m) ? *reinterpret_cast<const double2*>(prow + 8 * q) : make_double2(0.0, 0.0);
+  __syncthreads();
+
+  const int src_lo = (lane & ~3) | (t >> 1);  // quad lane holding column (t) of the first half of a fragment
+  const int src_hi = src_lo | 2;              // ... of the second half
+  const bool odd = (t & 1) != 0;
+#pragma unroll
+  for (int s = 0; s < NSB; ++s) {
+    // A-fragments of T_s: k-group kk covers columns 16 s + 4 kk + t
+    double a[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const double2 v = c[2 * s + (kk >> 1)];
+      const int src = (kk & 1) ? src_hi : src_lo;
+      const double vx = __shfl_sync(full, v.x, src), vy = __shfl_sync(full, v.y, src);
+      a[kk] = odd ? vy : vx;
+    }
+    double2 x[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      x[h] = make_double2(0.0, 0.0);
+      const double* xb = SX + (s * SB + 8 * h + g) * TXP + t;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) dmma884(x[h], a[kk], xb[4 * kk]);
+      c[2 * s + h] = x[h];
+    }
+    if (s + 1 < NSB) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const double2 v = x[kk >> 1];
+        const int src = (kk & 1) ? src_hi : src_lo;
+        const double vx = __shfl_sync(full, v.x, src), vy = __shfl_sync(full, v.y, src);
+        a[kk] = -(odd ? vy : vx);
+      }
+#pragma unroll
+      for (int q = 2 * s + 2; q < 16; ++q) {
+        const double* lb = SL + (8 * q + g) * TLP + s * SB + t;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) dmma884(c[q], a[kk], lb[4 * kk]);
+      }
+    }
+  }
+  if (r < m) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) *reinterpret_cast<double2*>(prow + 8 * q) = c[q];
   }
 }
 
@@ -955,6 +1056,32 @@ solve_pipelined_kernel(const double* __restrict__ L, int64_t ldm, const double* 
   }
 }
 
+// ------------------------------------------------------------------ distributed factorisation: panel pack / unpack
+// Broadcast payload of panel k:  [ inv(L_kk) : 128 x 128 ][ rows k0 .. m-1 of columns k0 .. k0+nb-1 : (m - k0) x nb ],
+// contiguous.  TO_BUF: owner, after potf2_inv + TRSM.  !TO_BUF: everyone else, after the broadcast.
+template <bool TO_BUF>
+__global__ void __launch_bounds__(256)
+panel_pack_kernel(double* __restrict__ Mat, int64_t ldm, int64_t k0, int64_t m, int nb, double* __restrict__ Linv,
+                  double* __restrict__ buf) {
+  const int64_t n_inv = NB * NB;
+  const int64_t total = n_inv + (m - k0) * nb;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    double* p;
+    if (idx < n_inv) {
+      p = Linv + idx;
+    } else {
+      const int64_t e = idx - n_inv;
+      const int64_t r = e / nb, c = e - r * nb;
+      p = Mat + (k0 + r) * ldm + k0 + c;
+    }
+    if (TO_BUF)
+      buf[idx] = *p;
+    else
+      *p = buf[idx];
+  }
+}
+
 template <typename K>
 int set_smem(K kern, size_t bytes) {
   LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -962,7 +1089,7 @@ int set_smem(K kern, size_t bytes) {
 }
 
 constexpr size_t kPotf2Smem = (size_t)(NB * LDS + NB) * sizeof(double);
-constexpr size_t kPotf2InvSmem = (size_t)(NB * LDS + NB + SB * XDP + 16 * SB * TWP) * sizeof(double);
+constexpr size_t kPotf2InvSmem = (size_t)(NB * LDS + NB + SB * XDP + 16 * SB * TWP + 2 * SB) * sizeof(double);
 constexpr size_t kTrsmSmem = (size_t)((NB + TRSM_ROWS) * LDS) * sizeof(double);
 constexpr size_t kTrsvSmem = (size_t)(NB * LDS + NB + 2 * NB) * sizeof(double);
 
@@ -973,6 +1100,7 @@ int configure_once() {
   LPB_TRY(set_smem(potf2_inv_kernel, kPotf2InvSmem));
   LPB_TRY(set_smem(trsm_kernel, kTrsmSmem));
   LPB_TRY(set_smem(trsm_blocked_kernel, kTrsmBlockedSmem));
+  LPB_TRY(set_smem(trsm_dmma_blocked_kernel, kTrsmDmmaSmem));
   LPB_TRY(set_smem(trsv_diag_kernel<false, 1>, kTrsvSmem));
   LPB_TRY(set_smem(trsv_diag_kernel<false, 2>, kTrsvSmem));
   LPB_TRY(set_smem(trsv_diag_kernel<true, 1>, kTrsvSmem));
@@ -1005,15 +1133,23 @@ static int ensure_chol_ws(LaunchCtx& lc, int64_t m) {
   return LPB_OK;
 }
 
+static int k_potrf_dist(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm);
+
 int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
   LPB_TRY(configure_once());
   LPB_TRY(ensure_chol_ws(lc, m));
   LPB_CUDA(cudaMemsetAsync(lc.info_dev, 0, sizeof(int), lc.stream));
+  if (lc.world > 1 && lc.nccl_comm && lc.potrf_dist && syrk_impl == 0 && lc.trsm_impl == 0 && lc.update_impl == 0 &&
+      m > NB && !(ldm & 1))
+    return k_potrf_dist(lc, m, Mat, ldm);
+  const int full_inverse = (lc.trsm_impl == 2 || lc.solve_impl == 1) ? 1 : 0;
+  lc.linv_full = full_inverse != 0;
   for (int64_t k0 = 0; k0 < m; k0 += NB) {
     const int nb = (int)((m - k0) < NB ? (m - k0) : NB);
     const int64_t rem = m - k0 - nb;
     double* linv = lc.chol_ws + (k0 / NB) * NB * NB;
-    potf2_inv_kernel<<<1, dim3(32, 16), kPotf2InvSmem, lc.stream>>>(Mat, ldm, (int)k0, nb, lc.info_dev, linv);
+    potf2_inv_kernel<<<1, dim3(32, 16), kPotf2InvSmem, lc.stream>>>(Mat, ldm, (int)k0, nb, lc.info_dev, linv,
+                                                                    full_inverse);
     LPB_KCHECK(lc);
     if (lc.sync_each_launch) LPB_CUDA(cudaStreamSynchronize(lc.stream));
     if (rem > 0) {
@@ -1023,9 +1159,14 @@ int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
         LPB_KCHECK(lc);
       } else if (lc.trsm_impl == 2) {             // GEMM with the full 128 x 128 inverse (not backward stable)
         LPB_TRY(k_trsm_dmma(lc, m, Mat, ldm, k0, linv));
-      } else {                                    // rem > 0 implies nb == NB
+      } else if (lc.trsm_impl == 3 || (ldm & 1) || (reinterpret_cast<uintptr_t>(Mat) & 15)) {
+        // blocked substitution in plain DFMA: reference for the default, and the path for unaligned matrices
         trsm_blocked_kernel<<<(unsigned)ceil_div(rem, TBR), 256, kTrsmBlockedSmem, lc.stream>>>(Mat, ldm, (int)k0,
                                                                                                (int)m, linv);
+        LPB_KCHECK(lc);
+      } else {                                    // rem > 0 implies nb == NB
+        trsm_dmma_blocked_kernel<<<(unsigned)ceil_div(rem, TBR), 256, kTrsmDmmaSmem, lc.stream>>>(Mat, ldm, (int)k0,
+                                                                                                 (int)m, linv);
         LPB_KCHECK(lc);
       }
       if (lc.sync_each_launch) LPB_CUDA(cudaStreamSynchronize(lc.stream));
@@ -1034,6 +1175,79 @@ int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
       else
         LPB_TRY(k_trailing_update_dmma(lc, m, Mat, ldm, k0, nb));
       if (lc.sync_each_launch) LPB_CUDA(cudaStreamSynchronize(lc.stream));
+    }
+  }
+  lc.linv_valid_m = m;
+  lc.linv_mat = Mat;
+  return LPB_OK;
+}
+
+// Distributed factorisation for column-sharded contexts (every rank holds the same all-reduced M).
+// Block column k belongs to rank k mod G.  Its owner factors the diagonal block and solves the panel
+// (potf2_inv + TRSM, as in k_potrf), then BROADCASTS the finished panel together with inv(L_kk) over
+// NVLink (one ncclBroadcast per panel); every rank stores it into its own copy of M, so at the end all
+// ranks hold the whole factor and the triangular solves stay local.  The trailing update -- the m^3/3
+// flop -- is sharded: each rank updates only the block columns it owns.  The rank that owns panel k+1
+// updates that column first and defers the rest of its update until its panel is on the wire, so its
+// potf2 / TRSM chain overlaps the other ranks' updates (look-ahead across ranks, one stream per rank).
+// Bit-identical factors on all ranks by construction (every entry of L is computed by exactly one rank).
+static int k_potrf_dist(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm) {
+  const int G = lc.world, me = lc.rank;
+  ncclComm_t comm = static_cast<ncclComm_t>(lc.nccl_comm);
+  const int64_t need = (int64_t)NB * NB + m * NB;
+  if (lc.panel_buf_cap < need) {
+    if (lc.panel_buf) cudaFree(lc.panel_buf);
+    lc.panel_buf = nullptr;
+    lc.panel_buf_cap = 0;
+    void* p = nullptr;
+    LPB_CUDA(cudaMalloc(&p, sizeof(double) * (size_t)need));
+    lc.panel_buf = static_cast<double*>(p);
+    lc.panel_buf_cap = need;
+  }
+  const int T = (int)ceil_div(m, NB);
+  lc.linv_full = false;
+  int pending = -1;  // panel whose update of the columns >= pending + 2 this rank still owes
+  for (int k = 0; k < T; ++k) {
+    const int64_t k0 = (int64_t)k * NB;
+    const int nb = (int)((m - k0) < NB ? (m - k0) : NB);
+    const int64_t rem = m - k0 - nb;
+    const int owner = k % G;
+    double* linv = lc.chol_ws + (int64_t)k * NB * NB;
+    const int64_t count = (int64_t)NB * NB + (m - k0) * nb;
+    const unsigned pack_grid = (unsigned)std::min<int64_t>(ceil_div(count, 256 * 4), kNumSMs * 4);
+    if (owner == me) {
+      potf2_inv_kernel<<<1, dim3(32, 16), kPotf2InvSmem, lc.stream>>>(Mat, ldm, (int)k0, nb, lc.info_dev, linv, 0);
+      LPB_KCHECK(lc);
+      if (rem > 0) {
+        trsm_dmma_blocked_kernel<<<(unsigned)ceil_div(rem, TBR), 256, kTrsmDmmaSmem, lc.stream>>>(Mat, ldm, (int)k0,
+                                                                                                 (int)m, linv);
+        LPB_KCHECK(lc);
+      }
+      panel_pack_kernel<true><<<pack_grid, 256, 0, lc.stream>>>(Mat, ldm, k0, m, nb, linv, lc.panel_buf);
+      LPB_KCHECK(lc);
+    }
+    {
+      const ncclResult_t r = ncclBroadcast(lc.panel_buf, lc.panel_buf, (size_t)count, ncclDouble, owner, comm, lc.stream);
+      if (r != ncclSuccess) {
+        set_last_error("potrf_dist: ncclBroadcast of panel %d -> %s", k, ncclGetErrorString(r));
+        return LPB_ERR_NCCL;
+      }
+    }
+    if (owner != me) {
+      panel_pack_kernel<false><<<pack_grid, 256, 0, lc.stream>>>(Mat, ldm, k0, m, nb, linv, lc.panel_buf);
+      LPB_KCHECK(lc);
+    }
+    if (pending >= 0) {  // the rest of the previous panel's update: columns >= pending + 2
+      LPB_TRY(k_trailing_update_part(lc, m, Mat, ldm, (int64_t)pending * NB, NB, pending + 2, 0, G, me));
+      pending = -1;
+    }
+    if (rem > 0) {
+      if ((k + 1) % G == me) {  // next panel is mine: bring its column up to date now, the rest after its broadcast
+        LPB_TRY(k_trailing_update_part(lc, m, Mat, ldm, k0, nb, k + 1, 1, 1, 0));
+        pending = k;
+      } else {
+        LPB_TRY(k_trailing_update_part(lc, m, Mat, ldm, k0, nb, k + 1, 0, G, me));
+      }
     }
   }
   lc.linv_valid_m = m;
@@ -1131,7 +1345,7 @@ int k_potrs(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B, i
   LPB_TRY(configure_once());
   const bool aligned = !(ldm & 1) && !(reinterpret_cast<uintptr_t>(L) & 15);  // double2 loads of L
   if (use_linv && aligned && lc.solve_impl != 2 && lc.linv_valid_m == m && lc.linv_mat == L && lc.chol_ws) {
-    if (lc.solve_impl == 1) {  // one launch per 128-block step (kept for bisecting)
+    if (lc.solve_impl == 1 && lc.linv_full) {  // one launch per 128-block step (kept for bisecting)
       if (nrhs == 1) return potrs_fused<1>(lc, m, L, ldm, B);
       if (nrhs == 2) return potrs_fused<2>(lc, m, L, ldm, B);
     } else {

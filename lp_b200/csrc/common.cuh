@@ -52,11 +52,18 @@ struct LaunchCtx {
   int64_t chol_ws_cap = 0;         // in doubles
   int64_t linv_valid_m = -1;       // order of the matrix whose block inverses chol_ws holds
   const double* linv_mat = nullptr; // ... and its address
+  bool linv_full = false;          // chol_ws holds the full 128 x 128 inverses (else only their 16 x 16 diagonal blocks)
   int solve_epoch = 0;             // flag value of the next pipelined solve (cholesky.cu)
   int solve_impl = 0;              // 0 = pipelined single launch, 1 = one launch per block step
   int sync_each_launch = 0;        // debug: stream-synchronise after every launch of k_potrf
   int trsm_impl = 0, update_impl = 0;  // bisecting knobs of k_potrf: 1 = plain DFMA kernel for that step
   int solve_grid_cap = 0;          // > 0: cap the pipelined solve's grid (tests: several block rows per CTA)
+  // column-sharded contexts: the distributed factorisation (k_potrf_dist) broadcasts panels over NCCL
+  void* nccl_comm = nullptr;       // ncclComm_t of this process, or null
+  int rank = 0, world = 1;
+  int potrf_dist = 1;              // 0 = every rank factors the whole of M itself (replicated)
+  double* panel_buf = nullptr;     // packed panel + inverted diagonal block, the broadcast payload
+  int64_t panel_buf_cap = 0;       // in doubles
   int* info_dev = nullptr;         // potrf info flag
   int* info_host = nullptr;        // pinned
 };

@@ -118,6 +118,30 @@ __device__ __forceinline__ void tri_decode(int L, int* ti, int* tj) {
   *tj = L - i * (i + 1) / 2;
 }
 
+// Tile list of the trailing update when the block columns are dealt round-robin to `G` ranks (the
+// distributed factorisation, cholesky.cu): this rank owns the trailing block columns tj = f + l G
+// (l = 0, 1, ...), column l has n - tj tiles (ti = tj .. n-1), columns are walked one after the other.
+//   S(l) = tiles before column l = l (n - f) - G l (l - 1) / 2.
+struct OwnedCols {
+  int G, f, n;  // modulus, first owned trailing column, trailing tile rows
+  __host__ __device__ int before(int l) const { return l * (n - f) - G * (l * (l - 1) / 2); }
+  __host__ __device__ int count() const {
+    if (f >= n) return 0;
+    const int nown = (n - f + G - 1) / G;
+    return before(nown);
+  }
+  __device__ void decode(int t, int* ti, int* tj) const {
+    const double a = 0.5 * G, b = (n - f) + 0.5 * G;
+    const double disc = b * b - 4.0 * a * t;
+    int l = static_cast<int>((b - sqrt(disc > 0.0 ? disc : 0.0)) / (2.0 * a));
+    if (l < 0) l = 0;
+    while (l > 0 && before(l) > t) --l;
+    while (before(l + 1) <= t) ++l;
+    *tj = f + l * G;
+    *ti = *tj + (t - before(l));
+  }
+};
+
 // Producer cursor: walks this CTA's (tile, k-block) sequence `kLead` iterations ahead of the
 // consumers.  Lives in lane 0 of warp 0 (the register file is split 4 x 16K per SM sub-partition,
 // so a ninth warp would not fit next to eight 200-register DMMA warps).
@@ -132,7 +156,11 @@ struct LoadCursor {
 // MODE_TRSM   : C[:, col_origin + 0..127] = A B^T with B = inv(L_kk) (128 x 128, its own tensor map):
 //               the panel TRSM X L_kk^T = P expressed as a GEMM; rectangular tile list (ntr x 1),
 //               in place (a CTA reads all K-blocks of its own rows before it stores them).
+// Tile lists (`shape`): SHAPE_TRI the lower triangle row by row; SHAPE_COL its first block column only
+// (ntr x 1: the look-ahead update of the next panel's column); SHAPE_OWNED the block columns this rank
+// owns in the distributed factorisation (OwnedCols).
 enum { MODE_SYRK = 0, MODE_UPDATE = 1, MODE_TRSM = 2 };
+enum { SHAPE_TRI = 0, SHAPE_COL = 1, SHAPE_OWNED = 2 };
 
 // VAR (experiments on the trailing update): bit 0 = accumulate from zero and read-modify-write C in
 // the epilogue instead of initialising the accumulators from C; bit 1 = CTA barrier at every tile end;
@@ -141,7 +169,7 @@ template <int MODE, bool SCALE, int VAR = 0>
 __global__ void __maxnreg__(255)
 syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  double* __restrict__ C, int64_t ldc, int m_total, int tile0, int ntr, int k_begin, int nkb,
-                 int col_origin) {
+                 int col_origin, int shape, OwnedCols own) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base + kSmemA, sB = smem_base + kSmemB, sD = smem_base + kSmemD;
@@ -157,14 +185,17 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   __syncthreads();
 
-  const int ntiles = MODE == MODE_TRSM ? ntr : ntr * (ntr + 1) / 2;
+  const int ntiles = (MODE == MODE_TRSM || shape == SHAPE_COL) ? ntr
+                     : (shape == SHAPE_OWNED ? own.count() : ntr * (ntr + 1) / 2);
   const bool is_producer = threadIdx.x == 0;
   constexpr uint32_t kBytes = 2 * kTileBytes + (SCALE ? kDBytes : 0);
 
   auto decode = [&](int L, int* ti, int* tj) {
-    if (MODE == MODE_TRSM) {
+    if (MODE == MODE_TRSM || shape == SHAPE_COL) {
       *ti = L;
       *tj = 0;
+    } else if (shape == SHAPE_OWNED) {
+      own.decode(L, ti, tj);
     } else {
       tri_decode(L, ti, tj);
     }
@@ -376,16 +407,20 @@ int make_tmap(CUtensorMap* tm, const double* base, uint64_t rows, uint64_t cols,
 
 template <int MODE, bool SCALE, int VAR = 0>
 int launch_dmma(LaunchCtx& lc, const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int m_total,
-                int tile0, int ntr, int k_begin, int nkb, int col_origin) {
+                int tile0, int ntr, int k_begin, int nkb, int col_origin, int shape = SHAPE_TRI,
+                OwnedCols own = OwnedCols{1, 0, 0}) {
   static bool configured = false;
   auto kern = syrk_dmma_kernel<MODE, SCALE, VAR>;
   if (!configured) {
     LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAlloc));
     configured = true;
   }
-  const int ntiles = MODE == MODE_TRSM ? ntr : ntr * (ntr + 1) / 2;
+  const int ntiles = (MODE == MODE_TRSM || shape == SHAPE_COL) ? ntr
+                     : (shape == SHAPE_OWNED ? own.count() : ntr * (ntr + 1) / 2);
+  if (ntiles <= 0) return LPB_OK;
   const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
-  kern<<<grid, kThreads, kSmemAlloc, lc.stream>>>(tmA, tmB, C, ldc, m_total, tile0, ntr, k_begin, nkb, col_origin);
+  kern<<<grid, kThreads, kSmemAlloc, lc.stream>>>(tmA, tmB, C, ldc, m_total, tile0, ntr, k_begin, nkb, col_origin, shape,
+                                                  own);
   lc.launches++;
   LPB_CUDA(cudaGetLastError());
   return LPB_OK;
@@ -437,6 +472,32 @@ int k_trailing_update_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, i
                                               (int)(kb / BK), 0);
   return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, (int)(row0 / BM), ntr, (int)k0, (int)(kb / BK),
                                          0);
+}
+
+// Trailing update with panel [k0, k0 + kb) restricted to a tile list: rows / columns from tile `tile0` on;
+// single_col: only block column tile0 (look-ahead); otherwise the block columns J >= tile0 with
+// J % own_mod == own_rem (own_mod == 1: all of them).
+int k_trailing_update_part(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb, int tile0,
+                           int single_col, int own_mod, int own_rem) {
+  const int ntr = (int)ceil_div(m, BM) - tile0;
+  if (ntr <= 0) return LPB_OK;
+  if ((kb % BK) || (ldm & 1) || (reinterpret_cast<uintptr_t>(Mat) & 15) || (int64_t)tile0 * BM < k0 + kb) {
+    set_last_error("trailing_update_part: bad panel / tile origin");
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  CUtensorMap tm;
+  LPB_TRY(make_tmap(&tm, Mat, (uint64_t)m, (uint64_t)m, (uint64_t)ldm, BM, BK, true));
+  if (single_col)
+    return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, (int)k0, (int)(kb / BK), 0,
+                                           SHAPE_COL);
+  if (own_mod <= 1)
+    return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, (int)k0, (int)(kb / BK), 0);
+  OwnedCols own;
+  own.G = own_mod;
+  own.f = ((own_rem - tile0) % own_mod + own_mod) % own_mod;
+  own.n = ntr;
+  return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, (int)k0, (int)(kb / BK), 0,
+                                         SHAPE_OWNED, own);
 }
 
 // Panel TRSM as a GEMM: Mat[row0.., k0..k0+128) <- Mat[row0.., k0..k0+128) * Linv^T, row0 = k0 + 128,

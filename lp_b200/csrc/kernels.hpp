@@ -78,6 +78,9 @@ int k_sym_back(LaunchCtx& lc, int64_t n, int nchunks, int with_pq, const double*
 int k_syrk_dmma(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* d, double* Cmat,
                 int64_t ldc);
 int k_trailing_update_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb);
+// C -= P P^T restricted to a tile list (look-ahead column / the block columns one rank owns): see dmma_gemm.cu
+int k_trailing_update_part(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb, int tile0,
+                           int single_col, int own_mod, int own_rem);
 // panel TRSM as a DMMA GEMM with the inverted 128 x 128 diagonal block (dense, ld 128)
 int k_trsm_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, const double* Linv);
 // plain DFMA reference kernels (tests / bisecting only)

@@ -578,6 +578,7 @@ void ctx_free(lpb_ctx* c) {
   for (auto e : c->ev_free) cudaEventDestroy(e);
   for (void* p : c->allocs) cudaFree(p);
   if (c->lc.chol_ws) cudaFree(c->lc.chol_ws);
+  if (c->lc.panel_buf) cudaFree(c->lc.panel_buf);
   if (c->lc.red_host) cudaFreeHost(c->lc.red_host);
   if (c->lc.info_host) cudaFreeHost(c->lc.info_host);
   if (c->chk_host) cudaFreeHost(c->chk_host);
@@ -795,6 +796,9 @@ int lpb_create_sharded(lpb_ctx** out, int64_t m, int64_t n_global, int64_t col0,
       }
     }
     c->comm = g_comm.comm;
+    c->lc.nccl_comm = g_comm.comm;
+    c->lc.rank = rank;
+    c->lc.world = world;
   }
   if (rc != LPB_OK) {
     ctx_free(c);
@@ -1146,6 +1150,10 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
   if (k == "structure") {  // 0: contract over every column of A (no slack-column shortcut)
     c->use_structure = value != 0;
     return c->has_problem ? analyze_structure(c) : LPB_OK;
+  }
+  if (k == "potrf_dist") {  // 0: replicated factorisation on every rank of a sharded context
+    c->lc.potrf_dist = value != 0;
+    return LPB_OK;
   }
   if (k == "potrf_verify") {
     c->potrf_verify = (int)value;

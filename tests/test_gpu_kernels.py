@@ -43,7 +43,7 @@ def test_syrk_adat_matches_numpy(m, n, impl, scaled):
     assert err.max() < 1e-12
 
 
-@pytest.mark.parametrize("impl,trsm", [(0, 0), (0, 1), (0, 2), (1, 0)])
+@pytest.mark.parametrize("impl,trsm", [(0, 0), (0, 1), (0, 2), (0, 3), (1, 0)])
 @pytest.mark.parametrize("m", [1, 5, 16, 17, 64, 128, 129, 200, 384, 1000, 1536])
 def test_potrf_matches_lapack(m, impl, trsm):
     """K2 vs numpy.linalg.cholesky (LAPACK potrf); ||L L^T - M|| / ||M|| < 1e-13 and L close to LAPACK's."""
@@ -55,7 +55,7 @@ def test_potrf_matches_lapack(m, impl, trsm):
     info = C.c_int32(-1)
     with BareCtx(m, m) as ctx:
         ctx.set("syrk_impl", impl)
-        ctx.set("trsm_impl", trsm)  # 0 blocked substitution (default), 1 column substitution, 2 GEMM with inv(L_kk)
+        ctx.set("trsm_impl", trsm)  # 0 blocked substitution on DMMA (default), 1 column substitution, 2 GEMM with inv(L_kk), 3 blocked substitution in DFMA
         ok(ctx.lib.lpb_k_potrf(ctx.h, m, dM.data_ptr(), ldm, C.byref(info)))
     assert info.value == 0
     L = np.tril(dM.cpu().numpy()[:, :m])

@@ -18,6 +18,7 @@ pytestmark = pytest.mark.gpu
 
 CASES = [(64, 128, 0), (130, 301, 2), (256, 512, 1)]
 SYN = (256, 640, 7)
+BIG = (1300, 3000, 4)   # 11 panels of 128 (ragged last one): exercises the distributed factorisation
 
 
 def _gpu_count():
@@ -85,10 +86,27 @@ def _worker(rank, world, port, q):
             A_k, b, c_k = sp.download()
             res = solver.solve_resident(sp)
         out["syn"] = (A_k, b, c_k, sp.col0, res.x(), res.fun(), res.iteration())
+        # distributed (panel-broadcast) vs replicated factorisation on the same all-reduced M
+        from lp_b200 import _ffi
+        lib = _ffi.load()
+        m, n, seed = BIG
+        c, A_ub, b_ub, A_eq, b_eq = o.synthetic_lp(m, n, seed)
+        pb = lp_b200.Problem.target(c).ub(A_ub, b_ub).eq(A_eq, b_eq).build()
+        ldm = (m + 15) // 16 * 16
+        big = {}
+        for mode in (1, 0):
+            with ShardedProblem(pb, rank, world, dist) as sp:
+                sp.set_option("potrf_dist", mode)
+                sp.set_option("check_replicas", 1)
+                assert lib.lpb_blind_start(sp.handle) == 0
+                assert lib.lpb_form_and_factor(sp.handle) == 0, _ffi.last_error()
+                L = np.tril(sp.debug_read("M").reshape(m, ldm)[:, :m])
+                res = solver.solve_resident(sp)
+            big[mode] = (L, res.x(), res.fun(), res.iteration())
+        out["big"] = big
         q.put((rank, out))
         dist.barrier()
-        from lp_b200 import _ffi
-        _ffi.load().lpb_comm_finalize()
+        lib.lpb_comm_finalize()
     finally:
         dist.destroy_process_group()
 
@@ -119,6 +137,19 @@ def test_two_gpu_column_sharded_solve_matches_oracle_and_one_gpu():
             assert comm_ms > 0.0                                          # the NCCL all-reduces did run
         np.testing.assert_array_equal(results[0][key][0], results[1][key][0])   # ranks agree bit for bit
         assert results[0][key][1] == results[1][key][1]
+    # distributed factorisation: every entry of L is computed by exactly one rank with the same kernels and
+    # the same order of updates as the replicated run -> identical bits across ranks AND across the two modes
+    ref = o.InteriorPoint().solve(o.build_problem(*o.synthetic_lp(*BIG)))
+    for rank in (0, 1):
+        for mode in (1, 0):
+            L, x, fun, it = results[rank]["big"][mode]
+            np.testing.assert_array_equal(L, results[0]["big"][0][0])
+            assert abs(it - ref.iteration) <= 1
+            assert np.abs(x - ref.x).max() < 1e-6
+            assert abs(fun - ref.fun) <= 1e-8 * max(1.0, abs(ref.fun))
+    Lref = np.linalg.cholesky((lambda A: A @ A.T)(o.build_problem(*o.synthetic_lp(*BIG)).A))
+    L = results[0]["big"][1][0]
+    assert np.abs(L - Lref).max() <= 1e-10 * np.abs(Lref).max()
     # device-side generator: the two shards tile the world-1 problem exactly (counter-based entries)
     m, n, seed = SYN
     with SyntheticShardedProblem(m, n, seed) as sp:
