@@ -17,6 +17,7 @@
 
 #include <algorithm>
 
+#include "dist_schedule.hpp"
 #include "kernels.hpp"
 
 namespace lpb {
@@ -1140,7 +1141,7 @@ int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
   LPB_TRY(ensure_chol_ws(lc, m));
   LPB_CUDA(cudaMemsetAsync(lc.info_dev, 0, sizeof(int), lc.stream));
   if (lc.world > 1 && lc.nccl_comm && lc.potrf_dist && syrk_impl == 0 && lc.trsm_impl == 0 && lc.update_impl == 0 &&
-      m > NB && !(ldm & 1))
+      m > NB && !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mat) & 15))
     return k_potrf_dist(lc, m, Mat, ldm);
   const int full_inverse = (lc.trsm_impl == 2 || lc.solve_impl == 1) ? 1 : 0;
   lc.linv_full = full_inverse != 0;
@@ -1206,50 +1207,48 @@ static int k_potrf_dist(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm) {
   }
   const int T = (int)ceil_div(m, NB);
   lc.linv_full = false;
-  int pending = -1;  // panel whose update of the columns >= pending + 2 this rank still owes
-  for (int k = 0; k < T; ++k) {
-    const int64_t k0 = (int64_t)k * NB;
-    const int nb = (int)((m - k0) < NB ? (m - k0) : NB);
-    const int64_t rem = m - k0 - nb;
-    const int owner = k % G;
-    double* linv = lc.chol_ws + (int64_t)k * NB * NB;
-    const int64_t count = (int64_t)NB * NB + (m - k0) * nb;
-    const unsigned pack_grid = (unsigned)std::min<int64_t>(ceil_div(count, 256 * 4), kNumSMs * 4);
-    if (owner == me) {
-      potf2_inv_kernel<<<1, dim3(32, 16), kPotf2InvSmem, lc.stream>>>(Mat, ldm, (int)k0, nb, lc.info_dev, linv, 0);
+  struct Ops {
+    LaunchCtx& lc;
+    ncclComm_t comm;
+    int64_t m, ldm;
+    double* Mat;
+    int G, me;
+    int64_t k0(int k) const { return (int64_t)k * NB; }
+    int nb(int k) const { return (int)((m - k0(k)) < NB ? (m - k0(k)) : NB); }
+    double* linv(int k) const { return lc.chol_ws + (int64_t)k * NB * NB; }
+    int64_t count(int k) const { return (int64_t)NB * NB + (m - k0(k)) * nb(k); }
+    unsigned pack_grid(int k) const { return (unsigned)std::min<int64_t>(ceil_div(count(k), 256 * 4), kNumSMs * 4); }
+    int factor_panel(int k) {
+      const int64_t rem = m - k0(k) - nb(k);
+      potf2_inv_kernel<<<1, dim3(32, 16), kPotf2InvSmem, lc.stream>>>(Mat, ldm, (int)k0(k), nb(k), lc.info_dev, linv(k), 0);
       LPB_KCHECK(lc);
       if (rem > 0) {
-        trsm_dmma_blocked_kernel<<<(unsigned)ceil_div(rem, TBR), 256, kTrsmDmmaSmem, lc.stream>>>(Mat, ldm, (int)k0,
-                                                                                                 (int)m, linv);
+        trsm_dmma_blocked_kernel<<<(unsigned)ceil_div(rem, TBR), 256, kTrsmDmmaSmem, lc.stream>>>(Mat, ldm, (int)k0(k),
+                                                                                                 (int)m, linv(k));
         LPB_KCHECK(lc);
       }
-      panel_pack_kernel<true><<<pack_grid, 256, 0, lc.stream>>>(Mat, ldm, k0, m, nb, linv, lc.panel_buf);
+      panel_pack_kernel<true><<<pack_grid(k), 256, 0, lc.stream>>>(Mat, ldm, k0(k), m, nb(k), linv(k), lc.panel_buf);
       LPB_KCHECK(lc);
+      return LPB_OK;
     }
-    {
-      const ncclResult_t r = ncclBroadcast(lc.panel_buf, lc.panel_buf, (size_t)count, ncclDouble, owner, comm, lc.stream);
+    int broadcast(int k, int owner) {
+      const ncclResult_t r =
+          ncclBroadcast(lc.panel_buf, lc.panel_buf, (size_t)count(k), ncclDouble, owner, comm, lc.stream);
       if (r != ncclSuccess) {
         set_last_error("potrf_dist: ncclBroadcast of panel %d -> %s", k, ncclGetErrorString(r));
         return LPB_ERR_NCCL;
       }
+      return LPB_OK;
     }
-    if (owner != me) {
-      panel_pack_kernel<false><<<pack_grid, 256, 0, lc.stream>>>(Mat, ldm, k0, m, nb, linv, lc.panel_buf);
+    int store_panel(int k) {
+      panel_pack_kernel<false><<<pack_grid(k), 256, 0, lc.stream>>>(Mat, ldm, k0(k), m, nb(k), linv(k), lc.panel_buf);
       LPB_KCHECK(lc);
+      return LPB_OK;
     }
-    if (pending >= 0) {  // the rest of the previous panel's update: columns >= pending + 2
-      LPB_TRY(k_trailing_update_part(lc, m, Mat, ldm, (int64_t)pending * NB, NB, pending + 2, 0, G, me));
-      pending = -1;
-    }
-    if (rem > 0) {
-      if ((k + 1) % G == me) {  // next panel is mine: bring its column up to date now, the rest after its broadcast
-        LPB_TRY(k_trailing_update_part(lc, m, Mat, ldm, k0, nb, k + 1, 1, 1, 0));
-        pending = k;
-      } else {
-        LPB_TRY(k_trailing_update_part(lc, m, Mat, ldm, k0, nb, k + 1, 0, G, me));
-      }
-    }
-  }
+    int update_column(int p, int col) { return k_trailing_update_part(lc, m, Mat, ldm, k0(p), nb(p), col, 1, 1, 0); }
+    int update_owned(int p, int tile0) { return k_trailing_update_part(lc, m, Mat, ldm, k0(p), nb(p), tile0, 0, G, me); }
+  } ops{lc, comm, m, ldm, Mat, G, me};
+  LPB_TRY(potrf_dist_schedule(T, G, me, ops));
   lc.linv_valid_m = m;
   lc.linv_mat = Mat;
   return LPB_OK;

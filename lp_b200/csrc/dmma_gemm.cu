@@ -22,6 +22,7 @@
 //  * d[k] is applied to the B-fragment in registers (8 DMUL per 64 DMMA).
 #include <cuda.h>
 
+#include "dist_schedule.hpp"
 #include "kernels.hpp"
 
 namespace lpb {
@@ -117,30 +118,6 @@ __device__ __forceinline__ void tri_decode(int L, int* ti, int* tj) {
   *ti = i;
   *tj = L - i * (i + 1) / 2;
 }
-
-// Tile list of the trailing update when the block columns are dealt round-robin to `G` ranks (the
-// distributed factorisation, cholesky.cu): this rank owns the trailing block columns tj = f + l G
-// (l = 0, 1, ...), column l has n - tj tiles (ti = tj .. n-1), columns are walked one after the other.
-//   S(l) = tiles before column l = l (n - f) - G l (l - 1) / 2.
-struct OwnedCols {
-  int G, f, n;  // modulus, first owned trailing column, trailing tile rows
-  __host__ __device__ int before(int l) const { return l * (n - f) - G * (l * (l - 1) / 2); }
-  __host__ __device__ int count() const {
-    if (f >= n) return 0;
-    const int nown = (n - f + G - 1) / G;
-    return before(nown);
-  }
-  __device__ void decode(int t, int* ti, int* tj) const {
-    const double a = 0.5 * G, b = (n - f) + 0.5 * G;
-    const double disc = b * b - 4.0 * a * t;
-    int l = static_cast<int>((b - sqrt(disc > 0.0 ? disc : 0.0)) / (2.0 * a));
-    if (l < 0) l = 0;
-    while (l > 0 && before(l) > t) --l;
-    while (before(l + 1) <= t) ++l;
-    *tj = f + l * G;
-    *ti = *tj + (t - before(l));
-  }
-};
 
 // Producer cursor: walks this CTA's (tile, k-block) sequence `kLead` iterations ahead of the
 // consumers.  Lives in lane 0 of warp 0 (the register file is split 4 x 16K per SM sub-partition,
@@ -492,10 +469,7 @@ int k_trailing_update_part(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, i
                                            SHAPE_COL);
   if (own_mod <= 1)
     return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, (int)k0, (int)(kb / BK), 0);
-  OwnedCols own;
-  own.G = own_mod;
-  own.f = ((own_rem - tile0) % own_mod + own_mod) % own_mod;
-  own.n = ntr;
+  const OwnedCols own = OwnedCols::make(own_mod, own_rem, tile0, ntr);
   return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, (int)k0, (int)(kb / BK), 0,
                                          SHAPE_OWNED, own);
 }

@@ -42,3 +42,14 @@ def test_cpp_host_mirror_reference_known_answers_on_gpu():
     assert r.returncode == 0, r.stdout + r.stderr
     m = re.search(r"symmetric: fun=(\S+) iterations=(\d+)", r.stdout)
     assert m and abs(float(m.group(1)) + 1000.0) < 1e-6 and int(m.group(2)) == 4
+
+
+def test_distributed_cholesky_schedule_and_tile_lists():
+    """lp_b200/csrc/dist_schedule.hpp on the CPU for world sizes 2, 3, 4, 8 (tests/cpp/test_dist_schedule.cpp):
+    the owned-column tile decode and the per-rank operation order of the panel-broadcast factorisation."""
+    src = os.path.join(HERE, "cpp", "test_dist_schedule.cpp")
+    out = os.path.join(HERE, "cpp", "_build", "test_dist_schedule")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", src, "-o", out])
+    r = subprocess.run([out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "dist_schedule ok" in r.stdout, r.stdout + r.stderr
