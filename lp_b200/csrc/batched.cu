@@ -16,6 +16,8 @@ namespace {
 constexpr int kBT = 256;       // threads per CTA
 constexpr int kBWarps = kBT / 32;
 constexpr int kMaxM = 64;      // register-tiled SYRK covers 64 x 64
+constexpr int kSB = 16;        // sub-block of the in-CTA blocked Cholesky
+constexpr int kXP = kSB + 1;   // pitch of the 16 x 16 inverted diagonal sub-blocks
 
 __device__ __forceinline__ double bw_sum(double v) {
 #pragma unroll
@@ -50,7 +52,10 @@ __device__ __forceinline__ void block_allreduce(double (&v)[NV], const bool is_m
 
 struct SmemDev {
   int m, n, lda, ldm;
-  double *A, *M, *diag, *b, *c, *x, *y, *z, *rP, *rD, *dinv, *xs, *r1, *p, *q, *u, *v, *dx, *dy, *dz, *t0, *t1, *sx,
+  int mp, nsb;           // m rounded up to a multiple of 16 (rows >= m of M are identity padding), mp / 16
+  double *Xinv, *cbuf;   // nsb x 16 x kXP inverted diagonal sub-blocks of L; 2 x 16 pivot-column broadcast buffer
+  int* flag;             // bad-pivot flag of the factorisation (shared)
+  double *A, *M, *b, *c, *x, *y, *z, *rP, *rD, *dinv, *xs, *r1, *p, *q, *u, *v, *dx, *dy, *dz, *t0, *t1, *sx,
       *red;
   int have_pq, nan_pq;
   double cp, bq;
@@ -172,68 +177,177 @@ struct SmemDev {
           if (av[i] && bv[j]) M[(ty + 16 * i) * ldm + tx + 16 * j] = acc[i][j];
     }
     __syncthreads();
-    // in-place lower Cholesky (right-looking), pivot <= 0 or non-finite -> NumericalProblem (:63)
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int j = 0; j < m; ++j) {
-      const double ajj = M[j * ldm + j];
-      if (!(ajj > 0.0) || !isfinite(ajj)) return LPB_ERR_NUMERICAL_PROBLEM;  // uniform across the CTA
-      const double d = sqrt(ajj);
-      if (threadIdx.x == 0) diag[j] = d;
-      for (int i = j + 1 + threadIdx.x; i < m; i += kBT) M[i * ldm + j] /= d;
+    // In-place lower Cholesky, blocked by 16 columns like potf2_inv_kernel (cholesky.cu): per block ONE warp
+    // factors the 16 x 16 diagonal sub-block and inverts it in the same 16 pivot steps (lanes 0..15: rows of
+    // the sub-block; lanes 16..31: forward substitutions L x = e_c for the columns of the inverse), then the
+    // CTA applies the inverse to the rows below and the rank-16 update to the remaining sub-blocks: 3 CTA
+    // barriers per 16 columns instead of 2 per column.  Pivot <= 0 or non-finite -> NumericalProblem
+    // (newton_equations.rs:63), decided uniformly from a shared flag.
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    if (tid == 0) *flag = 0;
+    for (int kb = 0; kb < nsb; ++kb) {
+      const int c0 = kb * kSB;
+      double* Xd = Xinv + kb * kSB * kXP;
+      if (warp == 0) {
+        const int i = lane & 15;
+        const bool inv_lane = lane >= kSB;
+        double v[kSB];
+#pragma unroll
+        for (int k = 0; k < kSB; ++k) v[k] = (!inv_lane && k <= i) ? M[(c0 + i) * ldm + c0 + k] : 0.0;
+#pragma unroll
+        for (int j = 0; j < kSB; ++j) {
+          const double ajj = __shfl_sync(full, v[j], j);
+          const bool bad = !(ajj > 0.0) || !isfinite(ajj);
+          if (bad && lane == 0) *flag = 1;
+          double rs = rsqrt(ajj);
+          double d = ajj * rs;
+          d = fma(fma(-d, d, ajj), 0.5 * rs, d);    // sqrt(ajj)
+          rs = fma(fma(-d, rs, 1.0), rs, rs);       // 1 / sqrt(ajj)
+          if (bad) d = rs = __longlong_as_double(0x7ff8000000000000ll);
+          double l;
+          if (!inv_lane) {
+            l = v[j] * rs;
+            l = fma(fma(-l, d, v[j]), rs, l);       // a[i][j] / d
+            if (i == j) l = d;
+          } else {
+            l = ((i == j ? 1.0 : 0.0) - v[j]) * rs;  // x_j of column i of the inverse
+          }
+          v[j] = l;
+          double* cb = cbuf + (j & 1) * kSB;
+          if (!inv_lane) cb[i] = l;
+          __syncwarp();
+          const double mult = inv_lane ? l : -l;
+#pragma unroll
+          for (int k = 0; k < kSB; ++k)
+            if (k > j) v[k] = fma(mult, cb[k], v[k]);
+        }
+        if (!inv_lane) {
+#pragma unroll
+          for (int k = 0; k < kSB; ++k)
+            if (k <= i) M[(c0 + i) * ldm + c0 + k] = v[k];
+        } else {
+#pragma unroll
+          for (int r = 0; r < kSB; ++r) Xd[r * kXP + i] = (r >= i) ? v[r] : 0.0;  // X[r][c = i]
+        }
+      }
       __syncthreads();
-      for (int i = j + 1 + ty; i < m; i += kBWarps) {
-        const double lij = M[i * ldm + j];
-        for (int k = j + 1 + tx; k <= i; k += 32) M[i * ldm + k] -= lij * M[k * ldm + j];
+      {  // rows below: P[r][c] = sum_l M[r][c0+l] X[c][l]  (4 columns per thread, the 4 threads of a row in one warp)
+        const int r = c0 + kSB + (tid >> 2), q4 = tid & 3;
+        const bool act = r < mp;
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
+        if (act) {
+          double row[kSB];
+#pragma unroll
+          for (int l = 0; l < kSB; ++l) row[l] = M[r * ldm + c0 + l];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const double* xr = Xd + (4 * q4 + e) * kXP;
+            double acc = 0.0;
+#pragma unroll
+            for (int l = 0; l < kSB; ++l) acc += row[l] * xr[l];
+            out[e] = acc;
+          }
+        }
+        __syncwarp();
+        if (act) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) M[r * ldm + c0 + 4 * q4 + e] = out[e];
+        }
+      }
+      __syncthreads();
+      {  // rank-16 update of the remaining 16 x 16 sub-blocks (lower triangle), one per warp per round
+        const int nrem = nsb - 1 - kb;
+        const int T = nrem * (nrem + 1) / 2;
+        const int ii = lane & 15, jh = lane >> 4;
+        for (int t = warp; t < T; t += kBWarps) {
+          int bi = 0;
+          while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+          const int bj = t - bi * (bi + 1) / 2;
+          const int ri = (kb + 1 + bi) * kSB + ii;
+          const int cj = (kb + 1 + bj) * kSB + 8 * jh;
+          double pr[kSB];
+#pragma unroll
+          for (int l = 0; l < kSB; ++l) pr[l] = M[ri * ldm + c0 + l];
+          double acc[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const double* pj = M + (cj + jj) * ldm + c0;
+            double a8 = 0.0;
+#pragma unroll
+            for (int l = 0; l < kSB; ++l) a8 += pr[l] * pj[l];
+            acc[jj] = a8;
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            if (cj + jj <= ri) M[ri * ldm + cj + jj] -= acc[jj];
+        }
       }
       __syncthreads();
     }
-    for (int j = threadIdx.x; j < m; j += kBT) M[j * ldm + j] = diag[j];
     have_pq = 0;
-    __syncthreads();
+    if (*flag) return LPB_ERR_NUMERICAL_PROBLEM;  // uniform: every thread reads the same shared word
     return LPB_OK;
   }
 
-  // solve L L^T w = rhs in place for NRHS vectors (r0, r1v); thread i owns row i
+  // solve L L^T w = rhs in place for NRHS vectors (r0, r1v; mp entries each): blocked substitution over the
+  // 16-row blocks with the inverted diagonal sub-blocks inside them -- 2 CTA barriers per block and direction.
+  // Thread t < mp owns row t of the first right-hand side, thread mp + t row t of the second.
   template <int NRHS>
   __device__ __forceinline__ void chol_solve(double* r0, double* r1v) {
-    const int i = threadIdx.x;
-    double b0 = 0.0, b1 = 0.0;
-    if (i < m) {
-      b0 = r0[i];
-      if (NRHS == 2) b1 = r1v[i];
-    }
-    for (int l = 0; l < m; ++l) {
-      if (i == l) {
-        const double dl = M[l * ldm + l];
-        sx[l] = b0 = b0 / dl;
-        if (NRHS == 2) sx[kMaxM + l] = b1 = b1 / dl;
+    const int tid = threadIdx.x;
+    const int which = tid >= mp ? 1 : 0;
+    const int row = tid - which * mp;
+    const bool act = which < NRHS && row < mp;
+    double* cv = which ? r1v : r0;
+    double* wv = sx + which * kMaxM;
+    if (act && row >= m) cv[row] = 0.0;  // identity padding rows carry a zero right-hand side
+    __syncthreads();
+    for (int s = 0; s < nsb; ++s) {      // forward: L w = c
+      const int c0 = s * kSB;
+      if (act && row >= c0 && row < c0 + kSB) {
+        const double* xr = Xinv + (s * kSB + (row - c0)) * kXP;
+        double acc = 0.0;
+#pragma unroll
+        for (int l = 0; l < kSB; ++l) acc += xr[l] * cv[c0 + l];  // X is zero above its diagonal
+        wv[row] = acc;
       }
       __syncthreads();
-      if (i > l && i < m) {
-        const double lil = M[i * ldm + l];
-        b0 -= sx[l] * lil;
-        if (NRHS == 2) b1 -= sx[kMaxM + l] * lil;
-      }
-    }
-    __syncthreads();
-    for (int l = m - 1; l >= 0; --l) {
-      if (i == l) {
-        const double dl = M[l * ldm + l];
-        sx[l] = b0 = b0 / dl;
-        if (NRHS == 2) sx[kMaxM + l] = b1 = b1 / dl;
+      if (act && row >= c0) {
+        if (row < c0 + kSB) {
+          cv[row] = wv[row];
+        } else {
+          const double* lr = M + row * ldm + c0;
+          double acc = 0.0;
+#pragma unroll
+          for (int l = 0; l < kSB; ++l) acc += lr[l] * wv[c0 + l];
+          cv[row] -= acc;
+        }
       }
       __syncthreads();
-      if (i < l) {
-        const double lli = M[l * ldm + i];
-        b0 -= sx[l] * lli;
-        if (NRHS == 2) b1 -= sx[kMaxM + l] * lli;
+    }
+    for (int s = nsb - 1; s >= 0; --s) {  // backward: L^T x = w
+      const int c0 = s * kSB;
+      if (act && row >= c0 && row < c0 + kSB) {
+        const int i = row - c0;
+        double acc = 0.0;
+#pragma unroll
+        for (int l = 0; l < kSB; ++l) acc += Xinv[(s * kSB + l) * kXP + i] * cv[c0 + l];  // x_i = sum_l X[l][i] c_l
+        wv[row] = acc;
       }
+      __syncthreads();
+      if (act && row < c0 + kSB) {
+        if (row >= c0) {
+          cv[row] = wv[row];
+        } else {
+          double acc = 0.0;
+#pragma unroll
+          for (int l = 0; l < kSB; ++l) acc += M[(c0 + l) * ldm + row] * wv[c0 + l];
+          cv[row] -= acc;
+        }
+      }
+      __syncthreads();
     }
-    if (i < m) {
-      r0[i] = b0;
-      if (NRHS == 2) r1v[i] = b1;
-    }
-    __syncthreads();
   }
 
   __device__ int direction(const lpb_direction_in& in, double tau, double kappa, lpb_direction_out* o) {
@@ -348,8 +462,11 @@ struct SmemDev {
   }
 };
 
+__host__ __device__ inline int batched_mp(int m) { return (m + kSB - 1) / kSB * kSB; }
 __host__ __device__ inline size_t batched_smem_doubles(int m, int n) {
-  return (size_t)m * (n + 1) + (size_t)m * (m + 1) + 10 * (size_t)n + 7 * (size_t)m + 2 * kMaxM + 8 * kBWarps;
+  const size_t mp = (size_t)batched_mp(m);
+  return (size_t)m * (n + 1) + mp * (mp + 1) + 10 * (size_t)n + 5 * (size_t)m + 2 * mp + 2 * kMaxM + 8 * kBWarps +
+         (mp / kSB) * kSB * kXP + 2 * kSB + 2;
 }
 
 __global__ void __launch_bounds__(kBT)
@@ -362,7 +479,9 @@ batched_ipm_kernel(int64_t batch, int m, int n, const double* __restrict__ gA, c
     d.m = m;
     d.n = n;
     d.lda = n + 1;
-    d.ldm = m + 1;
+    d.mp = batched_mp(m);
+    d.nsb = d.mp / kSB;
+    d.ldm = d.mp + 1;
     double* ptr = sm;
     auto take = [&](size_t cnt) {
       double* r = ptr;
@@ -370,16 +489,18 @@ batched_ipm_kernel(int64_t batch, int m, int n, const double* __restrict__ gA, c
       return r;
     };
     d.A = take((size_t)m * d.lda);
-    d.M = take((size_t)m * d.ldm);
+    d.M = take((size_t)d.mp * d.ldm);
     d.c = take(n); d.x = take(n); d.z = take(n); d.rD = take(n); d.dinv = take(n); d.xs = take(n);
     d.r1 = take(n); d.p = take(n); d.dx = take(n); d.dz = take(n);
     d.u = d.r1;        // u[j] = dinv[j] * (s - r1[j]) overwrites r1[j] in place (r1 is dead afterwards)
-    d.b = take(m); d.y = take(m); d.rP = take(m); d.q = take(m); d.v = take(m); d.dy = take(m);
+    d.b = take(m); d.y = take(m); d.rP = take(m); d.q = take(d.mp); d.v = take(d.mp); d.dy = take(m);
     d.t0 = take(m);
     d.t1 = d.dy;       // t1 is consumed (q = b + t1) before d_y is written
     d.sx = take(2 * kMaxM);
-    d.diag = d.sx;     // the factorisation's pivots live in the substitution scratch
     d.red = take(8 * kBWarps);
+    d.Xinv = take((size_t)d.nsb * kSB * kXP);
+    d.cbuf = take(2 * kSB);
+    d.flag = reinterpret_cast<int*>(take(2));
     d.have_pq = 0;
     d.nan_pq = 0;
     d.cp = d.bq = 0.0;
@@ -388,6 +509,10 @@ batched_ipm_kernel(int64_t batch, int m, int n, const double* __restrict__ gA, c
     for (int idx = threadIdx.x; idx < m * n; idx += kBT) {
       const int i = idx / n, j = idx - i * n;
       d.A[i * d.lda + j] = A[idx];
+    }
+    for (int idx = threadIdx.x; idx < d.mp * d.mp; idx += kBT) {  // identity padding of M beyond m (kept by the factorisation)
+      const int r = idx / d.mp, cc = idx - r * d.mp;
+      if (r >= m || cc >= m) d.M[r * d.ldm + cc] = (r == cc) ? 1.0 : 0.0;
     }
     for (int i = threadIdx.x; i < m; i += kBT) d.b[i] = gb[lp * m + i];
     for (int j = threadIdx.x; j < n; j += kBT) {
