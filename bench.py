@@ -362,9 +362,9 @@ def run_batched(args, torch, dist, rank, local_rank, world, stream):
     lo, hi = min(batch, rank * per), min(batch, (rank + 1) * per)
     nb = hi - lo
     t0 = time.perf_counter()
-    A = np.zeros((nb, m, n))
-    b = np.zeros((nb, m))
-    c = np.zeros((nb, n))
+    A = lp_b200.pinned_empty((nb, m, n))  # host inputs of the e2e leg live in pinned memory (H2D at PCIe rate)
+    b = lp_b200.pinned_empty((nb, m))
+    c = lp_b200.pinned_empty((nb, n))
     for i in range(nb):  # seeds 1000 + i
         cc, A_ub, b_ub, A_eq, b_eq = synthetic_lp(m, n, 1000 + lo + i)
         pb = lp_b200.Problem.target(cc).ub(A_ub, b_ub).eq(A_eq, b_eq).build()

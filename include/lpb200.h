@@ -208,6 +208,8 @@ int lpb_extract_x(lpb_ctx* ctx, double tau, double* x_out, double* fun);
 int lpb_solve_batched(int64_t batch, int64_t m, int64_t n, const double* A, const double* b,
                       const double* c, const lpb_options* opts, double* x_out, double* fun,
                       int64_t* iterations, int32_t* status, int mem, void* stream);
+/* Free the device staging memory lpb_solve_batched keeps between calls with host inputs (per calling thread). */
+int lpb_release_workspaces(void);
 
 /* ------------------------------------------------------------------ kernel entry points
  * Device-pointer forms of the hot kernels (parity tests and roofline measurements). */

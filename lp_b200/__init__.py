@@ -11,6 +11,7 @@ from .api import (  # noqa: F401
     ShardedProblem,
     SyntheticShardedProblem,
     solve_batched,
+    pinned_empty,
     EquationSolverType,
     IncompatibleInputDimensions,
     Infeasible,
@@ -29,7 +30,7 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "BatchedResult", "ResidentProblem", "ShardedProblem", "SyntheticShardedProblem", "solve_batched",
+    "BatchedResult", "ResidentProblem", "ShardedProblem", "SyntheticShardedProblem", "solve_batched", "pinned_empty",
     "EquationSolverType", "IncompatibleInputDimensions", "Infeasible", "InteriorPoint", "InteriorPointBuilder",
     "InvalidParameter", "IterationLimitExceeded", "LinearProgramError", "NumericalProblem", "OptimizeResult",
     "Problem", "ProblemBuilder", "Solver", "Unbounded", "Unconstrained",

@@ -119,6 +119,7 @@ SIGNATURES = {
     "lpb_k_potrs": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "lpb_k_gemv_n": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "lpb_k_gemv_t": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "lpb_release_workspaces": (C.c_int, []),
     "lpb_get_profile": (C.c_int, [C.c_void_p, C.POINTER(lpb_profile)]),
     "lpb_launch_count": (C.c_int64, [C.c_void_p]),
     "lpb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),

@@ -125,6 +125,20 @@ class _HostBuffer:
             self._ptr = None
 
 
+class _PinnedArray(np.ndarray):
+    """ndarray view of a pinned host allocation; keeps the allocation alive as long as any view of it is."""
+    _lpb_host = None
+
+
+def pinned_empty(shape) -> np.ndarray:
+    """A float64 array in pinned (page-locked) host memory when a CUDA device is visible -- inputs built in
+    it upload at PCIe rate (`solve_batched`, `Problem` buffers) -- else an ordinary NumPy array."""
+    buf = _HostBuffer(shape)
+    out = buf.array.view(_PinnedArray)
+    out._lpb_host = buf
+    return out
+
+
 def _as_f64(a, ndim):
     arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
     if arr.ndim != ndim:

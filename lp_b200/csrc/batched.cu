@@ -195,9 +195,12 @@ struct SmemDev {
         double v[kSB];
 #pragma unroll
         for (int k = 0; k < kSB; ++k) v[k] = (!inv_lane && k <= i) ? M[(c0 + i) * ldm + c0 + k] : 0.0;
+        // the diagonal entry of this lane's row lives in its own register: the next pivot then depends only on
+        // rsqrt -> l -> dg -= l * l, not on the shared-memory round trip of the column broadcast
+        double dg = inv_lane ? 0.0 : M[(c0 + i) * ldm + c0 + i];
 #pragma unroll
         for (int j = 0; j < kSB; ++j) {
-          const double ajj = __shfl_sync(full, v[j], j);
+          const double ajj = __shfl_sync(full, dg, j);
           const bool bad = !(ajj > 0.0) || !isfinite(ajj);
           if (bad && lane == 0) *flag = 1;
           double rs = rsqrt(ajj);
@@ -214,6 +217,7 @@ struct SmemDev {
             l = ((i == j ? 1.0 : 0.0) - v[j]) * rs;  // x_j of column i of the inverse
           }
           v[j] = l;
+          if (!inv_lane && i > j) dg = fma(-l, l, dg);
           double* cb = cbuf + (j & 1) * kSB;
           if (!inv_lane) cb[i] = l;
           __syncwarp();

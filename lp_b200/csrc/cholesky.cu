@@ -114,10 +114,13 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
       double v[SB];
 #pragma unroll
       for (int k = 0; k < SB; ++k) v[k] = (!inv_lane && k <= i) ? S[(c0 + i) * LDS + c0 + k] : 0.0;
+      // the diagonal entry of this lane's row lives in its own register: the next pivot then depends only on
+      // rsqrt -> l -> dg -= l * l, not on the shared-memory round trip of the column broadcast
+      double dg = inv_lane ? 0.0 : S[(c0 + i) * LDS + c0 + i];
       double myrd = 1.0;
 #pragma unroll
       for (int j = 0; j < SB; ++j) {
-        const double ajj = __shfl_sync(full, v[j], j);
+        const double ajj = __shfl_sync(full, dg, j);
         const bool bad = !(ajj > 0.0) || !isfinite(ajj);
         if (bad && lane == 0 && *info == 0) *info = k0 + c0 + j + 1;
         double rs = rsqrt(ajj);
@@ -135,6 +138,7 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
         }
         if (i == j) myrd = rs;
         v[j] = l;
+        if (!inv_lane && i > j) dg = fma(-l, l, dg);
         double* cb = cbuf + (j & 1) * SB;
         if (!inv_lane) cb[i] = l;
         __syncwarp();

@@ -153,6 +153,10 @@ struct ProcessComm {
 };
 ProcessComm g_comm;
 
+// device staging arena of lpb_solve_batched for host inputs (per host thread, grow-only)
+thread_local void* g_batched_ws = nullptr;
+thread_local size_t g_batched_ws_cap = 0;
+
 int allreduce(lpb_ctx* c, double* buf, int64_t count, ncclRedOp_t op) {
   if (c->world <= 1) return LPB_OK;
   PhaseTimer tm(c, PH_COMM);
@@ -1067,46 +1071,49 @@ int lpb_solve_batched(int64_t batch, int64_t m, int64_t n, const double* A, cons
     LPB_CUDA(cudaStreamSynchronize(st));
     return LPB_OK;
   }
-  double *dA = nullptr, *db = nullptr, *dc = nullptr, *dx = nullptr, *df = nullptr;
-  int64_t* dit = nullptr;
-  int32_t* dst = nullptr;
-  int rc = LPB_OK;
-  auto cleanup = [&]() {
-    cudaFree(dA); cudaFree(db); cudaFree(dc); cudaFree(dx); cudaFree(df); cudaFree(dit); cudaFree(dst);
-  };
-#define LPB_BCUDA(call)                                                                         \
-  do {                                                                                          \
-    cudaError_t e__ = (call);                                                                   \
-    if (e__ != cudaSuccess) {                                                                   \
-      set_last_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));     \
-      cleanup();                                                                                \
-      return LPB_ERR_CUDA;                                                                      \
-    }                                                                                           \
-  } while (0)
+  // Host arrays: stage through ONE cached device arena per host thread (grow-only; lpb_release_workspaces
+  // frees it), so a call costs the three uploads, the kernel and the four downloads -- no cudaMalloc / cudaFree.
   const size_t sA = sizeof(double) * (size_t)(batch * m * n), sb = sizeof(double) * (size_t)(batch * m),
-               sc = sizeof(double) * (size_t)(batch * n);
-  LPB_BCUDA(cudaMalloc(&dA, sA));
-  LPB_BCUDA(cudaMalloc(&db, sb));
-  LPB_BCUDA(cudaMalloc(&dc, sc));
-  LPB_BCUDA(cudaMalloc(&dx, sc));
-  LPB_BCUDA(cudaMalloc(&df, sizeof(double) * (size_t)batch));
-  LPB_BCUDA(cudaMalloc(&dit, sizeof(int64_t) * (size_t)batch));
-  LPB_BCUDA(cudaMalloc(&dst, sizeof(int32_t) * (size_t)batch));
-  LPB_BCUDA(cudaMemcpyAsync(dA, A, sA, cudaMemcpyHostToDevice, st));
-  LPB_BCUDA(cudaMemcpyAsync(db, b, sb, cudaMemcpyHostToDevice, st));
-  LPB_BCUDA(cudaMemcpyAsync(dc, c, sc, cudaMemcpyHostToDevice, st));
-  rc = batched_launch(batch, (int)m, (int)n, dA, db, dc, o, dx, df, dit, dst, st);
-  if (rc != LPB_OK) {
-    cleanup();
-    return rc;
+               sc = sizeof(double) * (size_t)(batch * n), s8 = sizeof(double) * (size_t)batch,
+               s4 = sizeof(int32_t) * (size_t)batch;
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t need = up(sA) + up(sb) + 2 * up(sc) + 2 * up(s8) + up(s4);
+  if (g_batched_ws_cap < need) {
+    if (g_batched_ws) cudaFree(g_batched_ws);
+    g_batched_ws = nullptr;
+    g_batched_ws_cap = 0;
+    LPB_CUDA(cudaMalloc(&g_batched_ws, need));
+    g_batched_ws_cap = need;
   }
-  LPB_BCUDA(cudaMemcpyAsync(x_out, dx, sc, cudaMemcpyDeviceToHost, st));
-  LPB_BCUDA(cudaMemcpyAsync(fun, df, sizeof(double) * (size_t)batch, cudaMemcpyDeviceToHost, st));
-  LPB_BCUDA(cudaMemcpyAsync(iterations, dit, sizeof(int64_t) * (size_t)batch, cudaMemcpyDeviceToHost, st));
-  LPB_BCUDA(cudaMemcpyAsync(status, dst, sizeof(int32_t) * (size_t)batch, cudaMemcpyDeviceToHost, st));
-  LPB_BCUDA(cudaStreamSynchronize(st));
-#undef LPB_BCUDA
-  cleanup();
+  char* p = static_cast<char*>(g_batched_ws);
+  auto carve = [&](size_t bytes) {
+    char* r = p;
+    p += up(bytes);
+    return r;
+  };
+  double* dA = reinterpret_cast<double*>(carve(sA));
+  double* db = reinterpret_cast<double*>(carve(sb));
+  double* dc = reinterpret_cast<double*>(carve(sc));
+  double* dx = reinterpret_cast<double*>(carve(sc));
+  double* df = reinterpret_cast<double*>(carve(s8));
+  int64_t* dit = reinterpret_cast<int64_t*>(carve(s8));
+  int32_t* dst = reinterpret_cast<int32_t*>(carve(s4));
+  LPB_CUDA(cudaMemcpyAsync(dA, A, sA, cudaMemcpyHostToDevice, st));
+  LPB_CUDA(cudaMemcpyAsync(db, b, sb, cudaMemcpyHostToDevice, st));
+  LPB_CUDA(cudaMemcpyAsync(dc, c, sc, cudaMemcpyHostToDevice, st));
+  LPB_TRY(batched_launch(batch, (int)m, (int)n, dA, db, dc, o, dx, df, dit, dst, st));
+  LPB_CUDA(cudaMemcpyAsync(x_out, dx, sc, cudaMemcpyDeviceToHost, st));
+  LPB_CUDA(cudaMemcpyAsync(fun, df, s8, cudaMemcpyDeviceToHost, st));
+  LPB_CUDA(cudaMemcpyAsync(iterations, dit, s8, cudaMemcpyDeviceToHost, st));
+  LPB_CUDA(cudaMemcpyAsync(status, dst, s4, cudaMemcpyDeviceToHost, st));
+  LPB_CUDA(cudaStreamSynchronize(st));
+  return LPB_OK;
+}
+
+int lpb_release_workspaces(void) {
+  if (g_batched_ws) cudaFree(g_batched_ws);
+  g_batched_ws = nullptr;
+  g_batched_ws_cap = 0;
   return LPB_OK;
 }
 
