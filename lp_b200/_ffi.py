@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "liblpb200.so")
@@ -129,6 +130,21 @@ SIGNATURES = {
 _lib = None
 
 
+def _preload_nccl():
+    """liblpb200.so needs `libnccl.so.2`.  A process that also imports torch must end up with ONE NCCL, and it
+    has to be torch's bundled one (newer than the system library; torch fails to import against the older
+    one: "undefined symbol ncclDevCommCreate").  Loading the bundled copy first, when there is one, makes the
+    order of `import torch` and the first lp_b200 call irrelevant."""
+    for base in sys.path:
+        cand = os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def load():
     """dlopen liblpb200.so (once) and attach the prototypes.  Raises LibraryNotBuilt if absent."""
     global _lib
@@ -138,6 +154,7 @@ def load():
         raise LibraryNotBuilt(
             "%s not found: run `python -c 'import __graft_entry__ as g; g.build()'` (or "
             "`python -m lp_b200.build`) first. There is no CPU fallback." % LIB_PATH)
+    _preload_nccl()
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)

@@ -291,6 +291,11 @@ def test_structure_detection_edge_cases():
     Lref2 = np.linalg.cholesky(A2 @ A2.T)
     assert cols2 == n0 + 6                    # columns n0+6 .. end fold (row 5 is taken by the last one)
     assert np.abs(L2 - Lref2).max() <= 1e-11 * np.abs(Lref2).max()
+    # odd number of dense columns (the TMA box runs past the tensor map's last column: zero fill)
+    A4 = np.hstack([A0[:, :59], tail])
+    L4, cols4 = factor(A4, 1)
+    assert cols4 == 59
+    assert np.abs(L4 - np.linalg.cholesky(A4 @ A4.T)).max() <= 1e-11 * np.abs(Lref).max()
     # short run: 8 singleton columns only -> dense
     A3 = A[:, : n0 + 8]
     L3, cols3 = factor(A3, 1)

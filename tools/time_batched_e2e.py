@@ -1,6 +1,10 @@
 """Where does the host-side time of lpb_solve_batched go?  (diagnostic; GPU box only)"""
 import ctypes as C
+import os
+import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 
