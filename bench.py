@@ -260,7 +260,12 @@ def _roofline(prof_sum, m, n_loc):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE syrk_dmma_kernel launch, from the committed
 # `ncu --set full` captures (profiles/); keyed by (m, n_local).
-SYRK_TRAFFIC = {}
+SYRK_TRAFFIC = {
+    # C3 on 1 GPU, banded tile order: 46.05 GB read + 1.08 GB written (profiles/ncu_syrk_C3_r01_v14.txt);
+    # algorithmic bytes: 3.22 GB of A (dense columns) + 1.07 GB of M.  The kernel is DMMA-bound (DRAM at 3 %
+    # of peak); the re-reads are operand tiles streamed once per wave of 148 tiles.
+    (16384, 24576): 46.048303e9 + 1.082822e9,
+}
 
 
 def _timed_solves(args, torch, dist, solver, rp, local_rank):

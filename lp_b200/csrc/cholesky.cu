@@ -123,19 +123,15 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
         const double ajj = __shfl_sync(full, dg, j);
         const bool bad = !(ajj > 0.0) || !isfinite(ajj);
         if (bad && lane == 0 && *info == 0) *info = k0 + c0 + j + 1;
+        // rsqrt is accurate to 1 ulp (CUDA math API), so d = a rs and l = a[i][j] rs are within 2 ulp of sqrt and of
+        // the quotient: far below the n eps backward error of the factorisation itself, and the pivot chain
+        // SHFL -> rsqrt -> l -> dg stays short (no divisions, no Newton steps, no divergent branch).
         double rs = rsqrt(ajj);
         double d = ajj * rs;
-        d = fma(fma(-d, d, ajj), 0.5 * rs, d);    // sqrt(ajj)
-        rs = fma(fma(-d, rs, 1.0), rs, rs);       // 1 / sqrt(ajj)
         if (bad) d = rs = __longlong_as_double(0x7ff8000000000000ll);
-        double l;
-        if (!inv_lane) {
-          l = v[j] * rs;
-          l = fma(fma(-l, d, v[j]), rs, l);       // a[i][j] / d
-          if (i == j) l = d;
-        } else {
-          l = ((i == j ? 1.0 : 0.0) - v[j]) * rs;  // x_j of column i
-        }
+        const double num = inv_lane ? ((i == j ? 1.0 : 0.0) - v[j]) : v[j];  // inverse lanes: x_j of column i
+        double l = num * rs;
+        if (!inv_lane && i == j) l = d;
         if (i == j) myrd = rs;
         v[j] = l;
         if (!inv_lane && i > j) dg = fma(-l, l, dg);

@@ -117,3 +117,13 @@ def test_compute_fails_loudly_without_gpu(lib):
     with pytest.raises(lp_b200.api.DeviceError) as e:
         lp_b200.InteriorPoint.default().solve(pb)
     assert e.value.code == _ffi.LPB_ERR_NO_DEVICE
+
+
+def test_pinned_empty_degrades_to_numpy_without_a_gpu():
+    import numpy as np
+    import lp_b200
+    a = lp_b200.pinned_empty((3, 5))
+    a[:] = 2.0
+    assert isinstance(a, np.ndarray) and a.shape == (3, 5) and a.dtype == np.float64 and a.sum() == 30.0
+    v = np.ascontiguousarray(a, dtype=np.float64)          # what solve_batched does: a view, not a copy
+    assert v.ctypes.data == a.ctypes.data

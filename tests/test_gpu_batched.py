@@ -57,3 +57,21 @@ def test_batched_statuses_and_limits():
     assert res.status[2] == _ffi.LPB_ERR_ITERATION_LIMIT_EXCEEDED and res.iteration[2] == 1
     with pytest.raises(lp_b200.InvalidParameter):
         lp_b200.solve_batched(np.zeros((1, 65, 70)), np.zeros((1, 65)), np.zeros((1, 70)))  # m > 64 unsupported
+
+
+def test_batched_staging_arena_and_pinned_inputs():
+    """Host inputs are staged through a cached device arena: repeated calls, a call after
+    lpb_release_workspaces and a call with page-locked inputs (lp_b200.pinned_empty) all give the same bits."""
+    A, b, c, n_slack = make_batch(16, 64, 128, 3000)
+    r1 = lp_b200.solve_batched(A, b, c, n_slack=n_slack)
+    r2 = lp_b200.solve_batched(A, b, c, n_slack=n_slack)
+    assert _ffi.load().lpb_release_workspaces() == 0
+    r3 = lp_b200.solve_batched(A[:5], b[:5], c[:5], n_slack=n_slack)       # smaller batch: arena re-created
+    Ap, bp, cp = lp_b200.pinned_empty(A.shape), lp_b200.pinned_empty(b.shape), lp_b200.pinned_empty(c.shape)
+    Ap[:], bp[:], cp[:] = A, b, c
+    r4 = lp_b200.solve_batched(Ap, bp, cp, n_slack=n_slack)
+    for r in (r2, r4):
+        np.testing.assert_array_equal(r.x, r1.x)
+        np.testing.assert_array_equal(r.iteration, r1.iteration)
+    np.testing.assert_array_equal(r3.x, r1.x[:5])
+    assert (r1.status == _ffi.LPB_OK).all()
