@@ -61,16 +61,25 @@ int k_gemv_n(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, 
 // Row-chunk partials of A^T v_k into lc.gemv_partials; returns chunk count.
 int k_gemv_t_partials(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* v0,
                       const double* v1, int nrhs, int* nchunks);
-// n-side epilogues consuming the partials:
+// Trailing singleton / zero columns of A (lpb_ctx::n_dense): the partials cover columns [0, nd) only (pitch
+// round_up(nd, 2)); for j >= nd, (A^T v_k)[j] = col_val[j] * v_k[col_row[j]] (0 if col_row[j] < 0).
+struct TailCols {
+  int64_t nd;
+  const int* col_row;
+  const double* col_val;
+  const double* v0;
+  const double* v1;
+};
+// n-side epilogues consuming the partials (tail == nullptr: every column comes from the partials):
 //  raw: out = sum_chunks
 int k_gemv_t_raw(LaunchCtx& lc, int64_t n, int nchunks, int nrhs, double* out0, double* out1);
 //  residual: rD = c*tau - s - z ; partials sum rD^2 -> val_base, c.x -> +1, x.z -> +2
 int k_resid_d(LaunchCtx& lc, int64_t n, int nchunks, double tau, const double* c, const double* z, const double* x,
-              double* rD, int val_base, int* nblocks);
+              double* rD, int val_base, int* nblocks, const TailCols* tail = nullptr);
 //  sym_solve back (newton_equations.rs:223): u = dinv*(s0 - r1) ; (with_pq) p = dinv*(s1 - c)
 //  partials c.u -> val_base ; (with_pq) c.p -> +1, #NaN(p) -> +2
 int k_sym_back(LaunchCtx& lc, int64_t n, int nchunks, int with_pq, const double* dinv, const double* r1,
-               const double* c, double* u, double* p, int val_base, int* nblocks);
+               const double* c, double* u, double* p, int val_base, int* nblocks, const TailCols* tail = nullptr);
 
 // ---------------------------------------------------------------- K1 / K2 trailing update (dmma_gemm.cu)
 // C(lower tiles) = A diag(d) A^T over k in [0, n)           (accumulate == 0, d may be null)
@@ -104,8 +113,14 @@ int k_slack_identity(LaunchCtx& lc, double* A, int64_t rows, int64_t cols, int64
 int k_add_vec(LaunchCtx& lc, double* out, const double* a, const double* b, int64_t count, int64_t count_b);
 // per-column structure of A: nnz count, last non-zero row (-1 if none), value (valid iff nnz == 1)
 int k_col_structure(LaunchCtx& lc, const double* A, int64_t m, int64_t n, int64_t lda, int* nnz, int* row, double* val);
-// M[r][r] += sq[r] * dinv[col[r]] where col[r] >= 0 (singleton columns folded into the diagonal)
-int k_diag_add(LaunchCtx& lc, int64_t m, double* M, int64_t ldm, const int* col, const double* sq, const double* dinv);
+// M[r][r] += val[r]^2 * dinv[col[r]] where col[r] >= 0 (singleton columns folded into the diagonal)
+int k_diag_add(LaunchCtx& lc, int64_t m, double* M, int64_t ldm, const int* col, const double* val, const double* dinv);
+// t_k[r] += val[r] * (dinv ? dinv[j] : 1) * w_k[j], j = col[r] >= 0: the singleton columns' share of A (dinv * w_k)
+int k_slack_add(LaunchCtx& lc, int64_t m, const int* col, const double* val, const double* dinv, const double* w0,
+                const double* w1, double* t0, double* t1, int nrhs);
+// lower triangle of M <-> packed buffer of tri_packed_doubles(m) doubles (block row i: 128 x 128 (i + 1), contiguous)
+int64_t tri_packed_doubles(int64_t m);
+int k_tri_pack(LaunchCtx& lc, double* M, int64_t ldm, int64_t m, double* buf, bool pack);
 // order-independent bit checksum of a matrix block (replica-agreement checks of the sharded path)
 int k_diff(LaunchCtx& lc, const double* a, const double* b, int64_t rows, int64_t cols, int64_t ld, int lower_only,
            unsigned long long* out_dev3);

@@ -45,8 +45,10 @@ struct lpb_ctx {
   // [I; 0] of linear_program.rs:145-156 -- folded into the diagonal of M instead of being contracted over.
   int64_t n_dense = 0, n_singleton = 0;
   int use_structure = 1;
-  int* sgl_col = nullptr;     // m: local column whose only non-zero sits in this row, or -1
-  double* sgl_sq = nullptr;   // m: that entry squared
+  int* sgl_col = nullptr;     // m: local column (>= n_dense) whose only non-zero sits in this row, or -1
+  double* sgl_val = nullptr;  // m: that entry
+  int* col_row = nullptr;     // n: for columns >= n_dense, the row of their only non-zero, or -1 (all-zero column)
+  double* col_val = nullptr;  // n: ... and its value
   int refine = 1;  // iterative-refinement steps per sym_solve (0 = the plain factor-and-solve of the reference)
   double *c = nullptr, *x = nullptr, *z = nullptr, *rD = nullptr, *dinv = nullptr, *xs = nullptr, *r1 = nullptr,
          *p = nullptr, *u = nullptr, *dx = nullptr, *dz = nullptr, *xo = nullptr;
@@ -57,6 +59,8 @@ struct lpb_ctx {
   bool profile = true;
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
+  int packed_allreduce = 1;             // sharded: all-reduce only the lower triangle of M (packed), not the square
+  double* tri_buf = nullptr;            // its staging buffer (tri_packed_doubles(m))
   int potrf_verify = 0;                 // debug: factor every M twice and compare the two factors bit for bit
   double *vfy1 = nullptr, *vfy2 = nullptr;
   int64_t vfy_mismatch = 0, vfy_runs = 0;
@@ -196,6 +200,27 @@ int finish_scalars(lpb_ctx* c, const RedSpec& spec, int n_sharded, ncclRedOp_t o
 struct CudaDev {
   lpb_ctx* c;
 
+  // t_k = A (dinv? dinv * w_k : w_k): the dense columns through the GEMV kernel, the trailing singleton columns
+  // (the slack block) as one scaled add per row -- they are never read from A (lpb_ctx::n_dense).
+  int sweep_n(const double* dinv, const double* w0, const double* w1, double* t0, double* t1, int nrhs) {
+    if (c->n_dense > 0) {
+      LPB_TRY(k_gemv_n(c->lc, c->m, c->n_dense, c->A, c->lda, dinv, w0, w1, t0, t1, nrhs));
+    } else {
+      LPB_CUDA(cudaMemsetAsync(t0, 0, sizeof(double) * (size_t)c->m, c->lc.stream));
+      if (nrhs == 2) LPB_CUDA(cudaMemsetAsync(t1, 0, sizeof(double) * (size_t)c->m, c->lc.stream));
+    }
+    if (c->n_singleton > 0)
+      LPB_TRY(k_slack_add(c->lc, c->m, c->sgl_col, c->sgl_val, dinv, w0, w1, t0, t1, nrhs));
+    return LPB_OK;
+  }
+  // row-chunk partials of A^T v_k over the dense columns; `tail` tells the epilogue how to form the rest
+  int sweep_t(const double* v0, const double* v1, int nrhs, int* nchunks, TailCols* tail) {
+    *nchunks = 0;
+    if (c->n_dense > 0) LPB_TRY(k_gemv_t_partials(c->lc, c->m, c->n_dense, c->A, c->lda, v0, v1, nrhs, nchunks));
+    *tail = TailCols{c->n_dense, c->col_row, c->col_val, v0, v1};
+    return LPB_OK;
+  }
+
   int blind_start() {  // feasible_point.rs:24-39
     PhaseTimer tm(c, PH_VEC);
     LPB_TRY(k_fill(c->lc, c->x, c->n, 1.0));
@@ -212,7 +237,7 @@ struct CudaDev {
     int nb_n = 0, nb_m = 0, nchunks = 0;
     {
       PhaseTimer tm(c, PH_SWEEP);
-      LPB_TRY(k_gemv_n(c->lc, c->m, c->n, c->A, c->lda, nullptr, c->x, nullptr, c->t, nullptr, 1));
+      LPB_TRY(sweep_n(nullptr, c->x, nullptr, c->t, nullptr, 1));
     }
     LPB_TRY(allreduce(c, c->t, c->m, ncclSum));
     LPB_TRY(check_replicated(c, "A x after the all-reduce", c->t, 1, c->m, c->m, 0));
@@ -220,8 +245,9 @@ struct CudaDev {
     {
       PhaseTimer tm(c, PH_SWEEP);
       LPB_TRY(k_resid_p(c->lc, c->m, tau, c->b, c->t, c->y, c->rP, 3, &nb_m));
-      LPB_TRY(k_gemv_t_partials(c->lc, c->m, c->n, c->A, c->lda, c->y, nullptr, 1, &nchunks));
-      LPB_TRY(k_resid_d(c->lc, c->n, nchunks, tau, c->c, c->z, c->x, c->rD, 0, &nb_n));
+      TailCols tail;
+      LPB_TRY(sweep_t(c->y, nullptr, 1, &nchunks, &tail));
+      LPB_TRY(k_resid_d(c->lc, c->n, nchunks, tau, c->c, c->z, c->x, c->rD, 0, &nb_n, &tail));
     }
     spec.nblocks[0] = spec.nblocks[1] = spec.nblocks[2] = nb_n;
     spec.nblocks[3] = spec.nblocks[4] = nb_m;
@@ -248,11 +274,28 @@ struct CudaDev {
         LPB_TRY(k_syrk_simple(c->lc, c->m, c->n_dense, c->A, c->lda, c->dinv, c->M, c->ldm));
       else
         LPB_TRY(k_syrk_dmma(c->lc, c->m, c->n_dense, c->A, c->lda, c->dinv, c->M, c->ldm));
-      if (c->n_singleton > 0) LPB_TRY(k_diag_add(c->lc, c->m, c->M, c->ldm, c->sgl_col, c->sgl_sq, c->dinv));
+      if (c->n_singleton > 0) LPB_TRY(k_diag_add(c->lc, c->m, c->M, c->ldm, c->sgl_col, c->sgl_val, c->dinv));
       c->prof.syrk_launches++;
       c->prof.syrk_cols = c->n_dense;
     }
-    LPB_TRY(allreduce(c, c->M, c->m * c->ldm, ncclSum));
+    if (c->world > 1 && c->packed_allreduce) {
+      const int64_t cnt = tri_packed_doubles(c->m);
+      if (!c->tri_buf) {
+        LPB_TRY(dev_alloc(c, &c->tri_buf, cnt));
+        LPB_CUDA(cudaMemsetAsync(c->tri_buf, 0, sizeof(double) * (size_t)cnt, c->lc.stream));  // padding stays finite
+      }
+      {
+        PhaseTimer tm(c, PH_COMM);
+        LPB_TRY(k_tri_pack(c->lc, c->M, c->ldm, c->m, c->tri_buf, true));
+      }
+      LPB_TRY(allreduce(c, c->tri_buf, cnt, ncclSum));
+      {
+        PhaseTimer tm(c, PH_COMM);
+        LPB_TRY(k_tri_pack(c->lc, c->M, c->ldm, c->m, c->tri_buf, false));
+      }
+    } else {
+      LPB_TRY(allreduce(c, c->M, c->m * c->ldm, ncclSum));
+    }
     LPB_TRY(check_replicated(c, "M after the all-reduce", c->M, c->m, c->m, c->ldm, 1));
     const size_t mbytes = sizeof(double) * (size_t)(c->m * c->ldm);
     if (c->potrf_verify) {
@@ -317,7 +360,7 @@ struct CudaDev {
     }
     {
       PhaseTimer tm(c, PH_SWEEP);
-      LPB_TRY(k_gemv_n(c->lc, c->m, c->n, c->A, c->lda, c->dinv, c->r1, c->c, c->t, c->t + c->m, nrhs));
+      LPB_TRY(sweep_n(c->dinv, c->r1, c->c, c->t, c->t + c->m, nrhs));
     }
     LPB_TRY(allreduce(c, c->t, c->m * nrhs, ncclSum));
     LPB_TRY(check_replicated(c, "A (Dinv r1) after the all-reduce", c->t, 1, c->m * nrhs, c->m * nrhs, 0));
@@ -335,8 +378,9 @@ struct CudaDev {
     int nchunks = 0, nb_n = 0, nb_m = 0;
     {
       PhaseTimer tm(c, PH_SWEEP);
-      LPB_TRY(k_gemv_t_partials(c->lc, c->m, c->n, c->A, c->lda, W0, W1, nrhs, &nchunks));
-      LPB_TRY(k_sym_back(c->lc, c->n, nchunks, with_pq, c->dinv, c->r1, c->c, c->u, c->p, 0, &nb_n));
+      TailCols tail;
+      LPB_TRY(sweep_t(W0, W1, nrhs, &nchunks, &tail));
+      LPB_TRY(k_sym_back(c->lc, c->n, nchunks, with_pq, c->dinv, c->r1, c->c, c->u, c->p, 0, &nb_n, &tail));
     }
     // Iterative refinement against the OPERATOR A Dinv A^T (not the stored M): the residual of
     //   M v = r2 + A Dinv r1   is   r2 - A u   with u = Dinv (A^T v - r1),   i.e.  rP*eta - A u  and  b - A p,
@@ -349,7 +393,7 @@ struct CudaDev {
       double* R1 = c->R + c->m;
       {
         PhaseTimer tm(c, PH_SWEEP);
-        LPB_TRY(k_gemv_n(c->lc, c->m, c->n, c->A, c->lda, nullptr, c->u, c->p, c->t, c->t + c->m, nrhs));
+        LPB_TRY(sweep_n(nullptr, c->u, c->p, c->t, c->t + c->m, nrhs));
       }
       LPB_TRY(allreduce(c, c->t, c->m * nrhs, ncclSum));
       {
@@ -366,8 +410,9 @@ struct CudaDev {
       }
       {
         PhaseTimer tm(c, PH_SWEEP);
-        LPB_TRY(k_gemv_t_partials(c->lc, c->m, c->n, c->A, c->lda, W0, W1, nrhs, &nchunks));
-        LPB_TRY(k_sym_back(c->lc, c->n, nchunks, with_pq, c->dinv, c->r1, c->c, c->u, c->p, 0, &nb_n));
+        TailCols tail;
+        LPB_TRY(sweep_t(W0, W1, nrhs, &nchunks, &tail));
+        LPB_TRY(k_sym_back(c->lc, c->n, nchunks, with_pq, c->dinv, c->r1, c->c, c->u, c->p, 0, &nb_n, &tail));
       }
     }
     {
@@ -481,12 +526,14 @@ int ctx_alloc_vectors(lpb_ctx* c, int64_t m, int64_t n, bool with_matrices) {
   LPB_TRY(dev_alloc(c, &c->t, 2 * m));
   LPB_TRY(dev_alloc(c, &c->W, 2 * m));
   LPB_TRY(dev_alloc(c, &c->R, 2 * m));
-  LPB_TRY(dev_alloc(c, &c->sgl_sq, m));
+  LPB_TRY(dev_alloc(c, &c->sgl_val, m));
+  LPB_TRY(dev_alloc(c, &c->col_val, n));
   {
     void* q = nullptr;
-    LPB_CUDA(cudaMalloc(&q, sizeof(int) * (size_t)m));
+    LPB_CUDA(cudaMalloc(&q, sizeof(int) * (size_t)(m + n)));
     c->allocs.push_back(q);
     c->sgl_col = static_cast<int*>(q);
+    c->col_row = c->sgl_col + m;
   }
   double** nv[] = {&c->c, &c->x, &c->z, &c->rD, &c->dinv, &c->xs, &c->r1, &c->p, &c->u, &c->dx, &c->dz, &c->xo};
   for (auto p : nv) LPB_TRY(dev_alloc(c, p, round_up(n, 2)));
@@ -541,14 +588,18 @@ int analyze_structure(lpb_ctx* c) {
       const int r = row[j];
       if (r < 0 || r >= m || col_of_row[r] >= 0) break;
       col_of_row[r] = (int)j;
-      sq[r] = h_val[j] * h_val[j];
+      sq[r] = h_val[j];  // the entry itself; squared on the device where M needs it
       ++nsgl;
     }
     --nd;
   }
   if (n - nd < 16) return LPB_OK;  // not worth a separate pass
+  for (int64_t j = nd; j < n; ++j)  // column-indexed view of the same run, for the A^T v epilogues
+    if (nnz[j] != 1) h_int[(size_t)(n + j)] = -1;
   LPB_CUDA(cudaMemcpyAsync(c->sgl_col, col_of_row.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, c->lc.stream));
-  LPB_CUDA(cudaMemcpyAsync(c->sgl_sq, sq.data(), sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, c->lc.stream));
+  LPB_CUDA(cudaMemcpyAsync(c->sgl_val, sq.data(), sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, c->lc.stream));
+  LPB_CUDA(cudaMemcpyAsync(c->col_row, row, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->lc.stream));
+  LPB_CUDA(cudaMemcpyAsync(c->col_val, h_val.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->lc.stream));
   LPB_CUDA(cudaStreamSynchronize(c->lc.stream));  // the host vectors go out of scope
   c->n_dense = nd;
   c->n_singleton = nsgl;
@@ -1157,6 +1208,10 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
   if (k == "structure") {  // 0: contract over every column of A (no slack-column shortcut)
     c->use_structure = value != 0;
     return c->has_problem ? analyze_structure(c) : LPB_OK;
+  }
+  if (k == "packed_allreduce") {
+    c->packed_allreduce = value != 0;
+    return LPB_OK;
   }
   if (k == "potrf_dist") {  // 0: replicated factorisation on every rank of a sharded context
     c->lc.potrf_dist = value != 0;

@@ -493,10 +493,12 @@ static inline void gemv_t_shape(int64_t m, int64_t n, int* nchunks, int* rows_pe
   *colblocks = (int)cb;
 }
 
+// Workspace bound for ANY column count n' <= n (the sweeps run over the dense leading columns only, and fewer
+// columns mean more row chunks): chunks never exceed max(kGemvTMaxChunks, ceil(m / kGemvTMaxRows)).
 int64_t gemv_t_partials_doubles(int64_t m, int64_t n) {
-  int nc, rpc, cb;
-  gemv_t_shape(m, n, &nc, &rpc, &cb);
-  return (int64_t)nc * 2 * round_up(n, 2);
+  int64_t nc = ceil_div(m, kGemvTMaxRows);
+  if (nc < kGemvTMaxChunks) nc = kGemvTMaxChunks;
+  return nc * 2 * round_up(n, 2);
 }
 
 int k_gemv_t_partials(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* v0,
@@ -530,6 +532,15 @@ __device__ __forceinline__ double sum_chunks(const double* __restrict__ partials
   return s;
 }
 
+// (A^T v_k)[j] for the epilogues: columns below tc.nd come from the row-chunk partials (pitch round_up(nd, 2));
+// the trailing singleton / zero columns (lpb_ctx::n_dense) are s_j * v_k[row_j] and never touch A.
+__device__ __forceinline__ double at_dot(const double* __restrict__ partials, int nchunks, int nrhs, int k,
+                                         const TailCols& tc, int64_t j) {
+  if (j < tc.nd) return sum_chunks(partials, nchunks, nrhs, k, (tc.nd + 1) & ~(int64_t)1, j);
+  const int r = tc.col_row[j];
+  return r >= 0 ? tc.col_val[j] * (k ? tc.v1 : tc.v0)[r] : 0.0;
+}
+
 __global__ void gemv_t_raw_kernel(int64_t n, int64_t n_pad, int nchunks, int nrhs,
                                   const double* __restrict__ partials, double* __restrict__ out0,
                                   double* __restrict__ out1) {
@@ -545,13 +556,13 @@ int k_gemv_t_raw(LaunchCtx& lc, int64_t n, int nchunks, int nrhs, double* out0, 
   return LPB_OK;
 }
 
-__global__ void resid_d_kernel(int64_t n, int64_t n_pad, int nchunks, double tau,
+__global__ void resid_d_kernel(int64_t n, TailCols tc, int nchunks, double tau,
                                const double* __restrict__ partials, const double* __restrict__ c,
                                const double* __restrict__ z, const double* __restrict__ x, double* __restrict__ rD,
                                double* __restrict__ red, int val_base) {
   double v[3] = {0.0, 0.0, 0.0};
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-    const double s = sum_chunks(partials, nchunks, 1, 0, n_pad, j);
+    const double s = at_dot(partials, nchunks, 1, 0, tc, j);
     const double cj = c[j], zj = z[j], xj = x[j];
     const double r = cj * tau - s - zj;  // feasible_point.rs:123 / residual.rs:24-26
     rD[j] = r;
@@ -563,16 +574,17 @@ __global__ void resid_d_kernel(int64_t n, int64_t n_pad, int nchunks, double tau
   block_reduce_store<3>(v, op, red, val_base);
 }
 int k_resid_d(LaunchCtx& lc, int64_t n, int nchunks, double tau, const double* c, const double* z, const double* x,
-              double* rD, int val_base, int* nblocks) {
+              double* rD, int val_base, int* nblocks, const TailCols* tail) {
   const int nb = vec_blocks(n);
-  resid_d_kernel<<<nb, kVecThreads, 0, lc.stream>>>(n, round_up(n, 2), nchunks, tau, lc.gemv_partials, c, z, x, rD,
+  const TailCols tc = tail ? *tail : TailCols{n, nullptr, nullptr, nullptr, nullptr};
+  resid_d_kernel<<<nb, kVecThreads, 0, lc.stream>>>(n, tc, nchunks, tau, lc.gemv_partials, c, z, x, rD,
                                                     lc.red_partials, val_base);
   LPB_LAUNCH_CHECK(lc);
   *nblocks = nb;
   return LPB_OK;
 }
 
-__global__ void sym_back_kernel(int64_t n, int64_t n_pad, int nchunks, int with_pq,
+__global__ void sym_back_kernel(int64_t n, TailCols tc, int nchunks, int with_pq,
                                 const double* __restrict__ partials, const double* __restrict__ dinv,
                                 const double* __restrict__ r1, const double* __restrict__ c, double* __restrict__ u,
                                 double* __restrict__ p, double* __restrict__ red, int val_base) {
@@ -580,12 +592,12 @@ __global__ void sym_back_kernel(int64_t n, int64_t n_pad, int nchunks, int with_
   const int nrhs = with_pq ? 2 : 1;
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
     const double dj = dinv[j], cj = c[j];
-    const double s0 = sum_chunks(partials, nchunks, nrhs, 0, n_pad, j);
+    const double s0 = at_dot(partials, nchunks, nrhs, 0, tc, j);
     const double uj = dj * (s0 - r1[j]);  // newton_equations.rs:223
     u[j] = uj;
     v[0] += cj * uj;
     if (with_pq) {
-      const double s1 = sum_chunks(partials, nchunks, nrhs, 1, n_pad, j);
+      const double s1 = at_dot(partials, nchunks, nrhs, 1, tc, j);
       const double pj = dj * (s1 - cj);
       p[j] = pj;
       v[1] += cj * pj;
@@ -596,9 +608,10 @@ __global__ void sym_back_kernel(int64_t n, int64_t n_pad, int nchunks, int with_
   block_reduce_store<3>(v, op, red, val_base);
 }
 int k_sym_back(LaunchCtx& lc, int64_t n, int nchunks, int with_pq, const double* dinv, const double* r1,
-               const double* c, double* u, double* p, int val_base, int* nblocks) {
+               const double* c, double* u, double* p, int val_base, int* nblocks, const TailCols* tail) {
   const int nb = vec_blocks(n);
-  sym_back_kernel<<<nb, kVecThreads, 0, lc.stream>>>(n, round_up(n, 2), nchunks, with_pq, lc.gemv_partials, dinv, r1,
+  const TailCols tc = tail ? *tail : TailCols{n, nullptr, nullptr, nullptr, nullptr};
+  sym_back_kernel<<<nb, kVecThreads, 0, lc.stream>>>(n, tc, nchunks, with_pq, lc.gemv_partials, dinv, r1,
                                                      c, u, p, lc.red_partials, val_base);
   LPB_LAUNCH_CHECK(lc);
   *nblocks = nb;
@@ -775,18 +788,81 @@ int k_col_structure(LaunchCtx& lc, const double* A, int64_t m, int64_t n, int64_
   return LPB_OK;
 }
 
-// M[r][r] += sq[r] * dinv[col[r]] for the rows that own a singleton column (col[r] >= 0).
+// M[r][r] += s_r^2 * dinv[col[r]] for the rows that own a singleton column (col[r] >= 0, value s_r).
 __global__ void diag_add_kernel(int64_t m, double* __restrict__ M, int64_t ldm, const int* __restrict__ col,
-                                const double* __restrict__ sq, const double* __restrict__ dinv) {
+                                const double* __restrict__ val, const double* __restrict__ dinv) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= m) return;
   const int j = col[r];
-  if (j >= 0) M[r * ldm + r] += sq[r] * dinv[j];
+  if (j >= 0) M[r * ldm + r] += (val[r] * val[r]) * dinv[j];
 }
-int k_diag_add(LaunchCtx& lc, int64_t m, double* M, int64_t ldm, const int* col, const double* sq,
+int k_diag_add(LaunchCtx& lc, int64_t m, double* M, int64_t ldm, const int* col, const double* val,
                const double* dinv) {
   if (m <= 0) return LPB_OK;
-  diag_add_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, lc.stream>>>(m, M, ldm, col, sq, dinv);
+  diag_add_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, lc.stream>>>(m, M, ldm, col, val, dinv);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+// The singleton columns' share of t_k = A (dinv? dinv * w_k : w_k):  t_k[r] += s_r * (dinv[j] *) w_k[j], j = col[r].
+__global__ void slack_add_kernel(int64_t m, const int* __restrict__ col, const double* __restrict__ val,
+                                 const double* __restrict__ dinv, const double* __restrict__ w0,
+                                 const double* __restrict__ w1, double* __restrict__ t0, double* __restrict__ t1,
+                                 int nrhs) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  const int j = col[r];
+  if (j < 0) return;
+  const double sd = dinv ? val[r] * dinv[j] : val[r];
+  t0[r] += sd * w0[j];
+  if (nrhs == 2) t1[r] += sd * w1[j];
+}
+int k_slack_add(LaunchCtx& lc, int64_t m, const int* col, const double* val, const double* dinv, const double* w0,
+                const double* w1, double* t0, double* t1, int nrhs) {
+  if (m <= 0) return LPB_OK;
+  slack_add_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, lc.stream>>>(m, col, val, dinv, w0, w1, t0, t1, nrhs);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
+// ------------------------------------------------------------------ lower-triangle pack / unpack (sharded contexts)
+// Only the lower triangle of M is ever read, so the all-reduce that assembles M from the ranks' partial
+// SYRKs moves the lower triangle alone: block row i (128 rows) contributes its columns [0, 128 (i + 1)),
+// stored contiguously at offset 128 * 128 * i (i + 1) / 2 with pitch 128 (i + 1).  Half the NVLink bytes for two
+// extra HBM passes over the triangle.
+constexpr int kTriBlk = 128;
+template <bool PACK>
+__global__ void __launch_bounds__(256)
+tri_pack_kernel(double* __restrict__ M, int64_t ldm, int64_t m, double* __restrict__ buf) {
+  const int64_t i = blockIdx.y;                       // block row
+  const int64_t r0 = i * kTriBlk;
+  const int64_t rows = (m - r0) < kTriBlk ? (m - r0) : kTriBlk;
+  int64_t width = (i + 1) * kTriBlk;
+  if (width > m) width = m;
+  const int64_t pitch = (i + 1) * kTriBlk;
+  double* dst = buf + (int64_t)kTriBlk * kTriBlk * (i * (i + 1) / 2);
+  const int64_t total = rows * width;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / width, cc = e - r * width;
+    if (PACK)
+      dst[r * pitch + cc] = M[(r0 + r) * ldm + cc];
+    else
+      M[(r0 + r) * ldm + cc] = dst[r * pitch + cc];
+  }
+}
+int64_t tri_packed_doubles(int64_t m) {
+  const int64_t T = ceil_div(m, kTriBlk);
+  return (int64_t)kTriBlk * kTriBlk * (T * (T + 1) / 2);
+}
+int k_tri_pack(LaunchCtx& lc, double* M, int64_t ldm, int64_t m, double* buf, bool pack) {
+  if (m <= 0) return LPB_OK;
+  const dim3 grid(64, (unsigned)ceil_div(m, kTriBlk));
+  if (pack) {
+    // rows beyond m / columns beyond min(width, m) of the last blocks are never written: keep them defined
+    tri_pack_kernel<true><<<grid, 256, 0, lc.stream>>>(M, ldm, m, buf);
+  } else {
+    tri_pack_kernel<false><<<grid, 256, 0, lc.stream>>>(M, ldm, m, buf);
+  }
   LPB_LAUNCH_CHECK(lc);
   return LPB_OK;
 }

@@ -103,6 +103,11 @@ def _worker(rank, world, port, q):
                 L = np.tril(sp.debug_read("M").reshape(m, ldm)[:, :m])
                 res = solver.solve_resident(sp)
             big[mode] = (L, res.x(), res.fun(), res.iteration())
+        with ShardedProblem(pb, rank, world, dist) as sp:   # all-reduce of the full square instead of the packed triangle
+            sp.set_option("packed_allreduce", 0)
+            assert lib.lpb_blind_start(sp.handle) == 0
+            assert lib.lpb_form_and_factor(sp.handle) == 0, _ffi.last_error()
+            big["square"] = np.tril(sp.debug_read("M").reshape(m, ldm)[:, :m])
         out["big"] = big
         q.put((rank, out))
         dist.barrier()
@@ -147,6 +152,9 @@ def test_two_gpu_column_sharded_solve_matches_oracle_and_one_gpu():
             assert abs(it - ref.iteration) <= 1
             assert np.abs(x - ref.x).max() < 1e-6
             assert abs(fun - ref.fun) <= 1e-8 * max(1.0, abs(ref.fun))
+    for rank in (0, 1):  # packed-triangle all-reduce vs the plain one: same M up to the order of the sums
+        Lsq = results[rank]["big"]["square"]
+        assert np.abs(Lsq - results[0]["big"][1][0]).max() <= 1e-12 * np.abs(Lsq).max()
     Lref = np.linalg.cholesky((lambda A: A @ A.T)(o.build_problem(*o.synthetic_lp(*BIG)).A))
     L = results[0]["big"][1][0]
     assert np.abs(L - Lref).max() <= 1e-10 * np.abs(Lref).max()

@@ -241,7 +241,7 @@ def test_slack_columns_are_folded_into_the_diagonal(m, n, seed):
     assert cols0 == n and cols1 == n - pb.n_slack()
     assert np.abs(L1 - L0).max() <= 1e-12 * np.abs(L0).max()
     assert res1.iteration() == res0.iteration()
-    assert np.abs(res1.x() - res0.x()).max() <= 1e-9
+    assert np.abs(res1.x() - res0.x()).max() <= 1e-7   # two roundings of the same iteration, stopped at tol = 1e-8
     assert abs(res1.fun() - res0.fun()) <= 1e-10 * max(1.0, abs(res0.fun()))
 
 
