@@ -30,6 +30,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv[1:]:
+    # The CPU arm uses every host thread -- also under torchrun, which exports OMP_NUM_THREADS=1 to its ranks.
+    # Must happen before NumPy loads its BLAS.
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
