@@ -1136,6 +1136,70 @@ static int ensure_chol_ws(LaunchCtx& lc, int64_t m) {
 
 static int k_potrf_dist(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm);
 
+// Single-GPU factorisation with look-ahead.  The serial part of a panel is potf2_inv: one CTA, ~40 us, with
+// 147 SMs idle.  Here the trailing update of panel k is split: its first block column (the one panel k+1
+// lives in) is updated first, then potf2_inv(k+1) runs on a second, high-priority stream while the update of
+// the remaining columns keeps 147 SMs busy on the main stream; the TRSM of panel k+1 follows on the main
+// stream once both are done.  Same kernels, same order of updates per tile as the sequential loop, so the
+// factor is bit-identical to it (option "potrf_lookahead" = 0 selects the sequential loop).
+static int k_potrf_lookahead(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm) {
+  if (!lc.side_stream) {
+    int lo = 0, hi = 0;
+    LPB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    LPB_CUDA(cudaStreamCreateWithPriority(&lc.side_stream, cudaStreamNonBlocking, hi));
+    for (int e = 0; e < 2; ++e) {
+      LPB_CUDA(cudaEventCreateWithFlags(&lc.ev_col[e], cudaEventDisableTiming));
+      LPB_CUDA(cudaEventCreateWithFlags(&lc.ev_pan[e], cudaEventDisableTiming));
+    }
+  }
+  const int T = (int)ceil_div(m, NB);
+  lc.linv_full = false;
+  auto nb_of = [&](int k) { return (int)((m - (int64_t)k * NB) < NB ? (m - (int64_t)k * NB) : NB); };
+  auto potf2 = [&](int k, cudaStream_t st) -> int {
+    potf2_inv_kernel<<<1, dim3(32, 16), kPotf2InvSmem, st>>>(Mat, ldm, k * NB, nb_of(k), lc.info_dev,
+                                                             lc.chol_ws + (int64_t)k * NB * NB, 0);
+    LPB_KCHECK(lc);
+    return LPB_OK;
+  };
+  auto trsm = [&](int k) -> int {
+    const int64_t rem = m - (int64_t)k * NB - nb_of(k);
+    if (rem <= 0) return LPB_OK;
+    trsm_dmma_blocked_kernel<<<(unsigned)ceil_div(rem, TBR), 256, kTrsmDmmaSmem, lc.stream>>>(
+        Mat, ldm, k * NB, (int)m, lc.chol_ws + (int64_t)k * NB * NB);
+    LPB_KCHECK(lc);
+    return LPB_OK;
+  };
+  LPB_TRY(potf2(0, lc.stream));
+  LPB_TRY(trsm(0));
+  const int saved_cap = lc.update_grid_cap;
+  int rc = LPB_OK;
+  for (int k = 0; k + 1 < T && rc == LPB_OK; ++k) {
+    const int64_t k0 = (int64_t)k * NB;
+    cudaEvent_t ec = lc.ev_col[k & 1], ep = lc.ev_pan[k & 1];
+    // (1) the block column of panel k+1, then hand it to the side stream
+    rc = k_trailing_update_part(lc, m, Mat, ldm, k0, NB, k + 1, 1, 1, 0);
+    if (rc != LPB_OK) break;
+    LPB_CUDA(cudaEventRecord(ec, lc.stream));
+    LPB_CUDA(cudaStreamWaitEvent(lc.side_stream, ec, 0));
+    rc = potf2(k + 1, lc.side_stream);
+    if (rc != LPB_OK) break;
+    LPB_CUDA(cudaEventRecord(ep, lc.side_stream));
+    // (2) the rest of update k on all SMs but one
+    lc.update_grid_cap = kNumSMs - 1;
+    rc = k_trailing_update_part(lc, m, Mat, ldm, k0, NB, k + 2, 0, 1, 0);
+    lc.update_grid_cap = saved_cap;
+    if (rc != LPB_OK) break;
+    // (3) panel k+1 joins the main stream
+    LPB_CUDA(cudaStreamWaitEvent(lc.stream, ep, 0));
+    rc = trsm(k + 1);
+  }
+  lc.update_grid_cap = saved_cap;
+  LPB_TRY(rc);
+  lc.linv_valid_m = m;
+  lc.linv_mat = Mat;
+  return LPB_OK;
+}
+
 int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
   LPB_TRY(configure_once());
   LPB_TRY(ensure_chol_ws(lc, m));
@@ -1143,6 +1207,9 @@ int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
   if (lc.world > 1 && lc.nccl_comm && lc.potrf_dist && syrk_impl == 0 && lc.trsm_impl == 0 && lc.update_impl == 0 &&
       m > NB && !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mat) & 15))
     return k_potrf_dist(lc, m, Mat, ldm);
+  if (lc.potrf_lookahead && syrk_impl == 0 && lc.trsm_impl == 0 && lc.update_impl == 0 && lc.solve_impl != 1 &&
+      !lc.sync_each_launch && m > 2 * NB && !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mat) & 15))
+    return k_potrf_lookahead(lc, m, Mat, ldm);
   const int full_inverse = (lc.trsm_impl == 2 || lc.solve_impl == 1) ? 1 : 0;
   lc.linv_full = full_inverse != 0;
   for (int64_t k0 = 0; k0 < m; k0 += NB) {

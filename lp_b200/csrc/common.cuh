@@ -64,6 +64,11 @@ struct LaunchCtx {
   int potrf_dist = 1;              // 0 = every rank factors the whole of M itself (replicated)
   double* panel_buf = nullptr;     // packed panel + inverted diagonal block, the broadcast payload
   int64_t panel_buf_cap = 0;       // in doubles
+  // single-GPU look-ahead of k_potrf: potf2 of panel k+1 runs on `side_stream` beside the trailing update of panel k
+  int potrf_lookahead = 1;         // 0 = strictly sequential panels on `stream`
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_col[2] = {nullptr, nullptr}, ev_pan[2] = {nullptr, nullptr};
+  int update_grid_cap = 0;         // > 0: CTAs of the trailing update (leaves SMs free for the side stream)
   int* info_dev = nullptr;         // potrf info flag
   int* info_host = nullptr;        // pinned
 };

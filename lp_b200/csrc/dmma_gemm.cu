@@ -427,7 +427,8 @@ int launch_dmma(LaunchCtx& lc, const CUtensorMap& tmA, const CUtensorMap& tmB, d
   const int ntiles = (MODE == MODE_TRSM || shape == SHAPE_COL) ? ntr
                      : (shape == SHAPE_OWNED ? own.count() : ntr * (ntr + 1) / 2);
   if (ntiles <= 0) return LPB_OK;
-  const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
+  int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
+  if (MODE == MODE_UPDATE && lc.update_grid_cap > 0 && grid > lc.update_grid_cap) grid = lc.update_grid_cap;
   kern<<<grid, kThreads, kSmemAlloc, lc.stream>>>(tmA, tmB, C, ldc, m_total, tile0, ntr, k_begin, nkb, col_origin, shape,
                                                   own);
   lc.launches++;

@@ -634,6 +634,14 @@ void ctx_free(lpb_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   if (c->lc.chol_ws) cudaFree(c->lc.chol_ws);
   if (c->lc.panel_buf) cudaFree(c->lc.panel_buf);
+  if (c->lc.side_stream) {
+    cudaStreamSynchronize(c->lc.side_stream);
+    for (int e = 0; e < 2; ++e) {
+      if (c->lc.ev_col[e]) cudaEventDestroy(c->lc.ev_col[e]);
+      if (c->lc.ev_pan[e]) cudaEventDestroy(c->lc.ev_pan[e]);
+    }
+    cudaStreamDestroy(c->lc.side_stream);
+  }
   if (c->lc.red_host) cudaFreeHost(c->lc.red_host);
   if (c->lc.info_host) cudaFreeHost(c->lc.info_host);
   if (c->chk_host) cudaFreeHost(c->chk_host);
@@ -1208,6 +1216,10 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
   if (k == "structure") {  // 0: contract over every column of A (no slack-column shortcut)
     c->use_structure = value != 0;
     return c->has_problem ? analyze_structure(c) : LPB_OK;
+  }
+  if (k == "potrf_lookahead") {  // 0: strictly sequential panels (single-GPU factorisation)
+    c->lc.potrf_lookahead = value != 0;
+    return LPB_OK;
   }
   if (k == "packed_allreduce") {
     c->packed_allreduce = value != 0;

@@ -147,3 +147,25 @@ def test_potrf_then_fused_potrs(m, nrhs, solve_impl, grid_cap):
     assert np.abs(X - ref).max() / np.abs(ref).max() < 1e-9
     for k in range(nrhs):
         assert np.linalg.norm(M @ X[k] - rhs[k]) / (np.linalg.norm(M) * np.linalg.norm(X[k])) < 1e-13
+
+
+@pytest.mark.parametrize("m", [257, 384, 1000, 1537, 4096])
+def test_potrf_lookahead_is_bit_identical_to_the_sequential_loop(m):
+    """K2 with look-ahead (potf2 of panel k+1 on a second stream beside the trailing update of panel k) applies
+    the same updates to every tile in the same order as the sequential loop: identical bits, twice in a row."""
+    rng = np.random.default_rng(5 * m)
+    B = rng.standard_normal((m, m + 8))
+    M = B @ B.T + 0.1 * np.eye(m)
+    Mp, ldm = pad_cols(M)
+    outs = []
+    info = C.c_int32(-1)
+    with BareCtx(m, m) as ctx:
+        for look in (1, 0, 1):
+            ctx.set("potrf_lookahead", look)
+            dM = to_dev(Mp)
+            ok(ctx.lib.lpb_k_potrf(ctx.h, m, dM.data_ptr(), ldm, C.byref(info)))
+            assert info.value == 0
+            outs.append(np.tril(dM.cpu().numpy()[:, :m]))
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_array_equal(outs[0], outs[2])
+    assert np.linalg.norm(outs[0] @ outs[0].T - M) / np.linalg.norm(M) < 1e-13
