@@ -99,44 +99,57 @@ def _raise_for(code: int, x=None):
 
 
 # --------------------------------------------------------------------------- host buffers
+class _PinnedAlloc:
+    """Owner of one page-locked host allocation (lpb_host_alloc); freed when the last array over it goes away."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        if getattr(self, "ptr", None) is not None:
+            try:
+                _ffi.load().lpb_host_free(self.ptr)
+            except Exception:
+                pass
+            self.ptr = None
+
+
+class _PinnedArray(np.ndarray):
+    """ndarray over a pinned host allocation.  The keep-alive hangs on the ctypes buffer at the bottom of the
+    `.base` chain, so EVERY view of the memory -- slices, reshapes, `.view(np.ndarray)` -- keeps the allocation
+    alive; `_lpb_host` only makes the owner visible for debugging."""
+    _lpb_host = None
+
+
 class _HostBuffer:
     """A float64 array in pinned host memory when a CUDA device is visible (uploads at PCIe rate),
-    else ordinary NumPy memory (building a Problem needs no GPU, exactly like the reference)."""
+    else ordinary NumPy memory (building a Problem needs no GPU, exactly like the reference).
+    `array` and every view derived from it own a reference to the allocation: a view that outlives the
+    _HostBuffer (e.g. `A = build().A()` returned from a helper) never points at freed memory."""
 
     def __init__(self, shape):
         self.shape = tuple(int(s) for s in shape)
         nbytes = int(np.prod(self.shape)) * 8
-        self._ptr = None
         lib = _ffi.load()
         p = C.c_void_p()
         if nbytes > 0 and lib.lpb_device_count() > 0 and lib.lpb_host_alloc(C.byref(p), nbytes) == _ffi.LPB_OK:
-            self._ptr = p
             buf = (C.c_double * (nbytes // 8)).from_address(p.value)
-            self.array = np.frombuffer(buf, dtype=np.float64).reshape(self.shape)
+            buf._lpb_alloc = _PinnedAlloc(p)  # the ctypes object is the base of every array view below
+            arr = np.frombuffer(buf, dtype=np.float64).reshape(self.shape).view(_PinnedArray)
+            arr._lpb_host = buf._lpb_alloc
+            self.array = arr
         else:
             self.array = np.zeros(self.shape, dtype=np.float64)
 
-    def __del__(self):
-        if getattr(self, "_ptr", None) is not None:
-            try:
-                _ffi.load().lpb_host_free(self._ptr)
-            except Exception:
-                pass
-            self._ptr = None
-
-
-class _PinnedArray(np.ndarray):
-    """ndarray view of a pinned host allocation; keeps the allocation alive as long as any view of it is."""
-    _lpb_host = None
+    @property
+    def pinned(self) -> bool:
+        return isinstance(self.array, _PinnedArray)
 
 
 def pinned_empty(shape) -> np.ndarray:
     """A float64 array in pinned (page-locked) host memory when a CUDA device is visible -- inputs built in
     it upload at PCIe rate (`solve_batched`, `Problem` buffers) -- else an ordinary NumPy array."""
-    buf = _HostBuffer(shape)
-    out = buf.array.view(_PinnedArray)
-    out._lpb_host = buf
-    return out
+    return _HostBuffer(shape).array
 
 
 def _as_f64(a, ndim):
@@ -479,7 +492,7 @@ class ShardedProblem(ResidentProblem):
         self.rank, self.world, self._dist = rank, world, dist
         self.shards = shard_columns(n_global, world, self.n_slack)
         self.col0, self.n = self.shards[rank]
-        if self.n <= 0:
+        if any(nl <= 0 for _, nl in self.shards):  # the same verdict on every rank, before any collective
             raise ValueError("more ranks than column blocks")
         self.last_iterations = 0
         self._problem = problem
@@ -540,7 +553,7 @@ class SyntheticShardedProblem(ShardedProblem):
         self.rank, self.world, self._dist = rank, world, dist
         self.shards = shard_columns(self.n_global, world, self.n_slack)
         self.col0, self.n = self.shards[rank]
-        if self.n <= 0:
+        if any(nl <= 0 for _, nl in self.shards):
             raise ValueError("more ranks than column blocks")
         self.last_iterations = 0
         self._problem = None

@@ -81,6 +81,60 @@ constexpr int NSB = NB / SB;  // 8
 constexpr int XDP = SB + 1;   // pitch of the 16 x 16 inverse of the current diagonal sub-block
 constexpr int TWP = 9;        // pitch of the per-warp 16 x 8 scratch of the block-inverse step
 
+// Off-diagonal 16 x 16 blocks of X = inv(L_kk) from L_kk (lower triangle of S) and the inverted diagonal sub-blocks
+// (X^T in the strictly upper triangle of S, its diagonal in rdiag): one block diagonal at a time,
+//     X_ij = -X_ii (sum_{k=j}^{i-1} L_ik X_kj),
+// block (i, j) by a pair of warps; 512 threads, ends with a CTA barrier.
+__device__ __forceinline__ void complete_block_inverse(double* S, const double* rdiag, double* Tw, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const int b = warp >> 1, h = warp & 1;
+  const int ii = lane & 15, cg = lane >> 4;
+  double* tw = Tw + warp * SB * TWP;
+  for (int d = 1; d < NSB; ++d) {
+    if (b < NSB - d) {
+      const int j = b, i = b + d;
+      const int ccb = 8 * h + 4 * cg;  // first of this lane's 4 columns within block column j
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      const double* lrow = S + (i * SB + ii) * LDS;
+      // k == j: X_jj (lower triangular; transposed in the upper triangle, diagonal in rdiag)
+#pragma unroll
+      for (int l = 0; l < SB; ++l) {
+        const double lv = lrow[j * SB + l];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int cc = ccb + e;
+          const double up = S[(j * SB + cc) * LDS + j * SB + l];
+          const double xv = (l > cc) ? up : ((l == cc) ? rdiag[j * SB + cc] : 0.0);
+          acc[e] += lv * xv;
+        }
+      }
+      for (int k = j + 1; k < i; ++k) {
+#pragma unroll
+        for (int l = 0; l < SB; ++l) {
+          const double lv = lrow[k * SB + l];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[e] += lv * S[(j * SB + ccb + e) * LDS + k * SB + l];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) tw[ii * TWP + 4 * cg + e] = acc[e];
+      __syncwarp();
+      // X_ij = -X_ii T
+      double o[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int l = 0; l < SB; ++l) {
+        const double up = S[(i * SB + l) * LDS + i * SB + ii];
+        const double xv = (l < ii) ? up : ((l == ii) ? rdiag[i * SB + ii] : 0.0);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] += xv * tw[l * TWP + 4 * cg + e];
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) S[(j * SB + ccb + e) * LDS + i * SB + ii] = -o[e];
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(512)
 potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __restrict__ info,
                  double* __restrict__ Linv, int full_inverse) {
@@ -221,57 +275,10 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
     if (r < nb && c <= r) blk[(int64_t)r * ldm + c] = S[r * LDS + c];
   }
 
-  // ---- off-diagonal blocks of X, one block diagonal at a time; block (i, j) by a pair of warps.  Only the
-  // full-inverse consumers need them (trsm_impl 2, solve_impl 1); the default TRSM and the pipelined solve
-  // use the 16 x 16 diagonal inverses alone, so this stage is normally skipped (the blocks stay zero).
-  if (full_inverse) {
-    const int b = warp >> 1, h = warp & 1;
-    const int ii = lane & 15, cg = lane >> 4;
-    double* tw = Tw + warp * SB * TWP;
-    for (int d = 1; d < NSB; ++d) {
-      if (b < NSB - d) {
-        const int j = b, i = b + d;
-        const int ccb = 8 * h + 4 * cg;  // first of this lane's 4 columns within block column j
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        const double* lrow = S + (i * SB + ii) * LDS;
-        // k == j: X_jj (lower triangular; transposed in the upper triangle, diagonal in rdiag)
-#pragma unroll
-        for (int l = 0; l < SB; ++l) {
-          const double lv = lrow[j * SB + l];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int cc = ccb + e;
-            const double up = S[(j * SB + cc) * LDS + j * SB + l];
-            const double xv = (l > cc) ? up : ((l == cc) ? rdiag[j * SB + cc] : 0.0);
-            acc[e] += lv * xv;
-          }
-        }
-        for (int k = j + 1; k < i; ++k) {
-#pragma unroll
-          for (int l = 0; l < SB; ++l) {
-            const double lv = lrow[k * SB + l];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[e] += lv * S[(j * SB + ccb + e) * LDS + k * SB + l];
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) tw[ii * TWP + 4 * cg + e] = acc[e];
-        __syncwarp();
-        // X_ij = -X_ii T
-        double o[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int l = 0; l < SB; ++l) {
-          const double up = S[(i * SB + l) * LDS + i * SB + ii];
-          const double xv = (l < ii) ? up : ((l == ii) ? rdiag[i * SB + ii] : 0.0);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] += xv * tw[l * TWP + 4 * cg + e];
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) S[(j * SB + ccb + e) * LDS + i * SB + ii] = -o[e];
-      }
-      __syncthreads();
-    }
-  }
+  // ---- off-diagonal blocks of X: only the full-inverse consumers need them (trsm_impl 2); the default TRSM uses
+  // the 16 x 16 diagonal inverses alone and the solves complete the inverses off the critical path
+  // (linv_complete_kernel), so this stage is normally skipped (the blocks stay zero).
+  if (full_inverse) complete_block_inverse(S, rdiag, Tw, tid);
   for (int idx = tid; idx < NB * NB; idx += 512) {
     const int i = idx >> 7, c = idx & (NB - 1);
     double v = 0.0;
@@ -799,16 +806,33 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// Bounded: a lost flag traps after ~2 s instead of hanging the GPU.
+// Bounded without trapping (a trap leaves a sticky error that kills every context of the process): after ~20 s
+// of wall-clock polling the waiter raises the context's fault word and carries on; every other poller sees the
+// word and leaves too; the host reports LPB_ERR_CUDA at its next scalar fetch.
 // `relaxed` pollers (blocks that are not next in the chain) back off so that up to ~1000 warps
 // spinning on one L2 line do not delay the release store they are waiting for.
-__device__ __forceinline__ void wait_flag(const int* flag, int epoch, bool relaxed = false) {
-  if (ld_acquire_gpu(flag) == epoch) return;
-  const long long t0 = clock64();
+__device__ __forceinline__ unsigned long long wall_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __noinline__ void wait_flag_slow(const int* flag, int epoch, bool relaxed, unsigned long long* fault) {
+  const unsigned long long t0 = wall_ns();
+  unsigned spins = 0;
   while (ld_acquire_gpu(flag) != epoch) {
     if (relaxed) __nanosleep(256);
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if ((++spins & 255u) == 0) {
+      if (*reinterpret_cast<volatile unsigned long long*>(fault) != 0ull) return;
+      if (wall_ns() - t0 > 20000000000ull) {
+        atomicExch(fault, 1ull);
+        return;
+      }
+    }
   }
+}
+__device__ __forceinline__ void wait_flag(const int* flag, int epoch, unsigned long long* fault, bool relaxed = false) {
+  if (ld_acquire_gpu(flag) == epoch) return;
+  wait_flag_slow(flag, epoch, relaxed, fault);
 }
 // Per-lane partials of 16 rows -> total of row (lane >> 1) in every lane (pairs hold copies).
 __device__ __forceinline__ double fold16(double (&v)[16], int lane) {
@@ -918,7 +942,8 @@ __device__ __forceinline__ void solve_diag_bwd(const double* sL, const double* s
 template <int NRHS>
 __global__ void __launch_bounds__(kSolveThreads, 1)
 solve_pipelined_kernel(const double* __restrict__ L, int64_t ldm, const double* __restrict__ Linv_all, int64_t m,
-                       int nblk, double* B, double* Y, int64_t ldy, int* flags_f, int* flags_b, int epoch) {
+                       int nblk, double* B, double* Y, int64_t ldy, int* flags_f, int* flags_b, int epoch,
+                       unsigned long long* fault) {
   extern __shared__ __align__(16) double sm[];
   double* sL = sm;                        // 128 x LDP: L_jj
   double* sX = sL + NB * LDP;             // 8 x 16 x XDP: inv of its 16 x 16 diagonal sub-blocks
@@ -955,7 +980,7 @@ solve_pipelined_kernel(const double* __restrict__ L, int64_t ldm, const double* 
             lb[i] = __ldg(p + 1);
           }
         }
-        if (half == 0) wait_flag(flags_f + k, epoch, k + 1 < j);
+        if (half == 0) wait_flag(flags_f + k, epoch, fault, k + 1 < j);
         double2 wa[NRHS], wb[NRHS];
 #pragma unroll
         for (int q = 0; q < NRHS; ++q) {
@@ -984,10 +1009,7 @@ solve_pipelined_kernel(const double* __restrict__ L, int64_t ldm, const double* 
       if (rr < nbj) Y[(int64_t)q * ldy + r0 + rr] = sw[q * NB + rr];
     }
     __syncthreads();  // all of w_j written
-    if (tid == 0) {
-      __threadfence();
-      st_release_gpu(flags_f + j, epoch);
-    }
+    if (tid == 0) st_release_gpu(flags_f + j, epoch);  // release is cumulative over the barrier: no extra fence
   }
 
   // ============================================================ backward: L^T x = w
@@ -1015,7 +1037,7 @@ solve_pipelined_kernel(const double* __restrict__ L, int64_t ldm, const double* 
             lb[i] = __ldg(p + 1);
           }
         }
-        if (half == 0) wait_flag(flags_b + k, epoch, k - 1 > j);
+        if (half == 0) wait_flag(flags_b + k, epoch, fault, k - 1 > j);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int64_t r = rw + half * 8 + i;
@@ -1036,7 +1058,7 @@ solve_pipelined_kernel(const double* __restrict__ L, int64_t ldm, const double* 
       *reinterpret_cast<double2*>(sred + (warp * 2 + q) * NB + c4 + 2) = make_double2(acc[q][2], acc[q][3]);
     __syncthreads();
     if (tid < NRHS * NB) {  // c = w_j - sum over the 8 warps
-      wait_flag(flags_f + j, epoch);  // w_j may come from another CTA (forward owner j mod G)
+      wait_flag(flags_f + j, epoch, fault);  // w_j may come from another CTA (forward owner j mod G)
       const int q = tid >> 7, c = tid & (NB - 1);
       double sum = 0.0;
 #pragma unroll
@@ -1050,9 +1072,285 @@ solve_pipelined_kernel(const double* __restrict__ L, int64_t ldm, const double* 
       if (c < nbj) B[(int64_t)q * m + j0 + c] = sw[q * NB + c];
     }
     __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      st_release_gpu(flags_b + j, epoch);
+    if (tid == 0) st_release_gpu(flags_b + j, epoch);
+  }
+}
+
+// ------------------------------------------------------------------ K3 v4: full block inverses + tagged hand-off
+// linv_complete_kernel: one CTA per diagonal block, AFTER the factorisation (off its critical path, all blocks in
+// parallel): completes X_j = inv(L_jj) from L_jj and the inverted 16 x 16 diagonal sub-blocks that potf2_inv left
+// in Linv (dense 128 x 128 per block, zero above the diagonal and beyond a ragged last block).
+constexpr size_t kLinvCompleteSmem = (size_t)(NB * LDS + NB + 16 * SB * TWP) * sizeof(double);
+
+__global__ void __launch_bounds__(512)
+linv_complete_kernel(const double* __restrict__ Mat, int64_t ldm, int64_t m, double* __restrict__ Linv_all) {
+  extern __shared__ double S[];   // NB * LDS: L_jj below / on the diagonal, X^T above
+  double* rdiag = S + NB * LDS;   // diagonal of X
+  double* Tw = rdiag + NB;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int64_t j0 = (int64_t)blockIdx.x * NB;
+  const int nb = (int)((m - j0) < NB ? (m - j0) : NB);
+  double* Xj = Linv_all + (int64_t)blockIdx.x * NB * NB;
+  const double* blk = Mat + j0 * ldm + j0;
+  for (int idx = tid; idx < NB * NB; idx += 512) {
+    const int r = idx >> 7, c = idx & (NB - 1);
+    if (c <= r) {
+      S[r * LDS + c] = (r < nb) ? blk[(int64_t)r * ldm + c] : (r == c ? 1.0 : 0.0);  // identity padding
+      const bool same_sub = (r >> 4) == (c >> 4);
+      const double xv = (r < nb) ? (same_sub ? Xj[idx] : 0.0) : (r == c ? 1.0 : 0.0);
+      if (r == c) rdiag[r] = xv;
+      else S[c * LDS + r] = xv;   // X^T above the diagonal; off-diagonal sub-blocks start at zero
+    }
+  }
+  __syncthreads();
+  complete_block_inverse(S, rdiag, Tw, tid);
+  for (int idx = tid; idx < NB * NB; idx += 512) {
+    const int i = idx >> 7, c = idx & (NB - 1);
+    double v = 0.0;
+    if (i < nb && c <= i) v = (c == i) ? rdiag[i] : S[c * LDS + i];
+    Xj[idx] = v;
+  }
+}
+
+// solve_ll_kernel: L L^T X = B for 1 or 2 right-hand sides in ONE cooperative launch, like solve_pipelined_kernel
+// (block row j owned by CTA j mod grid, every off-chain block product consumed as soon as its input exists), with
+// the serial chain  "w_{j-1} visible -> w_j visible"  cut to one L2 store + one L2 load + two 128 x 128 GEMVs:
+//   * hand-off without flags or fences: every solution entry travels as a 16-byte word {lo, tag, hi, tag}
+//     (tag = launch epoch) written with one st.volatile.v4 and polled with ld.volatile.v4 -- the LL scheme of
+//     NCCL: it only needs 8-byte store atomicity, and data + validity arrive in the same transaction;
+//   * w_j = X_j c_j with the FULL inverse X_j = inv(L_jj) staged in shared memory (one GEMV, two threads per
+//     row) instead of 8 dependent sub-block steps with two CTA barriers each;
+//   * the L block of the next product is in registers BEFORE its w is polled, so the chain never waits on HBM.
+// A lost hand-off does not hang or trap: after ~20 s of polling the waiter raises the context's fault word, every
+// other poller sees it and leaves, and the host reports LPB_ERR_CUDA at its next scalar fetch.
+struct __align__(16) Tagged {
+  uint32_t lo, tag0, hi, tag1;
+};
+__device__ __forceinline__ void st_tagged(Tagged* p, double v, uint32_t tag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((uint32_t)__double2loint(v)), "r"(tag),
+               "r"((uint32_t)__double2hiint(v)), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ bool ld_tagged_try(const Tagged* p, uint32_t tag, double* v) {
+  uint32_t a, b, c, d;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+  *v = __hiloint2double((int)c, (int)a);
+  return b == tag && d == tag;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __noinline__ double ld_tagged_slow(const Tagged* p, uint32_t tag, unsigned long long* fault, bool relaxed) {
+  double v = 0.0;
+  const unsigned long long t0 = global_ns();
+  unsigned spins = 0;
+  while (!ld_tagged_try(p, tag, &v)) {
+    if (relaxed) __nanosleep(200);
+    if ((++spins & 255u) == 0) {
+      if (*reinterpret_cast<volatile unsigned long long*>(fault) != 0ull) break;
+      if (global_ns() - t0 > 20000000000ull) {
+        atomicExch(fault, 1ull);
+        break;
+      }
+    }
+  }
+  return v;
+}
+__device__ __forceinline__ double ld_tagged(const Tagged* p, uint32_t tag, unsigned long long* fault, bool relaxed) {
+  double v;
+  if (ld_tagged_try(p, tag, &v)) return v;
+  return ld_tagged_slow(p, tag, fault, relaxed);
+}
+
+constexpr int XP = NB + 2;  // 130 = 2 mod 16: two threads per row (even / odd columns) read X_j conflict-free
+constexpr size_t kSolveLLSmem = (size_t)(NB * XP + 2 * NB + 8 * 2 * NB) * sizeof(double);
+
+// Stage X_j (TRANS: its transpose) into shared memory, pitch XP, zero above the diagonal.
+template <bool TRANS>
+__device__ __forceinline__ void stage_inverse(const double* __restrict__ Xj, double* sX, int tid) {
+  for (int idx = tid; idx < NB * NB / 2; idx += kSolveThreads) {
+    const int i = idx >> 6, c = (idx & 63) * 2;
+    const double2 v = __ldg(reinterpret_cast<const double2*>(Xj + i * NB + c));
+    if (TRANS) {
+      sX[c * XP + i] = v.x;
+      sX[(c + 1) * XP + i] = v.y;
+    } else {
+      sX[i * XP + c] = v.x;
+      sX[i * XP + c + 1] = v.y;
+    }
+  }
+}
+
+// y = T c for the staged 128 x 128 matrix T (X_j or X_j^T): thread (row = tid >> 1, h = tid & 1) takes the columns
+// = h mod 2; four independent chains per right-hand side; the two halves meet in one shuffle.
+template <int NRHS>
+__device__ __forceinline__ void block_gemv(const double* sX, const double* sc, int tid, double (&out)[NRHS]) {
+  const int r = tid >> 1, h = tid & 1;
+  const double* xr = sX + r * XP + h;
+  double s[NRHS][4];
+#pragma unroll
+  for (int q = 0; q < NRHS; ++q) s[q][0] = s[q][1] = s[q][2] = s[q][3] = 0.0;
+#pragma unroll 4
+  for (int i = 0; i < NB / 2; i += 4) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const double xv = xr[2 * (i + e)];
+#pragma unroll
+      for (int q = 0; q < NRHS; ++q) s[q][e] = fma(xv, sc[q * NB + 2 * (i + e) + h], s[q][e]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NRHS; ++q) {
+    const double t = (s[q][0] + s[q][1]) + (s[q][2] + s[q][3]);
+    out[q] = t + __shfl_xor_sync(0xffffffffu, t, 1);
+  }
+}
+
+template <int NRHS>
+__global__ void __launch_bounds__(kSolveThreads, 1)
+solve_ll_kernel(const double* __restrict__ L, int64_t ldm, const double* __restrict__ Xall, int64_t m, int nblk,
+                double* B, Tagged* Wt, Tagged* Xt, uint32_t epoch, unsigned long long* fault) {
+  extern __shared__ __align__(16) double sm[];
+  double* sX = sm;                 // 128 x XP: X_j (forward) / X_j^T (backward)
+  double* sc = sX + NB * XP;       // [2][128] right-hand side of the current block
+  double* sred = sc + 2 * NB;      // [8 warps][2][128] backward cross-warp fold
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c4 = 4 * lane;         // this lane's 4 columns inside a 128-wide block
+  const unsigned full = 0xffffffffu;
+
+  // ============================================================ forward: L w = b
+  for (int j = blockIdx.x; j < nblk; j += gridDim.x) {
+    const int64_t r0 = (int64_t)j * NB;
+    const int nbj = (int)((m - r0) < NB ? (m - r0) : NB);
+    __syncthreads();  // the previous block row is done with sX / sc
+    stage_inverse<false>(Xall + (int64_t)j * NB * NB, sX, tid);
+    double acc[NRHS][16];
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[q][i] = 0.0;
+    const int64_t rw = r0 + warp * 16;  // first row of this warp
+    double2 la[16], lb[16];
+    auto load_block = [&](int k) {
+      const double* base = L + (int64_t)k * NB + c4;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int64_t r = rw + i;
+        la[i] = lb[i] = make_double2(0.0, 0.0);
+        if (r < m) {
+          const double2* p = reinterpret_cast<const double2*>(base + r * ldm);
+          la[i] = __ldg(p);
+          lb[i] = __ldg(p + 1);
+        }
+      }
+    };
+    if (j > 0) load_block(0);
+    for (int k = 0; k < j; ++k) {
+      const bool relaxed = k + 1 < j;
+      const Tagged* wk = Wt + (int64_t)k * NRHS * NB;
+      // one sentinel poll per warp keeps the L2 polling traffic of the ~1000 waiting warps small
+      if (lane == 0) (void)ld_tagged(wk, epoch, fault, relaxed);
+      __syncwarp();
+      double w[NRHS][4];
+#pragma unroll
+      for (int q = 0; q < NRHS; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[q][e] = ld_tagged(wk + q * NB + c4 + e, epoch, fault, false);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q)
+          acc[q][i] += la[i].x * w[q][0] + la[i].y * w[q][1] + lb[i].x * w[q][2] + lb[i].y * w[q][3];
+      if (k + 1 < j) load_block(k + 1);  // in registers before w_{k+1} is polled
+    }
+    // fold across lanes; c = b - sum
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q) {
+      const double tot = fold16(acc[q], lane);
+      const int rr = warp * 16 + (lane >> 1);
+      if ((lane & 1) == 0) sc[q * NB + rr] = (rr < nbj) ? B[(int64_t)q * m + r0 + rr] - tot : 0.0;
+    }
+    __syncthreads();  // c_j and X_j are in shared memory
+    double wj[NRHS];
+    block_gemv<NRHS>(sX, sc, tid, wj);
+    if ((tid & 1) == 0) {
+#pragma unroll
+      for (int q = 0; q < NRHS; ++q) st_tagged(Wt + ((int64_t)j * NRHS + q) * NB + (tid >> 1), wj[q], epoch);
+    }
+  }
+
+  // ============================================================ backward: L^T x = w
+  for (int j = nblk - 1 - blockIdx.x; j >= 0; j -= gridDim.x) {
+    const int64_t j0 = (int64_t)j * NB;
+    const int nbj = (int)((m - j0) < NB ? (m - j0) : NB);
+    __syncthreads();  // previous users of sX / sc / sred are done
+    stage_inverse<true>(Xall + (int64_t)j * NB * NB, sX, tid);
+    double acc[NRHS][4];
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
+    double2 la[16], lb[16];
+    auto load_block = [&](int k) {
+      const double* base = L + j0 + c4;
+      const int64_t rw = (int64_t)k * NB + warp * 16;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int64_t r = rw + i;
+        la[i] = lb[i] = make_double2(0.0, 0.0);
+        if (r < m) {
+          const double2* p = reinterpret_cast<const double2*>(base + r * ldm);
+          la[i] = __ldg(p);
+          lb[i] = __ldg(p + 1);
+        }
+      }
+    };
+    if (j + 1 < nblk) load_block(nblk - 1);
+    for (int k = nblk - 1; k > j; --k) {
+      const bool relaxed = k - 1 > j;
+      // lane (i = lane & 15, q = lane >> 4) fetches x_k[16 warp + i] of right-hand side q; shuffles hand it round
+      const int qi = (NRHS == 2) ? (lane >> 4) : 0;
+      const Tagged* xk = Xt + ((int64_t)k * NRHS + qi) * NB + warp * 16 + (lane & 15);
+      if (lane == 0) (void)ld_tagged(xk, epoch, fault, relaxed);
+      __syncwarp();
+      const double mine = ld_tagged(xk, epoch, fault, false);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q) {
+          const double xv = __shfl_sync(full, mine, i + 16 * q);
+          acc[q][0] += la[i].x * xv;
+          acc[q][1] += la[i].y * xv;
+          acc[q][2] += lb[i].x * xv;
+          acc[q][3] += lb[i].y * xv;
+        }
+      }
+      if (k - 1 > j) load_block(k - 1);
+    }
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q) {
+      *reinterpret_cast<double2*>(sred + (warp * 2 + q) * NB + c4) = make_double2(acc[q][0], acc[q][1]);
+      *reinterpret_cast<double2*>(sred + (warp * 2 + q) * NB + c4 + 2) = make_double2(acc[q][2], acc[q][3]);
+    }
+    __syncthreads();
+    if (tid < NRHS * NB) {  // c = w_j - sum over the 8 warps (w_j comes from the forward owner of block j)
+      const int q = tid >> 7, c = tid & (NB - 1);
+      const double wv = ld_tagged(Wt + ((int64_t)j * NRHS + q) * NB + c, epoch, fault, false);
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += sred[(w * 2 + q) * NB + c];
+      sc[q * NB + c] = (c < nbj) ? wv - sum : 0.0;
+    }
+    __syncthreads();
+    double xj[NRHS];
+    block_gemv<NRHS>(sX, sc, tid, xj);
+    if ((tid & 1) == 0) {
+      const int c = tid >> 1;
+#pragma unroll
+      for (int q = 0; q < NRHS; ++q) {
+        st_tagged(Xt + ((int64_t)j * NRHS + q) * NB + c, xj[q], epoch);
+        if (c < nbj) B[(int64_t)q * m + j0 + c] = xj[q];
+      }
     }
   }
 }
@@ -1095,8 +1393,8 @@ constexpr size_t kTrsmSmem = (size_t)((NB + TRSM_ROWS) * LDS) * sizeof(double);
 constexpr size_t kTrsvSmem = (size_t)(NB * LDS + NB + 2 * NB) * sizeof(double);
 
 int configure_once() {
-  static bool done = false;
-  if (done) return LPB_OK;
+  static PerDeviceOnce once;
+  return once.run([](int) -> int {
   LPB_TRY(set_smem(potf2_kernel, kPotf2Smem));
   LPB_TRY(set_smem(potf2_inv_kernel, kPotf2InvSmem));
   LPB_TRY(set_smem(trsm_kernel, kTrsmSmem));
@@ -1106,8 +1404,8 @@ int configure_once() {
   LPB_TRY(set_smem(trsv_diag_kernel<false, 2>, kTrsvSmem));
   LPB_TRY(set_smem(trsv_diag_kernel<true, 1>, kTrsvSmem));
   LPB_TRY(set_smem(trsv_diag_kernel<true, 2>, kTrsvSmem));
-  done = true;
   return LPB_OK;
+  });
 }
 
 #define LPB_KCHECK(lc)             \
@@ -1118,19 +1416,48 @@ int configure_once() {
 
 }  // namespace
 
-// Workspace: one dense 128 x 128 inverse per diagonal block + a scratch right-hand side (2 m).
+// Workspace layout (doubles): [ inv(L_jj): nblk x 128 x 128 ][ scratch right-hand sides: 2 ldy ][ flags of the
+// flag-based pipelined solve: 2 nblk ints ][ tagged hand-off words of solve_ll_kernel: forward + backward,
+// nblk x 2 x 128 x 16 bytes each ].  Zero-filled at allocation: flags and tags start below any epoch.
+struct CholWs {
+  int64_t nblk, ldy, off_y, off_flags, off_wt, off_xt, total;
+  explicit CholWs(int64_t m) {
+    nblk = ceil_div(m, NB);
+    ldy = round_up(m, 2);
+    off_y = nblk * NB * NB;
+    off_flags = off_y + 2 * ldy;
+    off_wt = off_flags + round_up(nblk, 2);
+    off_xt = off_wt + nblk * 2 * NB * 2;
+    total = off_xt + nblk * 2 * NB * 2;
+  }
+};
+
 static int ensure_chol_ws(LaunchCtx& lc, int64_t m) {
-  const int64_t nblk = ceil_div(m, NB);
-  const int64_t need = nblk * NB * NB + 2 * round_up(m, 2) + nblk;  // + 2 nblk int flags of the pipelined solve
+  const int64_t need = CholWs(m).total;
   if (lc.chol_ws_cap >= need) return LPB_OK;
   if (lc.chol_ws) cudaFree(lc.chol_ws);
   lc.chol_ws = nullptr;
   lc.chol_ws_cap = 0;
+  lc.linv_valid_m = -1;
   void* p = nullptr;
   LPB_CUDA(cudaMalloc(&p, sizeof(double) * (size_t)need));
-  LPB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * (size_t)need, lc.stream));  // flags start below any epoch
+  LPB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * (size_t)need, lc.stream));
   lc.chol_ws = static_cast<double*>(p);
   lc.chol_ws_cap = need;
+  return LPB_OK;
+}
+
+// After a factorisation: complete the 128 x 128 block inverses (all blocks in parallel, ~20 us) for the solves.
+static int finish_factor(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm) {
+  if (!lc.linv_full) {
+    static PerDeviceOnce once;
+    LPB_TRY(once.run([](int) -> int { return set_smem(linv_complete_kernel, kLinvCompleteSmem); }));
+    linv_complete_kernel<<<(unsigned)ceil_div(m, NB), dim3(32, 16), kLinvCompleteSmem, lc.stream>>>(Mat, ldm, m, lc.chol_ws);
+    LPB_KCHECK(lc);
+    lc.linv_full = true;
+  }
+  lc.linv_valid_m = m;
+  lc.linv_mat = Mat;
   return LPB_OK;
 }
 
@@ -1195,22 +1522,25 @@ static int k_potrf_lookahead(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm)
   }
   lc.update_grid_cap = saved_cap;
   LPB_TRY(rc);
-  lc.linv_valid_m = m;
-  lc.linv_mat = Mat;
-  return LPB_OK;
+  return finish_factor(lc, m, Mat, ldm);
 }
 
 int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
   LPB_TRY(configure_once());
   LPB_TRY(ensure_chol_ws(lc, m));
+  if (lc.ws_m != m) {  // the workspace layout depends on m: stale words of another layout must not look like tags
+    const CholWs ws(m);
+    LPB_CUDA(cudaMemsetAsync(lc.chol_ws + ws.off_flags, 0, sizeof(double) * (size_t)(ws.total - ws.off_flags), lc.stream));
+    lc.ws_m = m;
+  }
   LPB_CUDA(cudaMemsetAsync(lc.info_dev, 0, sizeof(int), lc.stream));
   if (lc.world > 1 && lc.nccl_comm && lc.potrf_dist && syrk_impl == 0 && lc.trsm_impl == 0 && lc.update_impl == 0 &&
       m > NB && !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mat) & 15))
     return k_potrf_dist(lc, m, Mat, ldm);
-  if (lc.potrf_lookahead && syrk_impl == 0 && lc.trsm_impl == 0 && lc.update_impl == 0 && lc.solve_impl != 1 &&
+  if (lc.potrf_lookahead && syrk_impl == 0 && lc.trsm_impl == 0 && lc.update_impl == 0 &&
       !lc.sync_each_launch && m > 2 * NB && !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mat) & 15))
     return k_potrf_lookahead(lc, m, Mat, ldm);
-  const int full_inverse = (lc.trsm_impl == 2 || lc.solve_impl == 1) ? 1 : 0;
+  const int full_inverse = lc.trsm_impl == 2 ? 1 : 0;  // the solves complete the inverses themselves (finish_factor)
   lc.linv_full = full_inverse != 0;
   for (int64_t k0 = 0; k0 < m; k0 += NB) {
     const int nb = (int)((m - k0) < NB ? (m - k0) : NB);
@@ -1245,9 +1575,7 @@ int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
       if (lc.sync_each_launch) LPB_CUDA(cudaStreamSynchronize(lc.stream));
     }
   }
-  lc.linv_valid_m = m;
-  lc.linv_mat = Mat;
-  return LPB_OK;
+  return finish_factor(lc, m, Mat, ldm);
 }
 
 // Distributed factorisation for column-sharded contexts (every rank holds the same all-reduced M).
@@ -1259,19 +1587,23 @@ int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
 // updates that column first and defers the rest of its update until its panel is on the wire, so its
 // potf2 / TRSM chain overlaps the other ranks' updates (look-ahead across ranks, one stream per rank).
 // Bit-identical factors on all ranks by construction (every entry of L is computed by exactly one rank).
+int k_potrf_dist_reserve(LaunchCtx& lc, int64_t m) {
+  const int64_t need = (int64_t)NB * NB + m * NB;
+  if (lc.panel_buf_cap >= need) return LPB_OK;
+  if (lc.panel_buf) cudaFree(lc.panel_buf);
+  lc.panel_buf = nullptr;
+  lc.panel_buf_cap = 0;
+  void* p = nullptr;
+  LPB_CUDA(cudaMalloc(&p, sizeof(double) * (size_t)need));
+  lc.panel_buf = static_cast<double*>(p);
+  lc.panel_buf_cap = need;
+  return LPB_OK;
+}
+
 static int k_potrf_dist(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm) {
   const int G = lc.world, me = lc.rank;
   ncclComm_t comm = static_cast<ncclComm_t>(lc.nccl_comm);
-  const int64_t need = (int64_t)NB * NB + m * NB;
-  if (lc.panel_buf_cap < need) {
-    if (lc.panel_buf) cudaFree(lc.panel_buf);
-    lc.panel_buf = nullptr;
-    lc.panel_buf_cap = 0;
-    void* p = nullptr;
-    LPB_CUDA(cudaMalloc(&p, sizeof(double) * (size_t)need));
-    lc.panel_buf = static_cast<double*>(p);
-    lc.panel_buf_cap = need;
-  }
+  LPB_TRY(k_potrf_dist_reserve(lc, m));  // no-op for contexts made by lpb_create_sharded
   const int T = (int)ceil_div(m, NB);
   lc.linv_full = false;
   struct Ops {
@@ -1316,16 +1648,14 @@ static int k_potrf_dist(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm) {
     int update_owned(int p, int tile0) { return k_trailing_update_part(lc, m, Mat, ldm, k0(p), nb(p), tile0, 0, G, me); }
   } ops{lc, comm, m, ldm, Mat, G, me};
   LPB_TRY(potrf_dist_schedule(T, G, me, ops));
-  lc.linv_valid_m = m;
-  lc.linv_mat = Mat;
-  return LPB_OK;
+  return finish_factor(lc, m, Mat, ldm);
 }
 
 // Fast path: one launch per 128-block step, using the stored inv(L_kk) blocks of the last k_potrf.
 template <int NRHS>
 static int potrs_fused(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B) {
   const int nblk = (int)ceil_div(m, NB);
-  double* Y = lc.chol_ws + (int64_t)nblk * NB * NB;  // scratch m x NRHS (column-major, ld m)
+  double* Y = lc.chol_ws + CholWs(m).off_y;          // scratch m x NRHS (column-major, ld m)
   for (int kb = 0; kb < nblk; ++kb) {                // forward: B -> Y
     const int64_t k0 = (int64_t)kb * NB;
     const int nb = (int)((m - k0) < NB ? (m - k0) : NB);
@@ -1347,32 +1677,75 @@ static int potrs_fused(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, d
 // One cooperative launch for the whole solve (see solve_pipelined_kernel).
 template <int NRHS>
 static int potrs_pipelined(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B) {
-  static int max_ctas = 0;
+  static PerDeviceOnce once;
+  static int max_ctas_dev[kMaxDevices] = {};
   auto kern = solve_pipelined_kernel<NRHS>;
-  if (max_ctas == 0) {
+  LPB_TRY(once.run([&](int dev) -> int {
     LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmem));
-    int dev = 0, sms = 0, per_sm = 0;
-    LPB_CUDA(cudaGetDevice(&dev));
+    int sms = 0, per_sm = 0;
     LPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     LPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSolveThreads, kSolveSmem));
-    if (per_sm < 1) {
+    if (per_sm < 1 || dev < 0 || dev >= kMaxDevices) {
       set_last_error("solve_pipelined_kernel does not fit on this device");
       return LPB_ERR_CUDA;
     }
-    max_ctas = sms * per_sm;
-  }
-  int nblk = (int)ceil_div(m, NB);
-  double* Y = lc.chol_ws + (int64_t)nblk * NB * NB;
-  int64_t ldy = round_up(m, 2);
-  int* flags_f = reinterpret_cast<int*>(Y + 2 * ldy);
+    max_ctas_dev[dev] = sms * per_sm;
+    return LPB_OK;
+  }));
+  int cur_dev = 0;
+  LPB_CUDA(cudaGetDevice(&cur_dev));
+  const int max_ctas = max_ctas_dev[cur_dev];
+  const CholWs ws(m);
+  int nblk = (int)ws.nblk;
+  double* Y = lc.chol_ws + ws.off_y;
+  int64_t ldy = ws.ldy;
+  int* flags_f = reinterpret_cast<int*>(lc.chol_ws + ws.off_flags);
   int* flags_b = flags_f + nblk;
   int epoch = ++lc.solve_epoch;
   const double* linv = lc.chol_ws;
+  unsigned long long* fault = lc.fault_dev;
   void* args[] = {(void*)&L, (void*)&ldm, (void*)&linv, (void*)&m, (void*)&nblk, (void*)&B,
-                  (void*)&Y, (void*)&ldy, (void*)&flags_f, (void*)&flags_b, (void*)&epoch};
+                  (void*)&Y, (void*)&ldy, (void*)&flags_f, (void*)&flags_b, (void*)&epoch, (void*)&fault};
   int grid = nblk < max_ctas ? nblk : max_ctas;
   if (lc.solve_grid_cap > 0 && grid > lc.solve_grid_cap) grid = lc.solve_grid_cap;
   LPB_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kSolveThreads), args, kSolveSmem, lc.stream));
+  lc.launches++;
+  return LPB_OK;
+}
+
+// solve_ll_kernel: one cooperative launch, tagged hand-off, full block inverses (the default).
+template <int NRHS>
+static int potrs_ll(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B) {
+  static PerDeviceOnce once;
+  static int max_ctas_dev[kMaxDevices] = {};
+  auto kern = solve_ll_kernel<NRHS>;
+  LPB_TRY(once.run([&](int dev) -> int {
+    LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveLLSmem));
+    int sms = 0, per_sm = 0;
+    LPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    LPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSolveThreads, kSolveLLSmem));
+    if (per_sm < 1 || dev < 0 || dev >= kMaxDevices) {
+      set_last_error("solve_ll_kernel does not fit on this device");
+      return LPB_ERR_CUDA;
+    }
+    max_ctas_dev[dev] = sms * per_sm;
+    return LPB_OK;
+  }));
+  int cur_dev = 0;
+  LPB_CUDA(cudaGetDevice(&cur_dev));
+  const int max_ctas = max_ctas_dev[cur_dev];
+  const CholWs ws(m);
+  int nblk = (int)ws.nblk;
+  Tagged* Wt = reinterpret_cast<Tagged*>(lc.chol_ws + ws.off_wt);
+  Tagged* Xt = reinterpret_cast<Tagged*>(lc.chol_ws + ws.off_xt);
+  uint32_t epoch = (uint32_t)(++lc.solve_epoch);
+  const double* xall = lc.chol_ws;
+  unsigned long long* fault = lc.fault_dev;
+  void* args[] = {(void*)&L, (void*)&ldm, (void*)&xall, (void*)&m, (void*)&nblk, (void*)&B,
+                  (void*)&Wt, (void*)&Xt, (void*)&epoch, (void*)&fault};
+  int grid = nblk < max_ctas ? nblk : max_ctas;
+  if (lc.solve_grid_cap > 0 && grid > lc.solve_grid_cap) grid = lc.solve_grid_cap;
+  LPB_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kSolveThreads), args, kSolveLLSmem, lc.stream));
   lc.launches++;
   return LPB_OK;
 }
@@ -1410,13 +1783,20 @@ static int potrs_impl(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, do
 int k_potrs(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B, int nrhs, bool use_linv) {
   LPB_TRY(configure_once());
   const bool aligned = !(ldm & 1) && !(reinterpret_cast<uintptr_t>(L) & 15);  // double2 loads of L
-  if (use_linv && aligned && lc.solve_impl != 2 && lc.linv_valid_m == m && lc.linv_mat == L && lc.chol_ws) {
-    if (lc.solve_impl == 1 && lc.linv_full) {  // one launch per 128-block step (kept for bisecting)
+  // solve_impl: 0 = solve_ll_kernel (default), 1 = one launch per block step with the full inverses, 2 = plain
+  // substitution (no stored inverses at all), 3 = the flag-based pipelined kernel with blocked substitution over
+  // the 16 x 16 inverted sub-blocks (the round-1 default; kept as the accuracy / timing comparison).
+  if (use_linv && aligned && lc.solve_impl != 2 && lc.linv_valid_m == m && lc.linv_mat == L && lc.chol_ws &&
+      lc.linv_full && lc.fault_dev) {
+    if (lc.solve_impl == 1) {
       if (nrhs == 1) return potrs_fused<1>(lc, m, L, ldm, B);
       if (nrhs == 2) return potrs_fused<2>(lc, m, L, ldm, B);
-    } else {
+    } else if (lc.solve_impl == 3) {
       if (nrhs == 1) return potrs_pipelined<1>(lc, m, L, ldm, B);
       if (nrhs == 2) return potrs_pipelined<2>(lc, m, L, ldm, B);
+    } else {
+      if (nrhs == 1) return potrs_ll<1>(lc, m, L, ldm, B);
+      if (nrhs == 2) return potrs_ll<2>(lc, m, L, ldm, B);
     }
   } else {
     if (nrhs == 1) return potrs_impl<1>(lc, m, L, ldm, B);

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "../../include/lpb200.h"
 
@@ -29,6 +30,26 @@ const char* get_last_error();
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// One-time per-DEVICE setup (cudaFuncSetAttribute and occupancy queries apply to the current device only, and
+// several host threads may own contexts on several devices of one process): run(f) calls f(device) the first
+// time it is reached on each device, under a lock.
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce {
+  std::mutex mu;
+  bool done[kMaxDevices] = {};
+  template <class F>
+  int run(F&& f) {
+    int dev = 0;
+    LPB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return f(dev);
+    std::lock_guard<std::mutex> g(mu);
+    if (done[dev]) return LPB_OK;
+    const int rc = f(dev);
+    if (rc == LPB_OK) done[dev] = true;
+    return rc;
+  }
+};
+
 inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -44,17 +65,19 @@ struct LaunchCtx {
   cudaStream_t stream = nullptr;
   int64_t launches = 0;       // kernels launched by this library on this context
   double* red_partials = nullptr;  // kMaxRedVals * kMaxRedBlocks
-  double* red_out = nullptr;       // device, kMaxRedVals
-  double* red_host = nullptr;      // pinned, kMaxRedVals
+  double* red_out = nullptr;       // device, kMaxRedVals + 1: the last word is the context's fault word
+  double* red_host = nullptr;      // pinned, kMaxRedVals + 1
+  unsigned long long* fault_dev = nullptr;  // = red_out + kMaxRedVals: raised by a kernel that gave up waiting
   double* gemv_partials = nullptr; // gemv_t row-chunk partials
   int64_t gemv_partials_cap = 0;   // in doubles
   double* chol_ws = nullptr;       // inv(L_kk) blocks of the last k_potrf + solve scratch (cholesky.cu)
   int64_t chol_ws_cap = 0;         // in doubles
+  int64_t ws_m = -1;               // order of the matrix the hand-off words of chol_ws are laid out for
   int64_t linv_valid_m = -1;       // order of the matrix whose block inverses chol_ws holds
   const double* linv_mat = nullptr; // ... and its address
   bool linv_full = false;          // chol_ws holds the full 128 x 128 inverses (else only their 16 x 16 diagonal blocks)
   int solve_epoch = 0;             // flag value of the next pipelined solve (cholesky.cu)
-  int solve_impl = 0;              // 0 = pipelined single launch, 1 = one launch per block step
+  int solve_impl = 0;              // 0 = solve_ll_kernel, 1 = one launch per block step, 2 = substitution, 3 = flag-based pipelined
   int sync_each_launch = 0;        // debug: stream-synchronise after every launch of k_potrf
   int trsm_impl = 0, update_impl = 0;  // bisecting knobs of k_potrf: 1 = plain DFMA kernel for that step
   int solve_grid_cap = 0;          // > 0: cap the pipelined solve's grid (tests: several block rows per CTA)

@@ -379,7 +379,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int get_encode_fn(EncodeTiledFn* out) {
+  static std::mutex mu;
   static EncodeTiledFn fn = nullptr;
+  std::lock_guard<std::mutex> g(mu);
   if (!fn) {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -418,12 +420,12 @@ template <int MODE, bool SCALE, int VAR = 0>
 int launch_dmma(LaunchCtx& lc, const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int m_total,
                 int tile0, int ntr, int k_begin, int nkb, int col_origin, int shape = SHAPE_TRI,
                 OwnedCols own = OwnedCols{1, 0, 0}) {
-  static bool configured = false;
+  static PerDeviceOnce once;  // one per template instantiation
   auto kern = syrk_dmma_kernel<MODE, SCALE, VAR>;
-  if (!configured) {
+  LPB_TRY(once.run([&](int) -> int {
     LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAlloc));
-    configured = true;
-  }
+    return LPB_OK;
+  }));
   const int ntiles = (MODE == MODE_TRSM || shape == SHAPE_COL) ? ntr
                      : (shape == SHAPE_OWNED ? own.count() : ntr * (ntr + 1) / 2);
   if (ntiles <= 0) return LPB_OK;

@@ -100,6 +100,8 @@ int k_trailing_update_simple(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm,
 // ---------------------------------------------------------------- K2 / K3 (cholesky.cu)
 // In-place blocked right-looking lower Cholesky; info (device int) = 0 or first bad pivot + 1.
 int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl);
+// Allocate the panel buffers of the distributed factorisation for order m up front (column-sharded contexts).
+int k_potrf_dist_reserve(LaunchCtx& lc, int64_t m);
 // Solve L L^T X = B in place; B column-major m x nrhs.  use_linv: use the inverted diagonal blocks the
 // last k_potrf on this context left behind (L must be that factor); otherwise plain substitution.
 int k_potrs(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B, int nrhs, bool use_linv);

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -154,8 +155,10 @@ void profile_collect(lpb_ctx* c) {
 struct ProcessComm {
   ncclComm_t comm = nullptr;
   int rank = -1, world = 0;
+  int refs = 0;  // live contexts holding `comm`: it is neither rebuilt nor destroyed under them
 };
 ProcessComm g_comm;
+std::mutex g_comm_mu;
 
 // device staging arena of lpb_solve_batched for host inputs (per host thread, grow-only)
 thread_local void* g_batched_ws = nullptr;
@@ -166,6 +169,25 @@ int allreduce(lpb_ctx* c, double* buf, int64_t count, ncclRedOp_t op) {
   PhaseTimer tm(c, PH_COMM);
   LPB_NCCL(ncclAllReduce(buf, buf, (size_t)count, ncclDouble, op, c->comm, c->lc.stream));
   return LPB_OK;
+}
+
+// All ranks learn the worst status of any rank (one int all-reduce + sync): a rank-local failure (upload,
+// allocation) then fails the call on EVERY rank instead of leaving the others blocked in the next collective.
+int agree_status(lpb_ctx* c, int rc) {
+  if (c->world <= 1 || !c->comm || !c->chk_dev) return rc;
+  int* flag = reinterpret_cast<int*>(c->chk_dev);  // 16 bytes of device scratch owned by the context
+  const int mine = rc == LPB_OK ? 0 : 1;
+  if (cudaMemcpyAsync(flag, &mine, sizeof(int), cudaMemcpyHostToDevice, c->lc.stream) != cudaSuccess) return LPB_ERR_CUDA;
+  if (ncclAllReduce(flag, flag, 1, ncclInt32, ncclMax, c->comm, c->lc.stream) != ncclSuccess) return LPB_ERR_NCCL;
+  int any = 0;
+  if (cudaMemcpyAsync(&any, flag, sizeof(int), cudaMemcpyDeviceToHost, c->lc.stream) != cudaSuccess ||
+      cudaStreamSynchronize(c->lc.stream) != cudaSuccess)
+    return LPB_ERR_CUDA;
+  if (rc == LPB_OK && any) {
+    set_last_error("another rank of the sharded problem failed");
+    return LPB_ERR_NCCL;
+  }
+  return rc;
 }
 
 // Debug (option "check_replicas"): every rank must hold the same bits of a replicated buffer.  All
@@ -280,7 +302,7 @@ struct CudaDev {
     }
     if (c->world > 1 && c->packed_allreduce) {
       const int64_t cnt = tri_packed_doubles(c->m);
-      if (!c->tri_buf) {
+      if (!c->tri_buf) {  // normally allocated by lpb_create_sharded; option toggled on later
         LPB_TRY(dev_alloc(c, &c->tri_buf, cnt));
         LPB_CUDA(cudaMemsetAsync(c->tri_buf, 0, sizeof(double) * (size_t)cnt, c->lc.stream));  // padding stays finite
       }
@@ -496,8 +518,10 @@ int ctx_base_init(lpb_ctx* c, void* stream) {
     c->own_stream = true;
   }
   LPB_TRY(dev_alloc(c, &c->lc.red_partials, (int64_t)kMaxRedVals * kMaxRedBlocks));
-  LPB_TRY(dev_alloc(c, &c->lc.red_out, kMaxRedVals));
-  LPB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->lc.red_host), sizeof(double) * kMaxRedVals));
+  LPB_TRY(dev_alloc(c, &c->lc.red_out, kMaxRedVals + 1));
+  LPB_CUDA(cudaMemsetAsync(c->lc.red_out, 0, sizeof(double) * (kMaxRedVals + 1), c->lc.stream));
+  c->lc.fault_dev = reinterpret_cast<unsigned long long*>(c->lc.red_out + kMaxRedVals);
+  LPB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->lc.red_host), sizeof(double) * (kMaxRedVals + 1)));
   LPB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->lc.info_host), sizeof(int)));
   void* q = nullptr;
   LPB_CUDA(cudaMalloc(&q, sizeof(int)));
@@ -612,8 +636,11 @@ int upload_problem(lpb_ctx* c, const double* A, int64_t lda, const double* b, co
     return LPB_ERR_BAD_ARGUMENT;
   }
   const cudaMemcpyKind kind = mem == LPB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  LPB_CUDA(cudaMemcpy2DAsync(c->A, sizeof(double) * c->lda, A, sizeof(double) * lda, sizeof(double) * c->n, c->m, kind,
-                             c->lc.stream));
+  if (lda == c->lda && lda == c->n)  // contiguous on both sides: one linear copy at full PCIe / HBM rate
+    LPB_CUDA(cudaMemcpyAsync(c->A, A, sizeof(double) * (size_t)(c->m * c->lda), kind, c->lc.stream));
+  else
+    LPB_CUDA(cudaMemcpy2DAsync(c->A, sizeof(double) * c->lda, A, sizeof(double) * lda, sizeof(double) * c->n, c->m,
+                               kind, c->lc.stream));
   LPB_CUDA(cudaMemcpyAsync(c->b, b, sizeof(double) * c->m, kind, c->lc.stream));
   LPB_CUDA(cudaMemcpyAsync(c->c, cc, sizeof(double) * c->n, kind, c->lc.stream));
   LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
@@ -646,6 +673,10 @@ void ctx_free(lpb_ctx* c) {
   if (c->lc.info_host) cudaFreeHost(c->lc.info_host);
   if (c->chk_host) cudaFreeHost(c->chk_host);
   if (c->own_stream && c->lc.stream) cudaStreamDestroy(c->lc.stream);
+  if (c->comm) {
+    std::lock_guard<std::mutex> g(g_comm_mu);
+    if (c->comm == g_comm.comm && g_comm.refs > 0) --g_comm.refs;
+  }
   delete c;
 }
 
@@ -807,6 +838,11 @@ int lpb_destroy(lpb_ctx* c) {
 }
 
 int lpb_comm_finalize(void) {
+  std::lock_guard<std::mutex> g(g_comm_mu);
+  if (g_comm.refs > 0) {
+    set_last_error("comm_finalize: %d live context(s) still use the process communicator", g_comm.refs);
+    return LPB_ERR_BAD_ARGUMENT;
+  }
   if (g_comm.comm) ncclCommDestroy(g_comm.comm);
   g_comm = ProcessComm();
   return LPB_OK;
@@ -840,29 +876,55 @@ int lpb_create_sharded(lpb_ctx** out, int64_t m, int64_t n_global, int64_t col0,
   lpb_ctx* c = new (std::nothrow) lpb_ctx();
   if (!c) return LPB_ERR_BAD_ARGUMENT;
   int rc = ctx_base_init(c, stream);
-  if (rc == LPB_OK) rc = ctx_alloc_vectors(c, m, n_local, true);
-  if (rc == LPB_OK && A_local) rc = upload_problem(c, A_local, lda, b, c_local, c0, mem);
-  if (rc == LPB_OK && world > 1) {
-    if (nccl_unique_id) {  // (re)build the process communicator
-      if (g_comm.comm) ncclCommDestroy(g_comm.comm);
-      g_comm = ProcessComm();
-      ncclUniqueId id;
-      std::memcpy(&id, nccl_unique_id, sizeof(id));
-      ncclResult_t r = ncclCommInitRank(&g_comm.comm, world, id, rank);
-      if (r != ncclSuccess) {
-        set_last_error("ncclCommInitRank -> %s", ncclGetErrorString(r));
-        g_comm = ProcessComm();
-        rc = LPB_ERR_NCCL;
+  // The communicator comes FIRST: every later rank-local failure (allocation, upload) is then agreed on across
+  // the ranks (agree_status) instead of leaving the others blocked in ncclCommInitRank or in the first all-reduce.
+  if (world > 1) {
+    std::lock_guard<std::mutex> g(g_comm_mu);
+    int rc_comm = rc;
+    if (nccl_unique_id) {  // (re)build the process communicator -- every rank enters, whatever its local status
+      if (g_comm.refs > 0) {
+        set_last_error("create_sharded: a new ncclUniqueId was given while %d live context(s) still use the process "
+                       "communicator", g_comm.refs);
+        rc_comm = LPB_ERR_BAD_ARGUMENT;
       } else {
-        g_comm.rank = rank;
-        g_comm.world = world;
+        if (g_comm.comm) ncclCommDestroy(g_comm.comm);
+        g_comm = ProcessComm();
+        ncclUniqueId id;
+        std::memcpy(&id, nccl_unique_id, sizeof(id));
+        ncclResult_t r = ncclCommInitRank(&g_comm.comm, world, id, rank);
+        if (r != ncclSuccess) {
+          set_last_error("ncclCommInitRank -> %s", ncclGetErrorString(r));
+          g_comm = ProcessComm();
+          rc_comm = LPB_ERR_NCCL;
+        } else {
+          g_comm.rank = rank;
+          g_comm.world = world;
+        }
       }
     }
-    c->comm = g_comm.comm;
-    c->lc.nccl_comm = g_comm.comm;
-    c->lc.rank = rank;
-    c->lc.world = world;
+    if (g_comm.comm && g_comm.world == world && g_comm.rank == rank) {
+      c->comm = g_comm.comm;
+      c->lc.nccl_comm = g_comm.comm;
+      c->lc.rank = rank;
+      c->lc.world = world;
+      c->world = world;
+      c->rank = rank;
+      ++g_comm.refs;
+    } else if (rc_comm == LPB_OK) {
+      rc_comm = LPB_ERR_NCCL;
+    }
+    if (rc == LPB_OK) rc = rc_comm;
   }
+  if (rc == LPB_OK) rc = ctx_alloc_vectors(c, m, n_local, true);
+  if (rc == LPB_OK && world > 1) {  // buffers of the sharded factorisation: allocated here, not in the middle of a solve
+    const int64_t cnt = tri_packed_doubles(m);
+    rc = dev_alloc(c, &c->tri_buf, cnt);
+    if (rc == LPB_OK && cudaMemsetAsync(c->tri_buf, 0, sizeof(double) * (size_t)cnt, c->lc.stream) != cudaSuccess)
+      rc = LPB_ERR_CUDA;  // padding of the packed triangle stays finite
+    if (rc == LPB_OK) rc = k_potrf_dist_reserve(c->lc, m);
+  }
+  if (rc == LPB_OK && A_local) rc = upload_problem(c, A_local, lda, b, c_local, c0, mem);
+  rc = agree_status(c, rc);
   if (rc != LPB_OK) {
     ctx_free(c);
     return rc;
@@ -914,7 +976,7 @@ int lpb_create_sharded_synthetic(lpb_ctx** out, int64_t m, int64_t n_global, int
     LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
     return LPB_OK;
   };
-  rc = run();
+  rc = agree_status(c, run());
   if (rc != LPB_OK) {
     ctx_free(c);
     return rc;
@@ -1086,8 +1148,7 @@ int lpb_k_potrf(lpb_ctx* c, int64_t m, double* dM, int64_t ldm, int32_t* info_ho
 int lpb_k_potrs(lpb_ctx* c, int64_t m, const double* dL, int64_t ldm, double* dB, int64_t nrhs) {
   if (!c || !dL || !dB) return LPB_ERR_BAD_ARGUMENT;
   LPB_TRY(k_potrs(c->lc, m, dL, ldm, dB, (int)nrhs, c->syrk_impl == 0));
-  LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
-  return LPB_OK;
+  return fetch_scalars(c->lc, 0);  // stream sync + the fault word of the pipelined solve
 }
 
 int lpb_k_gemv_n(lpb_ctx* c, int64_t m, int64_t n, const double* dA, int64_t lda, const double* d_w, double* d_out) {
@@ -1194,7 +1255,7 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
     return LPB_OK;
   }
   if (k == "solve_impl") {
-    if (value < 0 || value > 2) return LPB_ERR_BAD_ARGUMENT;
+    if (value < 0 || value > 3) return LPB_ERR_BAD_ARGUMENT;
     c->lc.solve_impl = (int)value;
     return LPB_OK;
   }

@@ -107,8 +107,16 @@ int reduce_finalize(LaunchCtx& lc, const RedSpec& spec) {
 }
 
 int fetch_scalars(LaunchCtx& lc, int nvals) {
-  LPB_CUDA(cudaMemcpyAsync(lc.red_host, lc.red_out, sizeof(double) * nvals, cudaMemcpyDeviceToHost, lc.stream));
+  (void)nvals;  // always the whole line: the fault word rides along behind the kMaxRedVals results
+  LPB_CUDA(cudaMemcpyAsync(lc.red_host, lc.red_out, sizeof(double) * (kMaxRedVals + 1), cudaMemcpyDeviceToHost,
+                           lc.stream));
   LPB_CUDA(cudaStreamSynchronize(lc.stream));
+  unsigned long long fault;
+  std::memcpy(&fault, lc.red_host + kMaxRedVals, sizeof(fault));
+  if (fault != 0ull) {
+    set_last_error("a pipelined kernel gave up waiting for a hand-off from another CTA (fault word %llu)", fault);
+    return LPB_ERR_CUDA;
+  }
   return LPB_OK;
 }
 

@@ -448,8 +448,11 @@ class InteriorPoint:
             raise InvalidParameter("oracle restates the Cholesky arm only")
 
     def solve_normal_form(self, pb: Problem, trace: Optional[List[dict]] = None, gemm=None,
-                          timers: Optional[dict] = None, stop_after: Optional[int] = None):
-        """interior_point/mod.rs:199-240."""
+                          timers: Optional[dict] = None, stop_after: Optional[int] = None,
+                          on_iteration: Optional[Callable] = None):
+        """interior_point/mod.rs:199-240.  `on_iteration(iteration, point, indicators)` is a fixture-generation hook
+        (tools/oracle_full_size.py snapshots x / tau where a looser tolerance would have stopped); it does not
+        influence the loop."""
         pt = blind_start(pb)  # :203
         ind = indicators_from(pt, pb)  # :206
         if self.disp:  # :208-211
@@ -467,6 +470,8 @@ class InteriorPoint:
             if trace is not None:
                 trace.append(dict(iteration=iteration, alpha=alpha, tau=pt.tau, kappa=pt.kappa,
                                   **dataclasses.asdict(ind), **DEBUG_SCALARS))
+            if on_iteration is not None:
+                on_iteration(iteration, pt, ind)
             st = ind.status(pt.tau, pt.kappa, self.tol)  # :230-235
             if st == "Optimal":
                 return pt.x / pt.tau, iteration

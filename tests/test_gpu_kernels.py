@@ -117,13 +117,14 @@ def test_gemv_sweeps_match_numpy(m, n):
     assert (np.abs(o_t.cpu().numpy() - A.T @ v) / (np.abs(A.T) @ np.abs(v))).max() < 1e-13
 
 
-@pytest.mark.parametrize("solve_impl,grid_cap", [(0, 0), (0, 3), (0, 1), (1, 0)])
+@pytest.mark.parametrize("solve_impl,grid_cap", [(0, 0), (0, 3), (0, 1), (1, 0), (2, 0), (3, 0), (3, 3), (3, 1)])
 @pytest.mark.parametrize("nrhs", [1, 2])
 @pytest.mark.parametrize("m", [1, 17, 64, 128, 200, 640, 1537, 2305])
 def test_potrf_then_fused_potrs(m, nrhs, solve_impl, grid_cap):
     """K2 + K3 fast path: factor on the device, then solve with the stored inverted diagonal blocks
-    (pipelined single-launch kernel, also with its grid capped so one CTA owns several block rows, and
-    the one-launch-per-block variant); residual ||M x - b|| / (||M|| ||x||) < 1e-13, x close to LAPACK's."""
+    (solve_impl 0: the single-launch kernel with tagged hand-off and full block inverses, also with its grid capped
+    so one CTA owns several block rows; 1: one launch per block; 2: plain substitution; 3: the flag-based pipelined
+    kernel with blocked substitution); residual ||M x - b|| / (||M|| ||x||) < 1e-13, x close to LAPACK's."""
     from scipy.linalg import cho_factor, cho_solve
     rng = np.random.default_rng(3 * m + nrhs)
     Bm = rng.standard_normal((m, m + 8))
@@ -138,7 +139,7 @@ def test_potrf_then_fused_potrs(m, nrhs, solve_impl, grid_cap):
         ok(ctx.lib.lpb_k_potrf(ctx.h, m, dM.data_ptr(), ldm, C.byref(info)))
         assert info.value == 0
         ok(ctx.lib.lpb_k_potrs(ctx.h, m, dM.data_ptr(), ldm, dB.data_ptr(), nrhs))
-        if solve_impl == 0:  # a second solve on the same context: the flag epoch advances
+        if solve_impl in (0, 3):  # a second solve on the same context: the hand-off epoch advances
             dB2 = to_dev(rhs)
             ok(ctx.lib.lpb_k_potrs(ctx.h, m, dM.data_ptr(), ldm, dB2.data_ptr(), nrhs))
             assert np.array_equal(dB2.cpu().numpy(), dB.cpu().numpy())
