@@ -13,9 +13,17 @@ iterations/s"); ms_per_step is the time-to-solve.
   e2e   : the same through the public reference-shaped API (`InteriorPoint.solve(problem)`):
           context creation, H2D of A/b/c from pinned host memory, solve, D2H of x, teardown.
   roofline : the dominant kernel (K1, DMMA SYRK): m(m+1)n algorithmic flop per launch / its mean
-          launch duration (CUDA events inside the library, on the launching stream).
-  cpu_baseline : the oracle (NumPy/OpenBLAS restatement of the reference) on the host cores, on a
-          bounded sample of the same workload.
+          launch duration (CUDA events inside the library, on the launching stream); `peak` is the nominal
+          B200 FP64 figure, `peak_measured` the DMMA issue peak measured in this very run.
+  cpu_baseline : the oracle (NumPy/OpenBLAS restatement of the reference) on the host cores: REAL
+          iterations of its loop on the same workload, as many as fit a bounded budget.
+  c5 : every product line also carries a short record of config C5 (32768 x 131072, generated on the device
+          per column shard, 3 iterations): per-iteration time and phases at this N -- the configuration the
+          north star quotes the multi-GPU target on.
+
+`--impl reference` times the oracle's own loop (real iterations, all host threads); its `config` equals the
+product arm's.  Both arms report `ms_per_iteration`; `ms_per_step` is one complete solve in the product arm and
+one bounded sample of iterations in the reference arm (`details.step`).
 
 N > 1: strong scaling -- the same LP with A column-sharded over the ranks, NCCL
 all-reduce of M and of the A.w products.
@@ -55,6 +63,25 @@ NOMINAL_FP64_TFLOPS = 40.0  # B200 FP64 (tensor == vector), NVIDIA HGX B200 spec
 
 def workload_label(name, m, n, seed):
     return "%s dense LP slack-form m=%d n=%d seed=%d (ub+eq, SURVEY 8d generator)" % (name, m, n, seed)
+
+
+def bench_config(workload, m, n, seed, world, potrf_dist=1):
+    """`config` of the JSON line: the SAME dict in the product and the reference arm."""
+    if workload == "C4":
+        wl = "C4 batched: %d independent dense LPs slack-form m=%d n=%d, seeds 1000+i, one CTA per problem" % (
+            C4_BATCH, m, n)
+        par = "batch sharded over %d GPU(s), no collective" % world
+    else:
+        wl = workload_label(workload, m, n, seed)
+        if workload == "C5":
+            wl += ", generated on the device per column shard (counter-based N(0,1))"
+        par = "1 GPU" if world == 1 else "A column-sharded over %d GPUs, NCCL all-reduce of M, %s Cholesky" % (
+            world, "panel-broadcast distributed" if potrf_dist else "replicated")
+    a_mb = m * n * 8 / 1e6
+    l2 = ("inputs larger than L2 (A = %.0f MB, streamed from HBM by every sweep and SYRK)" % a_mb if a_mb > 126.0 else
+          "inputs fit in L2 (A = %.0f MB), no flush between iterations: a parity-test configuration, not a bench line"
+          % a_mb)
+    return {"workload": wl, "parallelism": par, "l2": l2}
 
 
 def synthetic_lp(m, n, seed):
@@ -134,91 +161,120 @@ def cpu_problem(m, n, seed):
     return o.build_problem(*synthetic_lp(m, n, seed))
 
 
-def cpu_sample(m, n, seed, budget_s=25.0, pb=None):
-    """Time the oracle (the reference's algorithm on host cores, OpenBLAS threads) on a bounded
-    sample of the workload.  Returns (iterations_per_s, sample_description, cores)."""
+def cpu_iterations(pb, budget_s, min_iters=1, max_iters=200):
+    """Run the oracle's loop (interior_point/mod.rs:199-240 restated) from the blind start and time REAL
+    iterations until `budget_s` is used up (at least `min_iters`).  Returns (iterations, seconds) of the timed
+    iterations; the blind-start residuals before the first iteration are not counted."""
     from oracle import ipm_oracle as o
+
+    class _Stop(Exception):
+        pass
+
+    stamps = []
+
+    def on_iteration(iteration, pt, ind):
+        stamps.append(time.perf_counter())
+        if (iteration >= min_iters and stamps[-1] - t_start >= budget_s) or iteration >= max_iters:
+            raise _Stop()
+
+    t_start = time.perf_counter()
+    box = {}
+
+    def first_tick(*a):
+        box.setdefault("t0", time.perf_counter())
+
+    # the clock starts when blind_start() has produced the first iterate (its 2 GEMVs are set-up, not an iteration)
+    orig = o.blind_start
+    try:
+        def timed_blind_start(p):
+            pt = orig(p)
+            first_tick()
+            return pt
+        o.blind_start = timed_blind_start
+        try:
+            o.InteriorPoint().solve(pb, on_iteration=on_iteration)
+        except (_Stop, o.LinearProgramError):
+            pass
+    finally:
+        o.blind_start = orig
+    its = len(stamps)
+    if its == 0:
+        return 0, 0.0
+    return its, stamps[-1] - box["t0"]
+
+
+def cpu_sample(m, n, seed, budget_s=25.0, pb=None):
+    """Time the oracle (the reference's algorithm on host cores, OpenBLAS threads) on a bounded sample of the
+    workload: REAL consecutive iterations of its loop.  Returns (iterations_per_s, sample_description, cores)."""
     cores = os.cpu_count() or 1
     if pb is None:
         pb = cpu_problem(m, n, seed)
-    if 2.0 * m * m * n < 1e12:  # small enough (C1, C2): time whole iterations of the real loop
-        t0 = time.perf_counter()
-        its = 0
-        tr = []
-        try:
-            o.InteriorPoint().solve(pb, trace=tr, stop_after=1)
-        except o.LinearProgramError:
-            pass
-        t_one = time.perf_counter() - t0
-        k = int(max(1, min(25, budget_s / max(t_one, 1e-3))))
-        t0 = time.perf_counter()
-        tr = []
-        try:
-            o.InteriorPoint().solve(pb, trace=tr, stop_after=k)
-        except o.LinearProgramError:
-            pass
-        its = max(1, len(tr))
-        dt = time.perf_counter() - t0
-        return its / dt, "oracle loop, first %d iterations of the %dx%d solve (incl. blind-start residuals)" % (
-            its, m, n), cores
-    # large: extrapolate one iteration from slices of its dominant pieces
-    from scipy.linalg import lapack
-    pt = o.blind_start(pb)
-    Dinv = pt.x / pt.z
-    A = pb.A
-    t0 = time.perf_counter()
-    B = Dinv[:, None] * A.T          # the reference's n x m temporary (newton_equations.rs:57), timed in full
-    t_temp = time.perf_counter() - t0
-    r = 256
-    while True:  # row slice of M = A B: the reference runs the FULL GEMM (2 m^2 n flop)
-        t0 = time.perf_counter()
-        _ = A[:r].dot(B)
-        t_slice = time.perf_counter() - t0
-        if t_slice > budget_s * 0.3 or r >= m:
-            break
-        r = min(m, r * 2)
-    del B
-    t_gemm = t_temp + t_slice * m / r
-    ms = min(m, 8192)
-    rng = np.random.default_rng(1)
-    B = rng.standard_normal((ms, ms + 16))
-    S = B.dot(B.T) + ms * np.eye(ms)
-    t0 = time.perf_counter()
-    cfac, info = lapack.dpotrf(S, lower=0)
-    t_potrf = (time.perf_counter() - t0) * (m / ms) ** 3
-    rhs = rng.standard_normal(ms)
-    t0 = time.perf_counter()
-    lapack.dpotrs(cfac, rhs, lower=0)
-    t_potrs = (time.perf_counter() - t0) * (m / ms) ** 2
-    t0 = time.perf_counter()
-    A.dot(pt.x)
-    A.T.dot(pt.y)
-    t_gemv2 = time.perf_counter() - t0
-    t_iter = t_gemm + t_potrf + 4 * t_potrs + 6 * t_gemv2  # reference: 12 sweeps + 4 potrs per iteration
-    desc = ("one %dx%d iteration extrapolated from slices: %d/%d rows of the A.D.A^T GEMM (%.1fs), dpotrf+dpotrs at "
-            "%d scaled cubically/quadratically, 2 of the 12 GEMV sweeps measured in full" % (m, n, r, m, t_slice, ms))
-    return 1.0 / t_iter, desc, cores
+    its, dt = cpu_iterations(pb, budget_s)
+    desc = "oracle loop on %d host threads: the first %d real iteration(s) of the %dx%d solve in %.1f s" % (
+        cores, its, m, n, dt)
+    return its / dt, desc, cores
 
 
 def run_reference_arm(args, m, n):
+    """The reference's own CPU implementation of the path (the oracle port: no Rust toolchain here) on the box's
+    host cores.  One continuous run of its loop; the first `warmup` samples are untimed, the next `steps` samples
+    are timed; a sample is `k` consecutive real iterations (k sized so the whole run stays within minutes)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    desc, cores = "", 1
+    cores = os.cpu_count() or 1
+    if args.workload in ("C4", "C5"):
+        print(json.dumps({"impl": "reference", "unavailable":
+                          "the CPU port of %s is not run by this arm (C4: see the product line's cpu_baseline; C5: "
+                          "A does not fit the host)" % args.workload}), flush=True)
+        return
     pb = cpu_problem(m, n, args.seed)
-    for i in range(args.warmup + args.steps):
-        budget = 20.0 if i >= args.warmup else 5.0
-        v, desc, cores = cpu_sample(m, n, args.seed, budget_s=budget, pb=pb)
-        if i >= args.warmup:
-            vals.append(v)
-    value = float(np.mean(vals))
+    # calibrate one iteration, then choose k so that (warmup + steps) * k iterations take <= ~4 minutes
+    its1, dt1 = cpu_iterations(pb, 0.0, min_iters=1)
+    t_it = dt1 / max(1, its1)
+    n_samples = args.warmup + args.steps
+    k = int(max(1, min(8, 240.0 / max(t_it, 1e-3) / max(1, n_samples))))
+    total_its = n_samples * k
+    from oracle import ipm_oracle as o
+    stamps = []
+
+    class _Stop(Exception):
+        pass
+
+    def on_iteration(iteration, pt, ind):
+        stamps.append(time.perf_counter())
+        if iteration >= total_its:
+            raise _Stop()
+
+    t0 = time.perf_counter()
+    finished = None
+    try:
+        res = o.InteriorPoint().solve(pb, on_iteration=on_iteration)
+        finished = res.iteration
+    except _Stop:
+        pass
+    except o.LinearProgramError:
+        pass
+    done = len(stamps)
+    w_its = min(args.warmup * k, max(0, done - 1))
+    t_begin = stamps[w_its - 1] if w_its > 0 else t0
+    timed_its = done - w_its
+    dt = stamps[-1] - t_begin
+    value = timed_its / dt
+    steps_done = max(1, timed_its // k) if finished is None else args.steps
+    sample = ("oracle loop on %d host threads: %d consecutive real iterations of the %dx%d solve timed (%.1f s) after %d "
+              "untimed ones; a step is a sample of %d iteration(s)%s" % (
+                  cores, timed_its, m, n, dt, w_its, k,
+                  "" if finished is None else "; the solve converged after %d iterations inside the run" % finished))
     line = {
         "impl": "reference", "metric": "ipm_iterations_per_s", "value": value, "unit": "iterations/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / steps_done * 1e3,
+        "ms_per_iteration": 1e3 / value,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_label(args.workload, m, n, args.seed)},
-        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": desc},
+        "config": bench_config(args.workload, m, n, args.seed, args.gpus, args.potrf_dist),
+        "details": {"step": "%d real iterations of the CPU loop" % k, "iterations_timed": timed_its,
+                    "calibration_s_per_iteration": t_it},
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -234,7 +290,7 @@ def _sync_max_ms(torch, dist, ms):
     return float(t.item())
 
 
-def _roofline(prof_sum, m, n_loc):
+def _roofline(prof_sum, m, n_loc, peak_measured=None):
     """K1 roofline.  `achieved` counts the flop the kernel EXECUTES: m(m+1) * syrk_cols, where syrk_cols
     is n minus the trailing slack columns that liblpb200 folds into the diagonal of M instead of
     contracting over them (lpb_profile.syrk_cols).  SURVEY 8(d)'s algorithmic figure m(m+1)n -- what a
@@ -251,9 +307,14 @@ def _roofline(prof_sum, m, n_loc):
     return {
         "bound": "tensor", "kernel": "syrk_dmma_kernel (K1, A.diag(x/z).A^T, FP64 DMMA)",
         "achieved": achieved, "peak": NOMINAL_FP64_TFLOPS, "unit": "TFLOP/s",
-        "frac": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None, "traffic": SYRK_TRAFFIC.get((m, int(n_exec))),
-        "peak_source": "nominal B200 FP64 (MEASURED_PEAKS.json has no FP64 entry; measured on this pool: DMMA issue "
-                       "peak 36.95, cuBLAS DGEMM 35.4 TFLOP/s, profiles/fp64_peaks_r01.json)",
+        "frac": (achieved / NOMINAL_FP64_TFLOPS) if achieved else None,
+        "traffic": SYRK_TRAFFIC.get((m, int(n_exec)), (None, None))[0],
+        "traffic_source": SYRK_TRAFFIC.get((m, int(n_exec)), (None, None))[1],
+        "peak_source": "nominal B200 FP64 (MEASURED_PEAKS.json has no FP64 entry)",
+        "peak_measured": peak_measured,
+        "peak_measured_source": "DMMA issue peak measured in this run (lpb_measure_dmma_peak: register-only "
+                                "mma.sync.m8n8k4.f64 loop on every SM, ~0.3 s)",
+        "frac_of_measured": (achieved / peak_measured) if (achieved and peak_measured) else None,
         "flop_per_launch": f_syrk, "ms_per_launch": syrk_ms, "syrk_cols": n_exec,
         "algorithmic_flop_per_launch": f_alg,
         "algorithmic_tflops": (f_alg / (syrk_ms * 1e-3) * 1e-12) if syrk_ms > 0 else None,
@@ -270,8 +331,57 @@ SYRK_TRAFFIC = {
     # C3 on 1 GPU, banded tile order: 46.05 GB read + 1.08 GB written (profiles/ncu_syrk_C3_r01_v14.txt);
     # algorithmic bytes: 3.22 GB of A (dense columns) + 1.07 GB of M.  The kernel is DMMA-bound (DRAM at 3 %
     # of peak); the re-reads are operand tiles streamed once per wave of 148 tiles.
-    (16384, 24576): 46.048303e9 + 1.082822e9,
+    # NOT measured in the run (ncu cannot run inside a timed bench): the value of the committed capture.
+    (16384, 24576): (46.048303e9 + 1.082822e9, "profiles/ncu_syrk_C3_r01_v14.txt (ncu --set full, one launch)"),
 }
+
+
+def measure_peak(rp):
+    """DMMA issue peak of this GPU, measured now through the library (None if the call fails)."""
+    from lp_b200 import _ffi
+    out = C.c_double(0.0)
+    rc = _ffi.load().lpb_measure_dmma_peak(rp.handle, C.c_double(0.3), C.byref(out))
+    return float(out.value) if rc == 0 and out.value > 0 else None
+
+
+C5_RECORD_ITERS = 3
+
+
+def c5_record(args, torch, dist, rank, world, stream):
+    """Config C5 (32768 x 131072, A generated on the device per column shard) for C5_RECORD_ITERS iterations at
+    this N: per-iteration time and phases.  Rides along in every product line so the scaling run shows the
+    configuration the north star quotes the multi-GPU target on (its full solve is `--workload C5`)."""
+    import lp_b200
+    from lp_b200.api import SyntheticShardedProblem
+    m5, n5 = WORKLOADS["C5"]
+    solver = lp_b200.InteriorPoint.custom().max_iter(C5_RECORD_ITERS).build()
+    rec = None
+    try:
+        with SyntheticShardedProblem(m5, n5, args.seed, rank, world, dist, stream=stream) as sp:
+            sp.set_option("potrf_dist", args.potrf_dist)
+            status = "IterationLimitExceeded"
+            try:
+                solver.solve_resident(sp)
+                status = "Optimal"
+            except lp_b200.IterationLimitExceeded:
+                pass
+            p = sp.profile()
+            n_loc = sp.n
+        its = max(1, int(p["iterations"]))
+        ms = _sync_max_ms(torch, dist, p["total_ms"])
+        f_syrk = float(m5) * (m5 + 1) * p["syrk_cols"]
+        rec = {"workload": bench_config("C5", m5, n5, args.seed, world, args.potrf_dist)["workload"],
+               "n_gpus": world, "iterations": its, "status_after_%d_iterations" % C5_RECORD_ITERS: status,
+               "ms_per_iteration": ms / its, "iterations_per_s": its / (ms * 1e-3),
+               "phases_ms_per_iteration": {k: p[k] / its for k in ("syrk_ms", "potrf_ms", "solve_ms", "sweep_ms",
+                                                                   "vector_ms", "comm_ms")},
+               "syrk_tflops_this_gpu": (f_syrk / (p["syrk_ms"] / max(1, p["syrk_launches"]) * 1e-3) * 1e-12
+                                        if p["syrk_ms"] > 0 else None),
+               "a_shard_gb": m5 * n_loc * 8 / 1e9,
+               "note": "times include the blind-start residuals; CUDA events on the launching stream, max over ranks"}
+    except Exception as e:  # noqa: BLE001 -- the record must never take the headline line down with it
+        rec = {"error": "%s: %s" % (type(e).__name__, e)}
+    return rec
 
 
 def _timed_solves(args, torch, dist, solver, rp, local_rank):
@@ -316,6 +426,7 @@ def run_device_synthetic(args, torch, dist, rank, local_rank, world, stream, m, 
     gen_s = time.perf_counter() - t0
     ms, total_iters, launches, prof_sum, clocks, res = _timed_solves(args, torch, dist, solver, rp, local_rank)
     value = total_iters / (ms * 1e-3)
+    peak_holder = [measure_peak(rp) if rank == 0 else None]
     rp.close()
     # e2e: context creation + on-device generation of the shard + solve + D2H / gather of x
     e2e = None
@@ -334,24 +445,21 @@ def run_device_synthetic(args, torch, dist, rank, local_rank, world, stream, m, 
                "d2h_bytes_per_step": int(rp.n * 8 + 16), "ms_per_step": dt / args.steps * 1e3,
                "note": "inputs are generated on the device (the %.1f GB matrix never exists on the host); "
                        "the timed region covers generation + solve + D2H of x" % (m * n * 8 / 1e9)}
+    n_loc = rp.n
     if rank == 0:
-        n_loc = rp.n
         steps = args.steps
         phases = {k: prof_sum.get(k, 0.0) / steps for k in
                   ("total_ms", "syrk_ms", "potrf_ms", "solve_ms", "sweep_ms", "vector_ms", "comm_ms")}
         line = {
             "metric": "ipm_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "ms_per_iteration": ms / max(1, total_iters), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s dense LP slack-form m=%d n=%d seed=%d, generated on the device per column "
-                                   "shard (counter-based N(0,1), SURVEY 8d construction)" % (args.workload, m, n, args.seed),
-                       "iterations_per_solve": total_iters / args.steps, "objective": res.fun(),
-                       "l2": "inputs larger than L2 (A shard = %.0f MB)" % (m * n_loc * 8 / 1e6),
-                       "parallelism": "1 GPU" if world == 1 else
-                       "A column-sharded over %d GPUs, NCCL all-reduce of M, %s Cholesky" % (
-                           world, "panel-broadcast distributed" if args.potrf_dist else "replicated"),
-                       "device_generation_s": gen_s},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": _roofline(prof_sum, m, n_loc),
+            "config": bench_config(args.workload, m, n, args.seed, world, args.potrf_dist),
+            "details": {"iterations_per_solve": total_iters / args.steps, "objective": res.fun(),
+                        "device_generation_s": gen_s, "step": "one complete solve (blind start -> Optimal)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": _roofline(prof_sum, m, n_loc, peak_holder[0]),
             "phases_ms_per_solve": phases, "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)
@@ -448,13 +556,10 @@ def run_batched(args, torch, dist, rank, local_rank, world, stream):
             "metric": "ipm_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C4 batched: %d independent dense LPs slack-form m=%d n=%d, seeds 1000+i, one CTA "
-                                   "per problem" % (batch, m, n),
-                       "lps_per_s": batch * args.steps / (ms * 1e-3), "optimal": int(n_ok.item()),
-                       "iterations_per_lp": total_iters / batch,
-                       "l2": "whole batch (%.0f MB) larger than L2" % (batch * bytes_per_lp / 1e6),
-                       "parallelism": "batch sharded over %d GPU(s), no collective" % world,
-                       "host_generation_s": gen_s},
+            "config": dict(bench_config("C4", m, n, args.seed, world),
+                           l2="whole batch (%.0f MB) larger than L2" % (batch * bytes_per_lp / 1e6)),
+            "details": {"lps_per_s": batch * args.steps / (ms * 1e-3), "optimal": int(n_ok.item()), "batch": batch,
+                        "iterations_per_lp": total_iters / batch, "host_generation_s": gen_s},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(args.steps),
             "roofline": {"bound": "hbm", "kernel": "batched_ipm_kernel (K6): latency / shared-memory bound; HBM only "
                                                    "for the one-time load of each LP",
@@ -493,6 +598,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the short C5 record that rides along with the C3 line")
     ap.add_argument("--device-synthetic", action="store_true",
                     help="generate the LP on the device per column shard (always on for C5)")
     ap.add_argument("--batch", type=int, default=C4_BATCH)
@@ -586,6 +692,7 @@ def main():
     value = total_iters / (ms * 1e-3)
     fun = res.fun()
     n_loc_rank = rp.n
+    peak_measured = measure_peak(rp) if rank == 0 else None
 
     # ---- e2e through the public API (host buffers, H2D + D2H inside the timed region)
     e2e = None
@@ -622,8 +729,14 @@ def main():
                "h2d_bytes_per_step": int((m * (n // world) + m + n // world) * 8),
                "d2h_bytes_per_step": int((n // world) * 8 + 16), "ms_per_step": dt / args.steps * 1e3}
 
+    # ---- C5 record (device-generated, 3 iterations) at this N: after the headline numbers, nothing above depends on it
+    c5 = None
+    if not args.no_c5 and args.workload == DEFAULT_WORKLOAD:
+        torch.cuda.empty_cache()
+        c5 = c5_record(args, torch, dist, rank, world, stream)
+
     if rank == 0:
-        roofline = _roofline(prof_sum, m, n_loc_rank)
+        roofline = _roofline(prof_sum, m, n_loc_rank, peak_measured)
         steps = args.steps
         phases = {k: prof_sum.get(k, 0.0) / steps for k in
                   ("total_ms", "syrk_ms", "potrf_ms", "solve_ms", "sweep_ms", "vector_ms", "comm_ms")}
@@ -633,16 +746,14 @@ def main():
             cpu = {"value": v, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": desc}
         line = {
             "metric": "ipm_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "ms_per_iteration": ms / max(1, total_iters), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_label(args.workload, m, n, args.seed),
-                       "iterations_per_solve": total_iters / args.steps,
-                "objective": fun, "l2": "inputs larger than L2 (A = %.0f MB)" % (m * n * 8 / 1e6),
-                "parallelism": "1 GPU" if world == 1 else "A column-sharded over %d GPUs, NCCL all-reduce of M, %s Cholesky" % (
-                           world, "panel-broadcast distributed" if args.potrf_dist else "replicated"),
-                "host_generation_s": gen_s},
+            "config": bench_config(args.workload, m, n, args.seed, world, args.potrf_dist),
+            "details": {"iterations_per_solve": total_iters / args.steps, "objective": fun, "host_generation_s": gen_s,
+                        "step": "one complete solve (blind start -> Optimal)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "phases_ms_per_solve": phases, "cpu_baseline": cpu,
+            "phases_ms_per_solve": phases, "cpu_baseline": cpu, "c5": c5,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -246,11 +246,17 @@ typedef struct lpb_profile {
                            which are folded into the diagonal of M (executed flop = m (m + 1) syrk_cols) */
 } lpb_profile;
 int lpb_get_profile(lpb_ctx* ctx, lpb_profile* out);
+/* FP64 tensor (DMMA) ISSUE peak of the device this context lives on, measured now: a register-only loop of
+ * independent mma.sync.m8n8k4.f64 (32 accumulator fragments per warp, 8 warps per SM, every SM) run back to
+ * back for about `seconds` (0.05 .. 2) on the context's stream.  bench.py reports it as roofline.peak_measured
+ * beside the nominal 40 TFLOP/s (MEASURED_PEAKS.json carries no FP64 figure).  No reference counterpart. */
+int lpb_measure_dmma_peak(lpb_ctx* ctx, double seconds, double* tflops_out);
 /* Kernels launched by this library on this context since creation (all entry points). */
 int64_t lpb_launch_count(lpb_ctx* ctx);
 /* Tuning / debug knobs.  "syrk_impl": 0 = DMMA+TMA, 1 = plain DFMA reference kernels (parity tests
- * bisect with it); "solve_impl": 0 = pipelined single-launch solve, 1 = one launch per 128-block
- * step; "solve_grid_cap": > 0 caps the pipelined solve's grid (tests: several block rows per CTA);
+ * bisect with it); "solve_impl": 0 = single-launch pipelined solve (tagged hand-off, full block inverses),
+ * 1 = one launch per 128-block step, 2 = plain substitution, 3 = the flag-based pipelined solve with blocked
+ * substitution; "refine": iterative-refinement steps per sym_solve (default 1); "solve_grid_cap": > 0 caps the pipelined solve's grid (tests: several block rows per CTA);
  * "profile": 1 = record per-phase events; "structure": 0 = contract the SYRK over every column of A
  * (default 1: trailing singleton columns -- the slack block -- are folded into the diagonal of M).  Unknown key -> BAD_ARGUMENT. */
 int lpb_set_option(lpb_ctx* ctx, const char* key, int64_t value);

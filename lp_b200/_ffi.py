@@ -123,6 +123,7 @@ SIGNATURES = {
     "lpb_release_workspaces": (C.c_int, []),
     "lpb_get_profile": (C.c_int, [C.c_void_p, C.POINTER(lpb_profile)]),
     "lpb_launch_count": (C.c_int64, [C.c_void_p]),
+    "lpb_measure_dmma_peak": (C.c_int, [C.c_void_p, C.c_double, c_double_p]),
     "lpb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "lpb_debug_read": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
 }

@@ -525,6 +525,54 @@ int k_trsm_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, 
   return launch_dmma<MODE_TRSM, false>(lc, tm, tl, Mat, ldm, (int)m, (int)(row0 / BM), ntr, (int)k0, BN / BK, (int)k0);
 }
 
+// ------------------------------------------------------------------ DMMA issue peak (measurement only)
+__global__ void __launch_bounds__(256)
+dmma_peak_kernel(double* out, int iters, double a0, double b0) {
+  double c[32][2];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) c[i][0] = c[i][1] = threadIdx.x * 1e-3 + i;
+  const double a = a0 + threadIdx.x * 1e-9, b = b0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;  // keeps the loop alive; never true in practice
+}
+
+int k_dmma_peak(LaunchCtx& lc, double seconds, double* tflops) {
+  if (seconds < 0.05) seconds = 0.05;
+  if (seconds > 2.0) seconds = 2.0;
+  const int iters = 4000;
+  const double flop_per_launch = 2.0 * 256 * 32 * iters * 8.0 * kNumSMs;  // m8n8k4 = 256 MAC per warp instruction
+  cudaEvent_t e0, e1;
+  LPB_CUDA(cudaEventCreate(&e0));
+  LPB_CUDA(cudaEventCreate(&e1));
+  auto run = [&](int launches, float* ms) -> int {
+    LPB_CUDA(cudaEventRecord(e0, lc.stream));
+    for (int i = 0; i < launches; ++i) dmma_peak_kernel<<<kNumSMs, 256, 0, lc.stream>>>(lc.red_partials, iters, 1.0000001, 1e-9);
+    LPB_CUDA(cudaEventRecord(e1, lc.stream));
+    LPB_CUDA(cudaEventSynchronize(e1));
+    LPB_CUDA(cudaEventElapsedTime(ms, e0, e1));
+    lc.launches += launches;
+    return LPB_OK;
+  };
+  float ms = 0.f;
+  int rc = run(4, &ms);  // warm-up + calibration (~2 ms per launch)
+  if (rc == LPB_OK) {
+    int launches = (int)(seconds * 1e3 / (ms / 4.0 > 1e-3 ? ms / 4.0 : 1e-3));
+    if (launches < 8) launches = 8;
+    if (launches > 4000) launches = 4000;
+    rc = run(launches, &ms);
+    if (rc == LPB_OK && tflops) *tflops = flop_per_launch * launches / (ms * 1e-3) * 1e-12;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
+
 // ------------------------------------------------------------------ plain DFMA reference kernel
 // Used by the parity tests to bisect the DMMA/TMA kernel; never selected by default.
 template <bool ACCUM>

@@ -92,6 +92,8 @@ int k_trailing_update_part(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, i
                            int single_col, int own_mod, int own_rem);
 // panel TRSM as a DMMA GEMM with the inverted 128 x 128 diagonal block (dense, ld 128)
 int k_trsm_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, const double* Linv);
+// DMMA issue peak: register-only loop of independent DMMAs on every SM for ~seconds; TFLOP/s out
+int k_dmma_peak(LaunchCtx& lc, double seconds, double* tflops);
 // plain DFMA reference kernels (tests / bisecting only)
 int k_syrk_simple(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t lda, const double* d, double* Cmat,
                   int64_t ldc);

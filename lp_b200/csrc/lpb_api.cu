@@ -10,7 +10,9 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <new>
 #include <string>
@@ -643,6 +645,13 @@ int upload_problem(lpb_ctx* c, const double* A, int64_t lda, const double* b, co
                                kind, c->lc.stream));
   LPB_CUDA(cudaMemcpyAsync(c->b, b, sizeof(double) * c->m, kind, c->lc.stream));
   LPB_CUDA(cudaMemcpyAsync(c->c, cc, sizeof(double) * c->n, kind, c->lc.stream));
+  if (std::getenv("LPB_TIME_CREATE")) {
+    const auto t0 = std::chrono::steady_clock::now();
+    LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::fprintf(stderr, "[upload] copies drained in %.1f ms after issue (%.1f GB/s)\n", ms,
+                 8.0 * c->m * c->n / (ms * 1e-3) / 1e9);
+  }
   LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
   c->c0 = c0;
   c->has_problem = true;
@@ -815,9 +824,19 @@ int lpb_create(lpb_ctx** out, int64_t m, int64_t n, const double* A, int64_t lda
   LPB_TRY(check_device());
   lpb_ctx* c = new (std::nothrow) lpb_ctx();
   if (!c) return LPB_ERR_BAD_ARGUMENT;
+  const bool timing = std::getenv("LPB_TIME_CREATE") != nullptr;  // stage times of the e2e path, to stderr
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   int rc = ctx_base_init(c, stream);
   if (rc == LPB_OK) rc = ctx_alloc_vectors(c, m, n, true);
+  if (timing && rc == LPB_OK) cudaStreamSynchronize(c->lc.stream);
+  const double t1 = now();
   if (rc == LPB_OK) rc = upload_problem(c, A, lda, b, cc, c0, mem);
+  const double t2 = now();
+  if (timing)
+    std::fprintf(stderr, "[lpb_create %lldx%lld] alloc+memset %.1f ms, upload+structure %.1f ms (%.1f GB/s incl. the "
+                 "structure scan)\n", (long long)m, (long long)n, t1 - t0, t2 - t1,
+                 8.0 * m * n / ((t2 - t1) * 1e-3) / 1e9);
   if (rc != LPB_OK) {
     ctx_free(c);
     return rc;
@@ -1245,6 +1264,11 @@ int lpb_get_profile(lpb_ctx* c, lpb_profile* out) {
 }
 
 int64_t lpb_launch_count(lpb_ctx* c) { return c ? c->lc.launches : 0; }
+
+int lpb_measure_dmma_peak(lpb_ctx* c, double seconds, double* tflops_out) {
+  if (!c || !tflops_out) return LPB_ERR_BAD_ARGUMENT;
+  return k_dmma_peak(c->lc, seconds, tflops_out);
+}
 
 int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
   if (!c || !key) return LPB_ERR_BAD_ARGUMENT;

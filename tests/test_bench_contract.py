@@ -18,8 +18,13 @@ def test_reference_arm_prints_one_json_line_for_the_smallest_config():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "ipm_iterations_per_s" and d["unit"] == "iterations/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
-    assert d["value"] > 0 and abs(d["ms_per_step"] - 1000.0 / d["value"]) < 1e-6
+    assert d["value"] > 0 and abs(d["ms_per_iteration"] - 1000.0 / d["value"]) < 1e-6 and d["ms_per_step"] > 0
+    assert d["details"]["iterations_timed"] >= 1          # REAL iterations of the oracle's loop, not a cost model
+    assert "real iterations" in d["cpu_baseline"]["sample"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.bench_config("C1", 512, 1024, 0, 1)    # the product arm prints the same dict
     assert d["e2e"] == {"value": d["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "C1" in d["config"]["workload"] and d["dtype"] == "f64" and d["vs_baseline"] is None
 
@@ -44,5 +49,17 @@ def test_roofline_counts_executed_flop():
     assert abs(r["achieved"] - m * (m + 1) * 24576.0 / 0.190 * 1e-12) < 1e-9
     assert abs(r["frac"] - r["achieved"] / 40.0) < 1e-12
     assert r["algorithmic_tflops"] > r["achieved"]                       # structure-blind count, reported beside it
-    assert r["traffic"] == bench.SYRK_TRAFFIC[(m, 24576)]                # ncu capture of this exact shape
+    assert r["traffic"] == bench.SYRK_TRAFFIC[(m, 24576)][0]             # ncu capture of this exact shape ...
+    assert r["traffic_source"].startswith("profiles/")                   # ... labelled as such, not measured in the run
     assert bench._roofline(prof, 4096, 8192)["traffic"] is None          # no capture -> null, not a guess
+    rm = bench._roofline(prof, m, n, peak_measured=36.9)
+    assert rm["peak"] == 40.0 and rm["peak_measured"] == 36.9 and abs(rm["frac_of_measured"] - rm["achieved"] / 36.9) < 1e-12
+
+
+def test_both_arms_share_one_config_dict():
+    sys.path.insert(0, ROOT)
+    import bench
+    for wl, (m, n) in bench.WORKLOADS.items():
+        for world in (1, 8):
+            c = bench.bench_config(wl, m, n, 0, world)
+            assert set(c) == {"workload", "parallelism", "l2"} and wl in c["workload"]
