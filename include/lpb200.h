@@ -265,6 +265,10 @@ int lpb_set_option(lpb_ctx* ctx, const char* key, int64_t value);
  * "x" "z" "c" "rD" "dinv" "dx" "dz" "p" "u", m-vectors "b" "y" "rP" "dy", "t" / "W" (2 m).  Returns the
  * number of doubles the buffer holds (-1: unknown name) and copies min(count, that) of them. */
 int64_t lpb_debug_read(lpb_ctx* ctx, const char* name, double* out, int64_t count);
+/* Named debug counters of the context: "potrf_verify_runs" / "potrf_verify_mismatches" (option "potrf_verify" = 1
+ * factors every M twice and compares the two factors bit for bit: a mismatch is a race), "refactorisations"
+ * (option "regularize": factorisations repeated with a diagonal shift).  -1: unknown name. */
+int64_t lpb_debug_counter(lpb_ctx* ctx, const char* name);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

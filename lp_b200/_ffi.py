@@ -126,6 +126,7 @@ SIGNATURES = {
     "lpb_measure_dmma_peak": (C.c_int, [C.c_void_p, C.c_double, c_double_p]),
     "lpb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "lpb_debug_read": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "lpb_debug_counter": (C.c_int64, [C.c_void_p, C.c_char_p]),
 }
 
 _lib = None

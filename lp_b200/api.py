@@ -163,10 +163,16 @@ def _as_f64(a, ndim):
 class Problem:
     """A linear program in slack form: min c'x st A x == b, x >= 0 (linear_program.rs:24-30)."""
 
-    def __init__(self, A_buf, b_buf, c_buf, c0: float, n_slack: int):
+    def __init__(self, A_buf, b_buf, c_buf, c0: float, n_slack: int, dtype=np.float64):
         self._A, self._b, self._c = A_buf, b_buf, c_buf
         self._c0 = float(c0)
         self._n_slack = int(n_slack)
+        # `Problem<f32>` of the reference (float.rs:43): the slack form is held and solved in FP64 on the B200
+        # path (inputs are widened at build); only the RESULT is narrowed back to the caller's float type.
+        self._dtype = np.dtype(dtype)
+
+    def dtype(self) -> np.dtype:
+        return self._dtype
 
     @staticmethod
     def target(c) -> "ProblemBuilder":
@@ -214,6 +220,8 @@ class ProblemBuilder:
     def build(self) -> Problem:
         """Validate + convert to slack form [[A_ub, I], [A_eq, 0]] (linear_program.rs:125-169)."""
         lib = _ffi.load()
+        given = [self._c] + [a for pair in (self._ub, self._eq) if pair is not None for a in pair]
+        all_f32 = all(isinstance(a, np.ndarray) and a.dtype == np.float32 for a in given)
         c = _as_f64(self._c, 1)
         n_c = c.shape[0]
 
@@ -241,7 +249,7 @@ class ProblemBuilder:
             b_eq.ctypes.data if b_eq.size else None, b_eq.shape[0],
             A_buf.array.ctypes.data, n.value, b_buf.array.ctypes.data, c_buf.array.ctypes.data)
         _raise_for(rc)
-        return Problem(A_buf, b_buf, c_buf, 0.0, ns.value)
+        return Problem(A_buf, b_buf, c_buf, 0.0, ns.value, np.float32 if all_f32 else np.float64)
 
 
 # --------------------------------------------------------------------------- solver config
@@ -359,6 +367,9 @@ class InteriorPoint(Solver):
             x_slack = rp.gather_x(x_slack)
         _raise_for(rc, x_slack)
         x = np.array(x_slack[: len(x_slack) - rp.n_slack])  # denormalize_x_into, linear_program.rs:65-69
+        dt = getattr(rp, "result_dtype", np.dtype(np.float64))
+        if dt != np.float64:  # Problem<f32>: FP64 arithmetic, result narrowed to the caller's float type
+            return OptimizeResult(x.astype(dt), float(dt.type(fun.value)), it.value)
         return OptimizeResult(x, fun.value, it.value)
 
 
@@ -370,6 +381,7 @@ class ResidentProblem:
         A = problem.A()
         self.m, self.n = A.shape
         self.n_slack = problem.n_slack()
+        self.result_dtype = problem.dtype()
         self.last_iterations = 0
         h = C.c_void_p()
         rc = lib.lpb_create(C.byref(h), self.m, self.n, A.ctypes.data, self.n, problem.b().ctypes.data,
@@ -401,6 +413,9 @@ class ResidentProblem:
         out = np.empty(n)
         lib.lpb_debug_read(self.handle, name.encode(), out.ctypes.data, n)
         return out
+
+    def debug_counter(self, name: str) -> int:
+        return int(_ffi.load().lpb_debug_counter(self.handle, name.encode()))
 
     def trace(self) -> np.ndarray:
         rows = np.zeros((max(1, self.last_iterations + 1), _ffi.LPB_TRACE_COLS))

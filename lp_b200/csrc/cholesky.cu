@@ -1164,6 +1164,45 @@ __device__ __forceinline__ double ld_tagged(const Tagged* p, uint32_t tag, unsig
   return ld_tagged_slow(p, tag, fault, relaxed);
 }
 
+// Poll NQ x K tagged words (K consecutive entries for each of NQ right-hand sides, `qstride` entries apart) until
+// every tag matches.  All loads of a round are issued back to back and checked together: one L2 round trip per
+// round, however many words (a load-check-branch per word would serialise the round trips -- measured: 8 words
+// cost 4 us of a 5 us chain step).
+template <int NQ, int K>
+__device__ __forceinline__ void poll_tagged(const Tagged* p, int qstride, uint32_t tag, unsigned long long* fault,
+                                            double (&v)[NQ][K]) {
+  unsigned spins = 0;
+  unsigned long long t0 = 0ull;
+  for (;;) {
+    uint32_t r[NQ][K][4];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int e = 0; e < K; ++e)
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[q][e][0]), "=r"(r[q][e][1]), "=r"(r[q][e][2]), "=r"(r[q][e][3])
+                     : "l"(p + q * qstride + e)
+                     : "memory");
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int e = 0; e < K; ++e) {
+        ok = ok && r[q][e][1] == tag && r[q][e][3] == tag;
+        v[q][e] = __hiloint2double((int)r[q][e][2], (int)r[q][e][0]);
+      }
+    if (ok) return;
+    if ((++spins & 63u) == 0) {
+      if (t0 == 0ull) t0 = global_ns();
+      if (*reinterpret_cast<volatile unsigned long long*>(fault) != 0ull) return;
+      if (global_ns() - t0 > 20000000000ull) {
+        atomicExch(fault, 1ull);
+        return;
+      }
+    }
+  }
+}
+
 constexpr int XP = NB + 2;  // 130 = 2 mod 16: two threads per row (even / odd columns) read X_j conflict-free
 constexpr size_t kSolveLLSmem = (size_t)(NB * XP + 2 * NB + 8 * 2 * NB) * sizeof(double);
 
@@ -1183,17 +1222,20 @@ __device__ __forceinline__ void stage_inverse(const double* __restrict__ Xj, dou
   }
 }
 
-// y = T c for the staged 128 x 128 matrix T (X_j or X_j^T): thread (row = tid >> 1, h = tid & 1) takes the columns
-// = h mod 2; four independent chains per right-hand side; the two halves meet in one shuffle.
-template <int NRHS>
+// y = T c for the staged 128 x 128 triangular matrix T (X_j: lower, or X_j^T: upper): thread (row = tid >> 1,
+// h = tid & 1) takes the columns = h mod 2; four independent chains per right-hand side; the two halves meet in one
+// shuffle.  A warp owns 16 consecutive rows and only walks the 16-column groups that hold non-zeros for them
+// (reading X_j out of shared memory is what bounds this step: 128 bytes per clock per SM).
+template <int NRHS, bool UPPER>
 __device__ __forceinline__ void block_gemv(const double* sX, const double* sc, int tid, double (&out)[NRHS]) {
-  const int r = tid >> 1, h = tid & 1;
+  const int r = tid >> 1, h = tid & 1, wrow = (tid >> 5) * 16;
   const double* xr = sX + r * XP + h;
   double s[NRHS][4];
 #pragma unroll
   for (int q = 0; q < NRHS; ++q) s[q][0] = s[q][1] = s[q][2] = s[q][3] = 0.0;
-#pragma unroll 4
-  for (int i = 0; i < NB / 2; i += 4) {
+  const int i_lo = UPPER ? wrow / 2 : 0, i_hi = UPPER ? NB / 2 : (wrow + 16) / 2;
+#pragma unroll 2
+  for (int i = i_lo; i < i_hi; i += 4) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const double xv = xr[2 * (i + e)];
@@ -1247,17 +1289,23 @@ solve_ll_kernel(const double* __restrict__ L, int64_t ldm, const double* __restr
       }
     };
     if (j > 0) load_block(0);
+    // b_j is fetched now: its L2 latency must not sit between the last product and the block solve
+    double bj[NRHS];
+    {
+      const int rr = warp * 16 + (lane >> 1);
+#pragma unroll
+      for (int q = 0; q < NRHS; ++q) bj[q] = (rr < nbj) ? B[(int64_t)q * m + r0 + rr] : 0.0;
+    }
     for (int k = 0; k < j; ++k) {
-      const bool relaxed = k + 1 < j;
       const Tagged* wk = Wt + (int64_t)k * NRHS * NB;
-      // one sentinel poll per warp keeps the L2 polling traffic of the ~1000 waiting warps small
-      if (lane == 0) (void)ld_tagged(wk, epoch, fault, relaxed);
-      __syncwarp();
+      if (k + 1 < j) {
+        // far from the chain: one backed-off sentinel poll per warp keeps the L2 polling traffic of the ~1000
+        // waiting warps small; the block next in the chain (k == j - 1) polls its words directly
+        if (lane == 0) (void)ld_tagged(wk, epoch, fault, true);
+        __syncwarp();
+      }
       double w[NRHS][4];
-#pragma unroll
-      for (int q = 0; q < NRHS; ++q)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) w[q][e] = ld_tagged(wk + q * NB + c4 + e, epoch, fault, false);
+      poll_tagged<NRHS, 4>(wk + c4, NB, epoch, fault, w);
 #pragma unroll
       for (int i = 0; i < 16; ++i)
 #pragma unroll
@@ -1270,11 +1318,11 @@ solve_ll_kernel(const double* __restrict__ L, int64_t ldm, const double* __restr
     for (int q = 0; q < NRHS; ++q) {
       const double tot = fold16(acc[q], lane);
       const int rr = warp * 16 + (lane >> 1);
-      if ((lane & 1) == 0) sc[q * NB + rr] = (rr < nbj) ? B[(int64_t)q * m + r0 + rr] - tot : 0.0;
+      if ((lane & 1) == 0) sc[q * NB + rr] = bj[q] - tot;
     }
     __syncthreads();  // c_j and X_j are in shared memory
     double wj[NRHS];
-    block_gemv<NRHS>(sX, sc, tid, wj);
+    block_gemv<NRHS, false>(sX, sc, tid, wj);
     if ((tid & 1) == 0) {
 #pragma unroll
       for (int q = 0; q < NRHS; ++q) st_tagged(Wt + ((int64_t)j * NRHS + q) * NB + (tid >> 1), wj[q], epoch);
@@ -1306,14 +1354,22 @@ solve_ll_kernel(const double* __restrict__ L, int64_t ldm, const double* __restr
       }
     };
     if (j + 1 < nblk) load_block(nblk - 1);
+    // w_j (from the forward owner of block j, long done except for the very first backward blocks) is fetched
+    // now, off the chain
+    double wjv[1][1] = {{0.0}};
+    if (tid < NRHS * NB)
+      poll_tagged<1, 1>(Wt + ((int64_t)j * NRHS + (tid >> 7)) * NB + (tid & (NB - 1)), 0, epoch, fault, wjv);
     for (int k = nblk - 1; k > j; --k) {
-      const bool relaxed = k - 1 > j;
       // lane (i = lane & 15, q = lane >> 4) fetches x_k[16 warp + i] of right-hand side q; shuffles hand it round
       const int qi = (NRHS == 2) ? (lane >> 4) : 0;
       const Tagged* xk = Xt + ((int64_t)k * NRHS + qi) * NB + warp * 16 + (lane & 15);
-      if (lane == 0) (void)ld_tagged(xk, epoch, fault, relaxed);
-      __syncwarp();
-      const double mine = ld_tagged(xk, epoch, fault, false);
+      if (k - 1 > j) {
+        if (lane == 0) (void)ld_tagged(xk, epoch, fault, true);
+        __syncwarp();
+      }
+      double mine_v[1][1];
+      poll_tagged<1, 1>(xk, 0, epoch, fault, mine_v);
+      const double mine = mine_v[0][0];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
 #pragma unroll
@@ -1335,7 +1391,7 @@ solve_ll_kernel(const double* __restrict__ L, int64_t ldm, const double* __restr
     __syncthreads();
     if (tid < NRHS * NB) {  // c = w_j - sum over the 8 warps (w_j comes from the forward owner of block j)
       const int q = tid >> 7, c = tid & (NB - 1);
-      const double wv = ld_tagged(Wt + ((int64_t)j * NRHS + q) * NB + c, epoch, fault, false);
+      const double wv = wjv[0][0];
       double sum = 0.0;
 #pragma unroll
       for (int w = 0; w < 8; ++w) sum += sred[(w * 2 + q) * NB + c];
@@ -1343,7 +1399,7 @@ solve_ll_kernel(const double* __restrict__ L, int64_t ldm, const double* __restr
     }
     __syncthreads();
     double xj[NRHS];
-    block_gemv<NRHS>(sX, sc, tid, xj);
+    block_gemv<NRHS, true>(sX, sc, tid, xj);
     if ((tid & 1) == 0) {
       const int c = tid >> 1;
 #pragma unroll
@@ -1534,10 +1590,11 @@ int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
     lc.ws_m = m;
   }
   LPB_CUDA(cudaMemsetAsync(lc.info_dev, 0, sizeof(int), lc.stream));
-  if (lc.world > 1 && lc.nccl_comm && lc.potrf_dist && syrk_impl == 0 && lc.trsm_impl == 0 && lc.update_impl == 0 &&
+  const bool dmma_update = lc.update_impl == 0 || lc.update_impl == 2;
+  if (lc.world > 1 && lc.nccl_comm && lc.potrf_dist && syrk_impl == 0 && lc.trsm_impl == 0 && dmma_update &&
       m > NB && !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mat) & 15))
     return k_potrf_dist(lc, m, Mat, ldm);
-  if (lc.potrf_lookahead && syrk_impl == 0 && lc.trsm_impl == 0 && lc.update_impl == 0 &&
+  if (lc.potrf_lookahead && syrk_impl == 0 && lc.trsm_impl == 0 && dmma_update &&
       !lc.sync_each_launch && m > 2 * NB && !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mat) & 15))
     return k_potrf_lookahead(lc, m, Mat, ldm);
   const int full_inverse = lc.trsm_impl == 2 ? 1 : 0;  // the solves complete the inverses themselves (finish_factor)

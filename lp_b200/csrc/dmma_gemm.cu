@@ -499,14 +499,13 @@ int k_trailing_update_part(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, i
   }
   CUtensorMap tm;
   LPB_TRY(make_tmap(&tm, Mat, (uint64_t)m, (uint64_t)m, (uint64_t)ldm, BM, BK, true));
-  if (single_col)
-    return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, (int)k0, (int)(kb / BK), 0,
-                                           SHAPE_COL);
-  if (own_mod <= 1)
-    return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, (int)k0, (int)(kb / BK), 0);
-  const OwnedCols own = OwnedCols::make(own_mod, own_rem, tile0, ntr);
-  return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, (int)k0, (int)(kb / BK), 0,
-                                         SHAPE_OWNED, own);
+  const int shape = single_col ? SHAPE_COL : (own_mod <= 1 ? SHAPE_TRI : SHAPE_OWNED);
+  const OwnedCols own = shape == SHAPE_OWNED ? OwnedCols::make(own_mod, own_rem, tile0, ntr) : OwnedCols{1, 0, 0};
+  if (lc.update_impl == 2)  // products accumulated from zero, C read-modify-written once per panel (see VAR)
+    return launch_dmma<MODE_UPDATE, false, 1>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, (int)k0, (int)(kb / BK), 0, shape,
+                                              own);
+  return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, (int)k0, (int)(kb / BK), 0, shape,
+                                         own);
 }
 
 // Panel TRSM as a GEMM: Mat[row0.., k0..k0+128) <- Mat[row0.., k0..k0+128) * Linv^T, row0 = k0 + 128,

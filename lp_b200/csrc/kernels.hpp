@@ -119,6 +119,8 @@ int k_add_vec(LaunchCtx& lc, double* out, const double* a, const double* b, int6
 int k_col_structure(LaunchCtx& lc, const double* A, int64_t m, int64_t n, int64_t lda, int* nnz, int* row, double* val);
 // M[r][r] += val[r]^2 * dinv[col[r]] where col[r] >= 0 (singleton columns folded into the diagonal)
 int k_diag_add(LaunchCtx& lc, int64_t m, double* M, int64_t ldm, const int* col, const double* val, const double* dinv);
+// M[r][r] *= (1 + delta) (+ delta if the entry is not positive): the diagonal shift of the regularised retry
+int k_diag_shift(LaunchCtx& lc, int64_t m, double* M, int64_t ldm, double delta);
 // t_k[r] += val[r] * (dinv ? dinv[j] : 1) * w_k[j], j = col[r] >= 0: the singleton columns' share of A (dinv * w_k)
 int k_slack_add(LaunchCtx& lc, int64_t m, const int* col, const double* val, const double* dinv, const double* w0,
                 const double* w1, double* t0, double* t1, int nrhs);

@@ -53,6 +53,8 @@ struct lpb_ctx {
   int* col_row = nullptr;     // n: for columns >= n_dense, the row of their only non-zero, or -1 (all-zero column)
   double* col_val = nullptr;  // n: ... and its value
   int refine = 1;  // iterative-refinement steps per sym_solve (0 = the plain factor-and-solve of the reference)
+  int regularize = 0;        // 1 = retry a failed factorisation with a shifted diagonal (see form_and_factor)
+  bool shifted_now = false;  // the factor of the current iteration belongs to a shifted M
   double *c = nullptr, *x = nullptr, *z = nullptr, *rD = nullptr, *dinv = nullptr, *xs = nullptr, *r1 = nullptr,
          *p = nullptr, *u = nullptr, *dx = nullptr, *dz = nullptr, *xo = nullptr;
   bool have_pq = false;
@@ -67,6 +69,7 @@ struct lpb_ctx {
   int potrf_verify = 0;                 // debug: factor every M twice and compare the two factors bit for bit
   double *vfy1 = nullptr, *vfy2 = nullptr;
   int64_t vfy_mismatch = 0, vfy_runs = 0;
+  int64_t refactorisations = 0;         // option "regularize": factorisations repeated with a diagonal shift
   bool check_replicas = false;          // debug: compare checksums of replicated buffers across ranks
   unsigned long long* chk_dev = nullptr;  // 2 words: {checksum, ~checksum}
   unsigned long long* chk_host = nullptr; // pinned
@@ -285,11 +288,8 @@ struct CudaDev {
     return LPB_OK;
   }
 
-  int form_and_factor() {  // newton_equations.rs:48-64
-    {
-      PhaseTimer tm(c, PH_VEC);
-      LPB_TRY(k_dinv(c->lc, c->n, c->x, c->z, c->dinv));
-    }
+  // M = A diag(x / z) A^T (lower triangle), all-reduced over the column shards   (newton_equations.rs:54-57)
+  int form_normal_matrix() {
     {
       PhaseTimer tm(c, PH_SYRK);
       if (c->n_dense <= 0)  // a shard made of slack columns only
@@ -320,7 +320,11 @@ struct CudaDev {
     } else {
       LPB_TRY(allreduce(c, c->M, c->m * c->ldm, ncclSum));
     }
-    LPB_TRY(check_replicated(c, "M after the all-reduce", c->M, c->m, c->m, c->ldm, 1));
+    return check_replicated(c, "M after the all-reduce", c->M, c->m, c->m, c->ldm, 1);
+  }
+
+  // Cholesky of M in place; *info_out = 0 or first bad pivot + 1 (agreed across ranks)   (newton_equations.rs:129-132)
+  int factor_normal_matrix(int* info_out) {
     const size_t mbytes = sizeof(double) * (size_t)(c->m * c->ldm);
     if (c->potrf_verify) {
       if (!c->vfy1) {
@@ -362,8 +366,40 @@ struct CudaDev {
     }
     LPB_CUDA(cudaMemcpyAsync(c->lc.info_host, c->lc.info_dev, sizeof(int), cudaMemcpyDeviceToHost, c->lc.stream));
     LPB_CUDA(cudaStreamSynchronize(c->lc.stream));
+    *info_out = *c->lc.info_host;
+    return LPB_OK;
+  }
+
+  int form_and_factor() {  // newton_equations.rs:48-64
+    {
+      PhaseTimer tm(c, PH_VEC);
+      LPB_TRY(k_dinv(c->lc, c->n, c->x, c->z, c->dinv));
+    }
+    LPB_TRY(form_normal_matrix());
+    int info = 0;
+    LPB_TRY(factor_normal_matrix(&info));
     c->have_pq = false;
-    if (*c->lc.info_host != 0) return LPB_ERR_NUMERICAL_PROBLEM;  // newton_equations.rs:63
+    c->shifted_now = false;
+    if (info == 0) return LPB_OK;
+    // The reference gives up here (newton_equations.rs:63: any factorisation error -> NumericalProblem; its
+    // Inverse / LeastSquares fallbacks only hang off a failed SOLVE, :201-209) and so does the default path.
+    // Option "regularize" = 1 is the GPU analogue of that fallback chain for a failed FACTOR: M is formed again
+    // and factored with a growing relative shift of its diagonal, M_ii (1 + delta); the regularised factor is then
+    // only a preconditioner -- every sym_solve of this iteration runs >= 2 refinement steps against the exact
+    // operator A D A^T (direction()), so the directions solve the unshifted normal equations.
+    if (!c->regularize) return LPB_ERR_NUMERICAL_PROBLEM;
+    double delta = 1e-13;
+    for (int attempt = 0; attempt < 6 && info != 0; ++attempt, delta *= 100.0) {
+      LPB_TRY(form_normal_matrix());
+      {
+        PhaseTimer tm(c, PH_VEC);
+        LPB_TRY(k_diag_shift(c->lc, c->m, c->M, c->ldm, delta));
+      }
+      LPB_TRY(factor_normal_matrix(&info));
+      c->refactorisations++;
+    }
+    if (info != 0) return LPB_ERR_NUMERICAL_PROBLEM;
+    c->shifted_now = true;
     return LPB_OK;
   }
 
@@ -412,7 +448,8 @@ struct CudaDev {
     // and of the factorisation from (u, v, p, q): without it -c.p + b.q (a difference of two numbers ~ the
     // objective that must come out as p' Dinv^-1 p >= 0, delta.rs:32) was 20x noisier than with LAPACK late
     // in the iteration, and d_tau went wild (C3: 27-28 iterations instead of the oracle's 24).
-    for (int step = 0; step < c->refine; ++step) {
+    const int refine_steps = c->shifted_now ? std::max(c->refine, 2) : c->refine;
+    for (int step = 0; step < refine_steps; ++step) {
       double* R0 = c->R;
       double* R1 = c->R + c->m;
       {
@@ -1057,6 +1094,15 @@ int64_t lpb_debug_read(lpb_ctx* c, const char* name, double* out, int64_t count)
   return -1;
 }
 
+int64_t lpb_debug_counter(lpb_ctx* c, const char* name) {
+  if (!c || !name) return -1;
+  const std::string k(name);
+  if (k == "potrf_verify_runs") return c->vfy_runs;
+  if (k == "potrf_verify_mismatches") return c->vfy_mismatch;
+  if (k == "refactorisations") return c->refactorisations;
+  return -1;
+}
+
 // ---------------------------------------------------------------- phases
 int lpb_blind_start(lpb_ctx* c) {
   LPB_TRY(need_problem(c));
@@ -1296,6 +1342,10 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
   if (k == "refine") {
     if (value < 0 || value > 4) return LPB_ERR_BAD_ARGUMENT;
     c->refine = (int)value;
+    return LPB_OK;
+  }
+  if (k == "regularize") {  // 0 (default, the reference's behaviour): a failed factorisation is NumericalProblem
+    c->regularize = value != 0;
     return LPB_OK;
   }
   if (k == "structure") {  // 0: contract over every column of A (no slack-column shortcut)

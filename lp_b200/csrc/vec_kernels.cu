@@ -812,6 +812,19 @@ int k_diag_add(LaunchCtx& lc, int64_t m, double* M, int64_t ldm, const int* col,
   return LPB_OK;
 }
 
+__global__ void diag_shift_kernel(int64_t m, double* __restrict__ M, int64_t ldm, double delta) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  const double d = M[r * ldm + r];
+  M[r * ldm + r] = d > 0.0 ? d * (1.0 + delta) : d + delta;
+}
+int k_diag_shift(LaunchCtx& lc, int64_t m, double* M, int64_t ldm, double delta) {
+  if (m <= 0) return LPB_OK;
+  diag_shift_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, lc.stream>>>(m, M, ldm, delta);
+  LPB_LAUNCH_CHECK(lc);
+  return LPB_OK;
+}
+
 // The singleton columns' share of t_k = A (dinv? dinv * w_k : w_k):  t_k[r] += s_r * (dinv[j] *) w_k[j], j = col[r].
 __global__ void slack_add_kernel(int64_t m, const int* __restrict__ col, const double* __restrict__ val,
                                  const double* __restrict__ dinv, const double* __restrict__ w0,

@@ -1,0 +1,120 @@
+//! Definition of a linear program in slack form -- same public surface as
+//! `/root/reference/src/linear_program.rs` (`Problem::target`, `ProblemBuilder::{new, ub, eq, build}`,
+//! accessors `A() b() c()`); host-only, O(mn), runs once per problem.
+//!
+//! ```text
+//! min_x c ' x   st   A x == b,  x >= 0          A = [[A_ub, I], [A_eq, 0]],  b = [b_ub; b_eq],  c = [c; 0]
+//! ```
+use crate::error::LinearProgramError;
+use ndarray::{s, Array1, Array2};
+use std::fmt::Debug;
+
+/// A linear program in slack form (only equality constraints, `x >= 0`).
+pub struct Problem<F> {
+    A: Array2<F>,
+    b: Array1<F>,
+    c: Array1<F>,
+    c0: F,
+    n_slack: usize,
+}
+
+impl Problem<f64> {
+    /// Start the builder with the cost vector `c` of `min c'x` (reference `linear_program.rs:37-39`).
+    pub fn target(c: &Array1<f64>) -> ProblemBuilder<'_, f64> {
+        ProblemBuilder::new(c)
+    }
+}
+
+impl<F: Copy + Debug> Problem<F> {
+    /// The slack-form constraint matrix (row-major, `m x n`).
+    pub fn A(&self) -> &Array2<F> {
+        &self.A
+    }
+
+    /// The slack-form right-hand side.
+    pub fn b(&self) -> &Array1<F> {
+        &self.b
+    }
+
+    /// The slack-form cost vector (`c` followed by `n_slack` zeros).
+    pub fn c(&self) -> &Array1<F> {
+        &self.c
+    }
+
+    pub(crate) fn c0(&self) -> F {
+        self.c0
+    }
+
+    pub(crate) fn n_slack(&self) -> usize {
+        self.n_slack
+    }
+
+    /// Drop the slack variables again (reference `linear_program.rs:65-69`).
+    pub(crate) fn denormalize_x_into(&self, x_slack: Array1<F>) -> Array1<F> {
+        let keep = x_slack.len() - self.n_slack;
+        x_slack.slice(s![..keep]).to_owned()
+    }
+}
+
+/// Collects borrowed constraint blocks and converts them to slack form in `build`.
+pub struct ProblemBuilder<'a, F> {
+    c: &'a Array1<F>,
+    ub: Option<(&'a Array2<F>, &'a Array1<F>)>,
+    eq: Option<(&'a Array2<F>, &'a Array1<F>)>,
+}
+
+impl<'a> ProblemBuilder<'a, f64> {
+    /// Start building a problem with cost vector `c`.
+    pub fn new(c: &'a Array1<f64>) -> Self {
+        ProblemBuilder { c, ub: None, eq: None }
+    }
+
+    /// Inequality block `A x <= b`.
+    pub fn ub(mut self, A: &'a Array2<f64>, b: &'a Array1<f64>) -> Self {
+        self.ub = Some((A, b));
+        self
+    }
+
+    /// Equality block `A x == b`.
+    pub fn eq(mut self, A: &'a Array2<f64>, b: &'a Array1<f64>) -> Self {
+        self.eq = Some((A, b));
+        self
+    }
+
+    /// Validate the shapes and assemble the slack form (reference `linear_program.rs:125-169`):
+    /// `Unconstrained` without any row, `IncompatibleInputDimensions` on a shape mismatch.
+    pub fn build(self) -> Result<Problem<f64>, LinearProgramError<f64>> {
+        let n_c = self.c.len();
+        let (rows_ub, cols_ub, len_b_ub) = match self.ub {
+            Some((A, b)) => (A.nrows(), A.ncols(), b.len()),
+            None => (0, n_c, 0), // (0, n) placeholders
+        };
+        let (rows_eq, cols_eq, len_b_eq) = match self.eq {
+            Some((A, b)) => (A.nrows(), A.ncols(), b.len()),
+            None => (0, n_c, 0),
+        };
+        if rows_ub + rows_eq == 0 {
+            return Err(LinearProgramError::Unconstrained);
+        }
+        if cols_ub != cols_eq || cols_eq != n_c || rows_ub != len_b_ub || rows_eq != len_b_eq {
+            return Err(LinearProgramError::IncompatibleInputDimensions);
+        }
+        let (m, n) = (rows_ub + rows_eq, n_c + rows_ub);
+        let mut A = Array2::<f64>::zeros((m, n));
+        let mut b = Array1::<f64>::zeros(m);
+        let mut c = Array1::<f64>::zeros(n);
+        if let Some((A_ub, b_ub)) = self.ub {
+            A.slice_mut(s![..rows_ub, ..n_c]).assign(A_ub);
+            for i in 0..rows_ub {
+                A[[i, n_c + i]] = 1.0; // the slack block [I; 0]
+            }
+            b.slice_mut(s![..rows_ub]).assign(b_ub);
+        }
+        if let Some((A_eq, b_eq)) = self.eq {
+            A.slice_mut(s![rows_ub.., ..n_c]).assign(A_eq);
+            b.slice_mut(s![rows_ub..]).assign(b_eq);
+        }
+        c.slice_mut(s![..n_c]).assign(self.c);
+        Ok(Problem { A, b, c, c0: 0.0, n_slack: rows_ub })
+    }
+}

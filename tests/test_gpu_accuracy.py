@@ -1,0 +1,269 @@
+"""Parity at full size against the committed oracle fixtures (tests/golden/, made by tools/oracle_full_size.py):
+every entry of x, the whole per-iteration trace, and the stage-by-stage rounding behaviour of the factor / solve
+chain on a late, ill-conditioned normal matrix.
+
+Bar (BASELINE.json north_star): same status, iterations within +-1, x within 1e-6 absolute, objective within
+1e-8 relative.  `tol` enters the reference only through Indicators::status (indicators.rs:66-83), so one oracle
+run yields the iterates at which tol = 1e-8 (default), 1e-9 and 1e-10 stop; the fixtures hold the full x of each.
+"""
+import ctypes as C
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+import lp_b200
+from lp_b200 import _ffi
+from lp_b200.api import ResidentProblem
+from oracle import ipm_oracle as o
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SIZES = {"C1": (512, 1024), "C2": (4096, 8192), "C3": (16384, 32768)}
+TRACE_COLS = ["alpha", "rho_p", "rho_d", "rho_A", "rho_g", "rho_mu", "obj", "bty", "tau", "kappa"]
+_problems = {}
+
+
+def problem(wl):
+    """The seeded workload LP, built once per session (C3: 4.3 GB of pinned host memory, ~30 s of NumPy)."""
+    if wl not in _problems:
+        m, n = SIZES[wl]
+        c, A_ub, b_ub, A_eq, b_eq = o.synthetic_lp(m, n, 0)
+        _problems[wl] = lp_b200.Problem.target(c).ub(A_ub, b_ub).eq(A_eq, b_eq).build()
+    return _problems[wl]
+
+
+def gold(wl):
+    g = json.load(open(os.path.join(GOLD, "oracle_%s_seed0.json" % wl)))
+    xs = {1e-8: np.load(os.path.join(GOLD, g["x_file"]))}
+    its = {1e-8: g["iterations"]}
+    for k, v in g.get("tighter", {}).items():
+        xs[float(k)] = np.load(os.path.join(GOLD, v["x_file"]))
+        its[float(k)] = v["iterations"]
+    return g, xs, its
+
+
+@pytest.mark.parametrize("wl", ["C1", "C2", "C3"])
+def test_every_entry_of_x_matches_the_oracle(wl):
+    """Full-x parity at the default tolerance AND at the tightest tolerance the oracle itself reaches
+    (1e-10 at C1 / C2, 1e-9 at C3: below that rho_p sits on LAPACK's own rounding floor).  At C3 the default
+    stopping point leaves x / tau 1.4e-4 away from the converged vertex (fixture: max_abs_dx_vs_default_tol), so
+    agreement there means the two runs follow the same TRAJECTORY to 1e-6, not merely the same optimum."""
+    g, xs, its = gold(wl)
+    assert g["status"] == "Optimal"
+    with ResidentProblem(problem(wl)) as rp:
+        for tol in sorted(xs, reverse=True):
+            res = lp_b200.InteriorPoint.custom().tol(tol).build().solve_resident(rp)
+            dx = np.abs(res.x() - xs[tol]).max()
+            print("%s tol %.0e: iterations %d (oracle %d), max|x - x_oracle| = %.3e over %d entries" % (
+                wl, tol, res.iteration(), its[tol], dx, len(res.x())))
+            assert abs(res.iteration() - its[tol]) <= 1
+            assert dx <= 1e-6
+            if tol == 1e-8:
+                assert abs(res.fun() - g["fun"]) <= 1e-8 * abs(g["fun"])
+    assert max(xs) == 1e-8 and min(xs) <= 1e-9   # a tighter-than-default fixture exists for every workload
+
+
+@pytest.mark.parametrize("wl", ["C1", "C2", "C3"])
+def test_whole_trace_matches_the_oracle(wl):
+    """Every iteration of the run, not the first four: alpha, the five indicators, obj, b.y, tau, kappa.
+    Per-iteration tolerance  rtol_k = 1e-9 + 3e-8 / rho_mu(k):  the condition number of M = A D A^T grows like
+    1 / mu, and two correctly rounded runs drift apart at that rate (measured: 1e-12 at iteration 1, 1e-6 at
+    rho_mu = 3e-5, 5e-3 at rho_mu = 3e-8).  Rows whose rtol exceeds 0.5 (the last one or two, where rho_p sits on
+    the rounding floor) are checked on obj, tau and kappa only."""
+    g, _, _ = gold(wl)
+    with ResidentProblem(problem(wl)) as rp:
+        res = lp_b200.InteriorPoint.default().solve_resident(rp)
+        tr = rp.trace()
+    assert res.iteration() == g["iterations"] and len(tr) == g["iterations"]
+    worst = 0.0
+    for k in range(len(tr)):
+        row = g["trace"][k]
+        want = np.array([row[c] for c in TRACE_COLS])
+        got = tr[k][:10]
+        rtol = 1e-9 + 3e-8 / row["rho_mu"]
+        rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
+        if rtol <= 0.5:
+            assert rel.max() <= rtol, (wl, k + 1, TRACE_COLS[int(rel.argmax())], rel.max(), rtol)
+            worst = max(worst, rel.max() / rtol)
+        else:
+            for col in ("obj", "tau"):
+                i = TRACE_COLS.index(col)
+                assert rel[i] <= 1e-6, (wl, k + 1, col, rel[i])
+    print("%s: %d iterations compared, worst (difference / tolerance) = %.3f" % (wl, len(tr), worst))
+
+
+@pytest.mark.parametrize("wl", ["C1", "C2", "C3"])
+def test_without_refinement_the_bar_is_still_met(wl):
+    """`refine` = 0 is the plain factor-and-solve of the reference (no iterative-refinement step): status,
+    iteration count (+-1) and objective (1e-8) still meet the bar at every workload.  x is then compared at the
+    tight tolerance only where it is determined (C1 / C2); at C3 the refinement-free trajectory leaves the
+    oracle's around rho_mu = 1e-4 (see test_stage_errors... and DESIGN.md section 5) and x at tol = 1e-8 is
+    1e-4-close only -- which is also how far TWO ORACLE RUNS with different summation orders are apart
+    (tests/golden/oracle_C3_seed0_splitk.json)."""
+    g, xs, its = gold(wl)
+    with ResidentProblem(problem(wl)) as rp:
+        rp.set_option("refine", 0)
+        res = lp_b200.InteriorPoint.default().solve_resident(rp)
+    dx = np.abs(res.x() - xs[1e-8]).max()
+    print("%s refine=0: iterations %d (oracle %d), max|dx| %.3e, rel. objective difference %.2e" % (
+        wl, res.iteration(), its[1e-8], dx, abs(res.fun() - g["fun"]) / abs(g["fun"])))
+    assert abs(res.iteration() - its[1e-8]) <= 1
+    assert abs(res.fun() - g["fun"]) <= 1e-8 * abs(g["fun"])
+    assert dx <= (1e-6 if wl != "C3" else 5e-4)
+
+
+def test_two_host_threads_each_with_its_own_context():
+    """The reference's solve(&self, &problem) is re-entrant: two host threads, one context each, run
+    concurrently (ctypes drops the GIL inside liblpb200) and must reproduce the sequential answers bit for bit --
+    also the first time the per-device kernel attributes are set from two threads at once."""
+    pbs = [problem("C1")]
+    c, A_ub, b_ub, A_eq, b_eq = o.synthetic_lp(768, 1536, 5)
+    pbs.append(lp_b200.Problem.target(c).ub(A_ub, b_ub).eq(A_eq, b_eq).build())
+    solver = lp_b200.InteriorPoint.default()
+    seq = [solver.solve(pb) for pb in pbs]
+    out = [None, None]
+    err = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                out[i] = solver.solve(pbs[i])
+        except Exception as e:  # noqa: BLE001
+            err.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not err, err
+    for i in range(2):
+        assert out[i].iteration() == seq[i].iteration()
+        np.testing.assert_array_equal(out[i].x(), seq[i].x())
+        assert out[i].fun() == seq[i].fun()
+
+
+def test_factoring_every_matrix_twice_finds_no_race():
+    """Option potrf_verify: every M of a C2 solve is factored twice (look-ahead path, two streams, mbarrier ring)
+    and the two factors are compared bit for bit -- the check that found the ring-stage release race in round 1."""
+    with ResidentProblem(problem("C2")) as rp:
+        rp.set_option("potrf_verify", 1)
+        res = lp_b200.InteriorPoint.default().solve_resident(rp)
+        runs, bad = rp.debug_counter("potrf_verify_runs"), rp.debug_counter("potrf_verify_mismatches")
+    assert runs == res.iteration() and bad == 0
+
+
+def test_stage_errors_on_a_late_normal_matrix_against_cublas_and_cusolver():
+    """Per-stage rounding behaviour on the normal matrix of a LATE iterate of C2 (D = x / z spans 18 orders of
+    magnitude): K1 vs cuBLAS, K2 vs cuSOLVER potrf, K3 vs cuSOLVER potrs -- the libraries are the checkers here.
+    Measured (profiles/accuracy_r02.txt): SYRK within 7e-16 of |A| D |A|^T of cuBLAS; factor backward error
+    1.6e-15 normwise / 7e-15 diagonally scaled (cuSOLVER 2.5e-16 / 1.3e-15 at this size, equal at C3); every solve
+    variant 2e-17 (cuSOLVER 3e-17)."""
+    import torch
+    lib = _ffi.load()
+    m, n = SIZES["C2"]
+    pb = problem("C2")
+    g, _, _ = gold("C2")
+    with ResidentProblem(pb) as rp:
+        try:
+            lp_b200.InteriorPoint.custom().max_iter(g["iterations"] - 2).build().solve_resident(rp)
+        except lp_b200.IterationLimitExceeded:
+            pass
+        d = torch.from_numpy(rp.debug_read("dinv")).cuda()
+    assert float(d.max() / d.min()) > 1e15
+    A = torch.from_numpy(pb.A()).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    h = C.c_void_p()
+    assert lib.lpb_create_bare(C.byref(h), m, n, C.c_void_p(stream)) == 0
+    try:
+        Mg = torch.zeros((m, m), dtype=torch.float64, device="cuda")
+        assert lib.lpb_k_syrk_adat(h, m, n, A.data_ptr(), n, d.data_ptr(), Mg.data_ptr(), m) == 0
+        Mref = (A * d) @ A.T
+        Mabs = (A.abs() * d) @ A.abs().T
+        low = torch.tril(torch.ones((m, m), dtype=torch.bool, device="cuda"))
+        assert ((Mg - Mref).abs() / Mabs)[low].max().item() < 1e-14          # ~ sqrt(n) eps, both sides rounded
+        Msym = torch.tril(Mref) + torch.tril(Mref, -1).T
+        dg = torch.sqrt(torch.diagonal(Msym))
+        nM = torch.linalg.norm(Msym).item()
+
+        def factor_err(L):
+            R = L @ L.T - Msym
+            return torch.linalg.norm(R).item() / nM, (R.abs() / torch.outer(dg, dg)).max().item()
+
+        Lref = torch.linalg.cholesky(Msym)
+        ref_n, ref_s = factor_err(Lref)
+        W = Msym.clone()
+        info = C.c_int32(-1)
+        assert lib.lpb_k_potrf(h, m, W.data_ptr(), m, C.byref(info)) == 0 and info.value == 0
+        got_n, got_s = factor_err(torch.tril(W))
+        print("factor backward error: lpb %.2e normwise / %.2e scaled; cuSOLVER %.2e / %.2e" % (got_n, got_s, ref_n, ref_s))
+        assert got_n < 1e-14 and got_s < 5e-14          # m eps = 9e-13 is the textbook bound; LAPACK-grade is ~1e-15
+        assert got_n < 20 * ref_n and got_s < 20 * ref_s
+        rhs = torch.stack([A @ (d * torch.from_numpy(pb.c()).cuda()) + torch.from_numpy(pb.b()).cuda(),
+                           torch.randn(m, dtype=torch.float64, device="cuda")])
+
+        def solve_err(X):
+            return max(torch.linalg.norm(Msym @ X[k] - rhs[k]).item() /
+                       (nM * torch.linalg.norm(X[k]).item() + torch.linalg.norm(rhs[k]).item()) for k in range(2))
+
+        ref_e = solve_err(torch.cholesky_solve(rhs.T.contiguous(), Lref).T.contiguous())
+        for impl in (0, 3, 2):
+            assert lib.lpb_set_option(h, b"solve_impl", impl) == 0
+            X = rhs.clone()
+            assert lib.lpb_k_potrs(h, m, W.data_ptr(), m, X.data_ptr(), 2) == 0, _ffi.last_error()
+            e = solve_err(X)
+            print("solve_impl %d backward error %.2e (cuSOLVER %.2e)" % (impl, e, ref_e))
+            assert e < 1e-15 and e < 10 * ref_e
+    finally:
+        lib.lpb_destroy(h)
+
+
+def test_regularised_refactorisation_is_opt_in_and_solves_rank_deficient_systems():
+    """the GPU analogue of the reference's Inverse / LeastSquares fallback chain
+    (newton_equations.rs:201-209).  Default (`regularize` = 0): a failed factorisation is NumericalProblem, as in
+    the reference (:63).  `regularize` = 1: the factorisation is repeated with a shifted diagonal and the
+    directions are refined against the exact operator; the LP with duplicated constraint rows (M exactly singular)
+    then solves to the optimum of the LP without the redundant rows."""
+    rng = np.random.default_rng(3)
+    A0 = rng.standard_normal((20, 60))
+    x0 = rng.uniform(0.5, 1.5, 60)
+    A_eq = np.vstack([A0, A0[:5]])             # five duplicated rows: rank 20, 25 rows
+    b_eq = A_eq @ x0
+    c = A0.T @ rng.standard_normal(20) + rng.uniform(0.5, 1.5, 60)
+    ref = o.InteriorPoint().solve(o.build_problem(c, A_eq=A0, b_eq=A0 @ x0))
+    pb = lp_b200.Problem.target(c).eq(A_eq, b_eq).build()
+    with ResidentProblem(pb) as rp:
+        try:
+            default = lp_b200.InteriorPoint.default().solve_resident(rp)
+        except lp_b200.NumericalProblem:
+            default = None
+        rp.set_option("regularize", 1)
+        res = lp_b200.InteriorPoint.default().solve_resident(rp)
+        refacts = rp.debug_counter("refactorisations")
+    print("default path: %s; regularised: %d iterations, %d refactorisations, max|dx| %.2e" % (
+        "NumericalProblem" if default is None else "pushed through in %d iterations" % default.iteration(),
+        res.iteration(), refacts, np.abs(res.x() - ref.x).max()))
+    assert np.abs(res.x() - ref.x).max() < 1e-6
+    assert abs(res.fun() - ref.fun) <= 1e-8 * max(1.0, abs(ref.fun))
+    if default is None:
+        assert refacts > 0
+
+
+def test_f32_problems_are_widened_and_results_narrowed():
+    """`Problem<f32>` (float.rs:43): float32 inputs are widened to FP64 at build, solved in FP64, and the result is
+    narrowed back -- the reference's own known answers hold to its 1e-6 at float32."""
+    A_ub = np.array([[-3.0, 1.0], [1.0, 2.0]], dtype=np.float32)
+    b_ub = np.array([6.0, 4.0], dtype=np.float32)
+    A_eq = np.array([[1.0, 1.0]], dtype=np.float32)
+    b_eq = np.array([1.0], dtype=np.float32)
+    c = np.array([-1.0, 4.0], dtype=np.float32)
+    pb = lp_b200.Problem.target(c).ub(A_ub, b_ub).eq(A_eq, b_eq).build()
+    assert pb.dtype() == np.float32
+    res = lp_b200.InteriorPoint.default().solve(pb)
+    assert res.x().dtype == np.float32
+    np.testing.assert_allclose(res.x(), [1.0, 0.0], atol=1e-6)
+    assert lp_b200.InteriorPoint.default().solve(
+        lp_b200.Problem.target(c.astype(np.float64)).ub(A_ub, b_ub).build()).x().dtype == np.float64

@@ -50,16 +50,20 @@ def main():
             wl, m, n, git, gold and gold.get("fun"), sorted(gx)), flush=True)
         with ResidentProblem(pb) as rp:
             # ---------------------------------------------------------------- (A) option combinations
-            combos = [dict(), dict(refine=0), dict(refine=0, solve_impl=3), dict(refine=0, solve_impl=2),
-                      dict(refine=0, trsm_impl=1), dict(refine=0, trsm_impl=1, solve_impl=2),
-                      dict(refine=0, trsm_impl=1, solve_impl=2, structure=0), dict(solve_impl=3), dict(refine=2)]
-            base = dict(refine=1, trsm_impl=0, solve_impl=0, structure=1)
+            combos = [dict(), dict(refine=0), dict(refine=0, update_impl=2), dict(update_impl=2),
+                      dict(refine=0, update_impl=2, solve_impl=3), dict(refine=0, update_impl=2, solve_impl=2),
+                      dict(refine=0, update_impl=2, trsm_impl=1, solve_impl=2), dict(refine=0, update_impl=1)]
+            if os.environ.get("DIAG_ALL"):
+                combos += [dict(refine=0, solve_impl=3), dict(refine=0, solve_impl=2), dict(refine=0, trsm_impl=1),
+                           dict(refine=0, trsm_impl=1, solve_impl=2),
+                           dict(refine=0, trsm_impl=1, solve_impl=2, structure=0), dict(solve_impl=3), dict(refine=2)]
+            base = dict(refine=1, trsm_impl=0, solve_impl=0, structure=1, update_impl=0)
             traces = {}
             for combo in combos:
                 opts = dict(base, **combo)
                 for k, v in opts.items():
                     rp.set_option(k, v)
-                for tol in (1e-8, 1e-10):
+                for tol in ((1e-8, 1e-10) if 1e-10 in gx else (1e-8, 1e-9)):
                     t0 = time.perf_counter()
                     try:
                         res = lp_b200.InteriorPoint.custom().tol(tol).max_iter(60).build().solve_resident(rp)
@@ -74,7 +78,8 @@ def main():
                         traces[json.dumps(combo, sort_keys=True)] = rp.trace().copy()
             # ---------------------------------------------------------------- (B) trace differences, default options
             if gold:
-                for key in ("{}", json.dumps(dict(refine=0), sort_keys=True)):
+                for key in ("{}", json.dumps(dict(refine=0), sort_keys=True),
+                            json.dumps(dict(refine=0, update_impl=2), sort_keys=True)):
                     tr = traces.get(key)
                     if tr is None:
                         continue
@@ -104,6 +109,7 @@ def main():
         assert lib.lpb_create_bare(C.byref(h), m, n, None) == 0
         ldm = (m + 15) // 16 * 16
         Mg = torch.zeros((m, ldm), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()  # the library runs on its own stream
         assert lib.lpb_k_syrk_adat(h, m, n, A.data_ptr(), n, d.data_ptr(), Mg.data_ptr(), ldm) == 0
         Mref = (A * d) @ A.T            # cuBLAS DGEMM: the library-grade comparator
         Mabs = (A.abs() * d) @ A.abs().T
@@ -136,19 +142,22 @@ def main():
         Xref = torch.cholesky_solve(rhs2.T.contiguous(), Lref).T.contiguous()
         solve_errors(Xref, "cuSOLVER potrf + potrs")
         info_h = C.c_int32(-1)
-        for trsm in (0, 1):
+        for trsm, upd in ((0, 0), (0, 2), (1, 2), (0, 1)):
             assert lib.lpb_set_option(h, b"trsm_impl", trsm) == 0
+            assert lib.lpb_set_option(h, b"update_impl", upd) == 0
             Lg = torch.zeros((m, ldm), dtype=torch.float64, device="cuda")
             Lg[:, :m] = Msym
+            torch.cuda.synchronize()
             assert lib.lpb_k_potrf(h, m, Lg.data_ptr(), ldm, C.byref(info_h)) == 0
-            name = "lpb trsm_impl=%d" % trsm
+            name = "lpb trsm=%d update=%d" % (trsm, upd)
             print("  lpb potrf (%s) info = %d" % (name, info_h.value))
             Lt = torch.tril(Lg[:, :m])
             factor_errors(Lt, name)
             print("        max |L_gpu - L_cusolver| / max|L| = %.2e" % ((Lt - Lref).abs().max().item() / Lref.abs().max().item()))
-            for simpl in (0, 3, 2):
+            for simpl in ((0, 3, 2) if (trsm, upd) == (0, 0) else (0,)):
                 assert lib.lpb_set_option(h, b"solve_impl", simpl) == 0
                 Bx = rhs2.clone()
+                torch.cuda.synchronize()
                 rc = lib.lpb_k_potrs(h, m, Lg.data_ptr(), ldm, Bx.data_ptr(), 2)
                 assert rc == 0, _ffi.last_error()
                 solve_errors(Bx, "%s solve_impl=%d" % (name, simpl))

@@ -2,7 +2,7 @@
 # One parameterised GPU-box script (replaces the per-call scripts of round 1).  Usage, under gpurun:
 #   bash tools/gpu_run.sh TAG step [step ...]
 # Steps:  tests | tests:<pytest -k expr> | smoke | bench:<WL> | benchq:<WL> (1 step, no CPU leg) | diag:<WL>[,<WL>]
-#         | time:<m>[,<m>] | create:<WL> | launches:<WL> | ncu:<WL>:<kernel regex>:<skip>:<count> | ref:<WL>
+#         | dtau:<WL>:<K> | time:<m>[,<m>] | create:<WL> | launches:<WL> | ncu:<WL>:<kernel regex>:<skip>:<count> | ref:<WL>
 # Everything is written under gpurun_out/ with TAG in the name; a failing step does not stop the later ones.
 set -u
 TAG=$1; shift
@@ -33,6 +33,10 @@ for step in "$@"; do
     diag)
       timeout 1500 python tools/diag_accuracy.py ${arg//,/ } > gpurun_out/diag_${TAG}.log 2>&1
       echo "[$step] rc=$? $(wc -l < gpurun_out/diag_${TAG}.log) lines";;
+    dtau)
+      IFS=: read -r wl k <<< "$arg"
+      timeout 900 python tools/diag_dtau.py $wl $k > gpurun_out/dtau_${wl}_${k}_${TAG}.log 2>&1
+      echo "[$step] rc=$?"; cat gpurun_out/dtau_${wl}_${k}_${TAG}.log | tail -40;;
     time)
       timeout 600 python tools/time_kernels.py ${arg//,/ } > gpurun_out/time_${TAG}.log 2>&1
       echo "[$step] rc=$?"; cat gpurun_out/time_${TAG}.log | tail -4;;
