@@ -65,7 +65,7 @@ def workload_label(name, m, n, seed):
     return "%s dense LP slack-form m=%d n=%d seed=%d (ub+eq, SURVEY 8d generator)" % (name, m, n, seed)
 
 
-def bench_config(workload, m, n, seed, world, potrf_dist=1):
+def bench_config(workload, m, n, seed, world, potrf_dist=2):
     """`config` of the JSON line: the SAME dict in the product and the reference arm."""
     if workload == "C4":
         wl = "C4 batched: %d independent dense LPs slack-form m=%d n=%d, seeds 1000+i, one CTA per problem" % (
@@ -602,8 +602,9 @@ def main():
     ap.add_argument("--device-synthetic", action="store_true",
                     help="generate the LP on the device per column shard (always on for C5)")
     ap.add_argument("--batch", type=int, default=C4_BATCH)
-    ap.add_argument("--potrf-dist", type=int, default=1, choices=[0, 1],
-                    help="N > 1: 1 = distributed panel-broadcast Cholesky (default), 0 = replicated on every rank")
+    ap.add_argument("--potrf-dist", type=int, default=2, choices=[0, 1, 2],
+                    help="N > 1: 2 = distributed Cholesky, two broadcasts per panel + side-stream potf2 (default), "
+                         "1 = one broadcast per panel, 0 = replicated on every rank")
     args = ap.parse_args()
     m, n = WORKLOADS[args.workload]
 

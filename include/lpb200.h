@@ -270,6 +270,20 @@ int64_t lpb_debug_read(lpb_ctx* ctx, const char* name, double* out, int64_t coun
  * (option "regularize": factorisations repeated with a diagonal shift).  -1: unknown name. */
 int64_t lpb_debug_counter(lpb_ctx* ctx, const char* name);
 
+/* ---- opt-in presolve (host only; no reference counterpart: the crate's own TODO, CONTRIBUTING.md:8).
+ * Works on the slack form (the output of lpb_build_slack_form): drops empty rows and rows that are multiples of an
+ * earlier row (infeasible -> status LPB_ERR_INFEASIBLE if their right-hand sides disagree), then `scale_passes` rounds
+ * of power-of-two geometric row / column equilibration.  Presolved problem: min (C c)'y st (R A C) y = R b, y >= 0,
+ * x = C y.  Columns are never removed, so n and n_slack carry over. */
+typedef struct lpb_presolve lpb_presolve;
+int lpb_presolve_create(lpb_presolve** out, int64_t m, int64_t n, const double* A, int64_t lda, const double* b,
+                        const double* c, int64_t n_slack, int scale_passes);
+int lpb_presolve_info(const lpb_presolve* p, int64_t* m_out, int64_t* n_out, int64_t* n_slack_out,
+                      int64_t* dropped_empty, int64_t* dropped_duplicate, int* status);
+int lpb_presolve_get(const lpb_presolve* p, double* A_out, int64_t lda_out, double* b_out, double* c_out);
+int lpb_presolve_restore_x(const lpb_presolve* p, const double* y, double* x);
+int lpb_presolve_destroy(lpb_presolve* p);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

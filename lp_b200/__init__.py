@@ -12,6 +12,8 @@ from .api import (  # noqa: F401
     SyntheticShardedProblem,
     solve_batched,
     pinned_empty,
+    presolve,
+    Presolved,
     EquationSolverType,
     IncompatibleInputDimensions,
     Infeasible,
@@ -30,7 +32,7 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "BatchedResult", "ResidentProblem", "ShardedProblem", "SyntheticShardedProblem", "solve_batched", "pinned_empty",
+    "BatchedResult", "ResidentProblem", "ShardedProblem", "SyntheticShardedProblem", "solve_batched", "pinned_empty", "presolve", "Presolved",
     "EquationSolverType", "IncompatibleInputDimensions", "Infeasible", "InteriorPoint", "InteriorPointBuilder",
     "InvalidParameter", "IterationLimitExceeded", "LinearProgramError", "NumericalProblem", "OptimizeResult",
     "Problem", "ProblemBuilder", "Solver", "Unbounded", "Unconstrained",

@@ -127,6 +127,12 @@ SIGNATURES = {
     "lpb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "lpb_debug_read": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "lpb_debug_counter": (C.c_int64, [C.c_void_p, C.c_char_p]),
+    "lpb_presolve_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.c_int]),
+    "lpb_presolve_info": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p, c_int64_p, c_int64_p, c_int64_p, c_int32_p]),
+    "lpb_presolve_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "lpb_presolve_restore_x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lpb_presolve_destroy": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

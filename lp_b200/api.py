@@ -473,6 +473,50 @@ def solve_batched(A, b, c, n_slack: int = 0, solver: Optional["InteriorPoint"] =
     return BatchedResult(x[:, : n - n_slack].copy(), x, fun, it, st)
 
 
+class Presolved:
+    """Outcome of `presolve`: `.problem` is the reduced / scaled slack-form Problem to hand to any Solver;
+    `.restore(result)` maps its OptimizeResult back to the original variables (x = C y; the objective is unchanged
+    by the scaling).  `dropped_empty` / `dropped_duplicate` count the constraint rows removed."""
+
+    def __init__(self, problem, original, col_scale, dropped_empty, dropped_duplicate, kept_rows):
+        self.problem, self._original, self._col_scale = problem, original, col_scale
+        self.dropped_empty, self.dropped_duplicate, self.rows = dropped_empty, dropped_duplicate, kept_rows
+
+    def restore(self, result: "OptimizeResult") -> "OptimizeResult":
+        n_user = len(result.x())
+        x = self._col_scale[:n_user] * result.x()
+        return OptimizeResult(x, result.fun(), result.iteration())
+
+
+def presolve(problem: Problem, scale_passes: int = 2) -> Presolved:
+    """Opt-in presolve (no reference counterpart: the crate lists it as a TODO, CONTRIBUTING.md:8): drop empty and
+    duplicated constraint rows, then `scale_passes` rounds of power-of-two geometric equilibration -- the two
+    causes of NumericalProblem the reference's error message names (error.rs:12-14).  Host only.
+    Raises Infeasible when a dropped row contradicts the one it duplicates (or an empty row has b != 0)."""
+    lib = _ffi.load()
+    A = problem.A()
+    m, n = A.shape
+    h = C.c_void_p()
+    rc = lib.lpb_presolve_create(C.byref(h), m, n, A.ctypes.data, n, problem.b().ctypes.data, problem.c().ctypes.data,
+                                 problem.n_slack(), int(scale_passes))
+    _raise_for(rc)
+    try:
+        m2, n2, ns2, de, dd = (C.c_int64() for _ in range(5))
+        st = C.c_int32()
+        _raise_for(lib.lpb_presolve_info(h, C.byref(m2), C.byref(n2), C.byref(ns2), C.byref(de), C.byref(dd), C.byref(st)))
+        _raise_for(st.value)
+        A_buf, b_buf, c_buf = _HostBuffer((m2.value, n2.value)), _HostBuffer((m2.value,)), _HostBuffer((n2.value,))
+        _raise_for(lib.lpb_presolve_get(h, A_buf.array.ctypes.data, n2.value, b_buf.array.ctypes.data,
+                                        c_buf.array.ctypes.data))
+        ones = np.ones(n2.value)
+        scale = np.empty(n2.value)
+        _raise_for(lib.lpb_presolve_restore_x(h, ones.ctypes.data, scale.ctypes.data))
+    finally:
+        lib.lpb_presolve_destroy(h)
+    reduced = Problem(A_buf, b_buf, c_buf, problem.c0(), ns2.value, problem.dtype())
+    return Presolved(reduced, problem, scale, de.value, dd.value, m2.value)
+
+
 def shard_columns(n: int, world: int, n_slack: int = 0):
     """Contiguous column blocks [col0, col0 + n_local) per rank (even widths keep 16-byte alignment).
 

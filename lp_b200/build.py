@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "liblpb200.so")
-SOURCES = ["vec_kernels.cu", "dmma_gemm.cu", "cholesky.cu", "batched.cu", "lpb_api.cu"]
+SOURCES = ["vec_kernels.cu", "dmma_gemm.cu", "cholesky.cu", "batched.cu", "presolve.cu", "lpb_api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

@@ -137,7 +137,8 @@ __device__ __forceinline__ void complete_block_inverse(double* S, const double* 
 
 __global__ void __launch_bounds__(512)
 potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __restrict__ info,
-                 double* __restrict__ Linv, int full_inverse) {
+                 double* __restrict__ Linv, int full_inverse, double* __restrict__ pack_lkk = nullptr,
+                 double* __restrict__ pack_linv = nullptr) {
   extern __shared__ double S[];    // NB*LDS block
   double* rdiag = S + NB * LDS;    // NB: 1 / L[i][i]
   double* Xd = rdiag + NB;         // SB * XDP
@@ -269,10 +270,13 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
     __syncthreads();
   }
 
-  // ---- L back to Mat
+  // ---- L back to Mat (and, for the distributed factorisation, into the packed send buffer: dense 128 x 128, zero
+  // above the diagonal and beyond a ragged block)
   for (int idx = tid; idx < NB * NB; idx += 512) {
     const int r = idx >> 7, c = idx & (NB - 1);
-    if (r < nb && c <= r) blk[(int64_t)r * ldm + c] = S[r * LDS + c];
+    const bool in = r < nb && c <= r;
+    if (in) blk[(int64_t)r * ldm + c] = S[r * LDS + c];
+    if (pack_lkk) pack_lkk[idx] = in ? S[r * LDS + c] : 0.0;
   }
 
   // ---- off-diagonal blocks of X: only the full-inverse consumers need them (trsm_impl 2); the default TRSM uses
@@ -284,6 +288,7 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
     double v = 0.0;
     if (i < nb && c <= i) v = (c == i) ? rdiag[i] : S[c * LDS + i];
     Linv[idx] = v;
+    if (pack_linv) pack_linv[idx] = v;
   }
 }
 
@@ -441,7 +446,11 @@ __device__ __forceinline__ void dmma884(double2& c, double a, double b) {
 }
 
 __global__ void __launch_bounds__(256)
-trsm_dmma_blocked_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int m, const double* __restrict__ Linv) {
+trsm_dmma_blocked_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int m, const double* __restrict__ Linv,
+                         double* __restrict__ pack = nullptr) {
+  // pack != null (distributed factorisation): the solved rows also go into the packed send buffer of the panel --
+  // 128 doubles per row, row (r - k0) at buffer row (r - k0), except that block k+1 (the rows the next owner needs
+  // first) sits at buffer rows 0..127 and the diagonal block at rows 128..255 (written by potf2_inv_kernel).
   extern __shared__ __align__(16) double sm[];
   double* SL = sm;               // NB * TLP : L_kk (lower triangle incl. diagonal)
   double* SX = SL + NB * TLP;    // NSB * SB * TXP : inv(L_ss), s = 0..7 (zero above their diagonals)
@@ -508,6 +517,13 @@ trsm_dmma_blocked_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int m, c
   if (r < m) {
 #pragma unroll
     for (int q = 0; q < 16; ++q) *reinterpret_cast<double2*>(prow + 8 * q) = c[q];
+    if (pack) {
+      int64_t br = r - k0;
+      if (br < 2 * NB) br -= NB;
+      double* brow = pack + br * NB + 2 * t;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) *reinterpret_cast<double2*>(brow + 8 * q) = c[q];
+    }
   }
 }
 
@@ -1437,6 +1453,49 @@ panel_pack_kernel(double* __restrict__ Mat, int64_t ldm, int64_t k0, int64_t m, 
   }
 }
 
+// Packed panel of the two-broadcast distributed factorisation (k_potrf_dist2), all in units of doubles:
+//   [0, NB NB)               rows of block k+1        (the SMALL broadcast)
+//   [NB NB, 2 NB NB)         the diagonal block L_kk  (dense, zero above the diagonal)
+//   [2 NB NB, ... )          rows from block k+2 on
+//   then NB NB               inv(L_kk) (its 16 x 16 diagonal sub-blocks)
+struct PackedPanel {
+  int64_t k0, rows_total, r1, rest, off_linv, large_count, map_rows;
+  PackedPanel(int64_t m, int k) {
+    k0 = (int64_t)k * NB;
+    rows_total = m - k0;
+    const int64_t nbk = rows_total < NB ? rows_total : NB;
+    const int64_t below = rows_total - nbk;
+    r1 = below < NB ? below : NB;
+    rest = below - r1;
+    off_linv = 2 * (int64_t)NB * NB + rest * NB;
+    large_count = (int64_t)NB * NB + rest * NB + (int64_t)NB * NB;
+    map_rows = 2 * NB + rest;  // rows of the buffer seen by the update kernels' tensor map
+  }
+};
+
+// Non-owners: copy a received packed panel into the local M (lower triangle of the diagonal block, all rows below)
+// and its inverted diagonal sub-blocks into the Linv workspace.
+__global__ void __launch_bounds__(256)
+panel_unpack2_kernel(double* __restrict__ Mat, int64_t ldm, int64_t k0, int64_t m, const double* __restrict__ buf,
+                     int64_t off_linv, double* __restrict__ Linv) {
+  const int64_t rows = m - k0;
+  const int64_t total = rows * NB + (int64_t)NB * NB;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    if (idx < rows * NB) {
+      const int64_t lr = idx >> 7;
+      const int c = (int)(idx & (NB - 1));
+      int64_t br = lr;                       // buffer row of local row lr: the first two blocks are swapped
+      if (lr < NB) br = lr + NB;
+      else if (lr < 2 * NB) br = lr - NB;
+      if (lr >= NB || c <= lr) Mat[(k0 + lr) * ldm + k0 + c] = buf[br * NB + c];
+    } else {
+      const int64_t e = idx - rows * NB;
+      Linv[e] = buf[off_linv + e];
+    }
+  }
+}
+
 template <typename K>
 int set_smem(K kern, size_t bytes) {
   LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -1518,6 +1577,7 @@ static int finish_factor(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm) {
 }
 
 static int k_potrf_dist(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm);
+static int k_potrf_dist2(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm);
 
 // Single-GPU factorisation with look-ahead.  The serial part of a panel is potf2_inv: one CTA, ~40 us, with
 // 147 SMs idle.  Here the trailing update of panel k is split: its first block column (the one panel k+1
@@ -1593,7 +1653,7 @@ int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
   const bool dmma_update = lc.update_impl == 0 || lc.update_impl == 2;
   if (lc.world > 1 && lc.nccl_comm && lc.potrf_dist && syrk_impl == 0 && lc.trsm_impl == 0 && dmma_update &&
       m > NB && !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mat) & 15))
-    return k_potrf_dist(lc, m, Mat, ldm);
+    return lc.potrf_dist == 2 ? k_potrf_dist2(lc, m, Mat, ldm) : k_potrf_dist(lc, m, Mat, ldm);
   if (lc.potrf_lookahead && syrk_impl == 0 && lc.trsm_impl == 0 && dmma_update &&
       !lc.sync_each_launch && m > 2 * NB && !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mat) & 15))
     return k_potrf_lookahead(lc, m, Mat, ldm);
@@ -1644,7 +1704,38 @@ int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
 // updates that column first and defers the rest of its update until its panel is on the wire, so its
 // potf2 / TRSM chain overlaps the other ranks' updates (look-ahead across ranks, one stream per rank).
 // Bit-identical factors on all ranks by construction (every entry of L is computed by exactly one rank).
+static int ensure_dist_streams(LaunchCtx& lc) {
+  if (!lc.side_stream) {
+    int lo = 0, hi = 0;
+    LPB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    LPB_CUDA(cudaStreamCreateWithPriority(&lc.side_stream, cudaStreamNonBlocking, hi));
+    for (int e = 0; e < 2; ++e) {
+      LPB_CUDA(cudaEventCreateWithFlags(&lc.ev_col[e], cudaEventDisableTiming));
+      LPB_CUDA(cudaEventCreateWithFlags(&lc.ev_pan[e], cudaEventDisableTiming));
+    }
+  }
+  for (int e = 0; e < 4; ++e)
+    if (!lc.ev_dist[e]) LPB_CUDA(cudaEventCreateWithFlags(&lc.ev_dist[e], cudaEventDisableTiming));
+  return LPB_OK;
+}
+
 int k_potrf_dist_reserve(LaunchCtx& lc, int64_t m) {
+  const int64_t slot = 3 * (int64_t)NB * NB + round_up(m, NB) * NB;
+  if (lc.panel_slot_cap < slot) {
+    for (int i = 0; i < 2; ++i) {
+      if (lc.panel_slot[i]) cudaFree(lc.panel_slot[i]);
+      lc.panel_slot[i] = nullptr;
+    }
+    lc.panel_slot_cap = 0;
+    for (int i = 0; i < 2; ++i) {
+      void* p = nullptr;
+      LPB_CUDA(cudaMalloc(&p, sizeof(double) * (size_t)slot));
+      LPB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * (size_t)slot, lc.stream));
+      lc.panel_slot[i] = static_cast<double*>(p);
+    }
+    lc.panel_slot_cap = slot;
+  }
+  LPB_TRY(ensure_dist_streams(lc));
   const int64_t need = (int64_t)NB * NB + m * NB;
   if (lc.panel_buf_cap >= need) return LPB_OK;
   if (lc.panel_buf) cudaFree(lc.panel_buf);
@@ -1705,6 +1796,88 @@ static int k_potrf_dist(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm) {
     int update_owned(int p, int tile0) { return k_trailing_update_part(lc, m, Mat, ldm, k0(p), nb(p), tile0, 0, G, me); }
   } ops{lc, comm, m, ldm, Mat, G, me};
   LPB_TRY(potrf_dist_schedule(T, G, me, ops));
+  return finish_factor(lc, m, Mat, ldm);
+}
+
+// Schedule v2 of the distributed factorisation (dist_schedule.hpp::potrf_dist_schedule2): the panel is produced
+// straight into a packed buffer (slot k & 1), travels as two broadcasts (first the 128 rows the next owner needs
+// for its diagonal tile, then the rest), the updates read it from the buffer through a TMA map, and potf2 of the
+// next panel runs on the side stream while the rest of the panel is still on the wire.  Same kernels, same order
+// of updates per tile: the factor is bit-identical to the single-GPU one and to schedule 1.
+static int k_potrf_dist2(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm) {
+  const int G = lc.world, me = lc.rank;
+  ncclComm_t comm = static_cast<ncclComm_t>(lc.nccl_comm);
+  LPB_TRY(k_potrf_dist_reserve(lc, m));
+  const int T = (int)ceil_div(m, NB);
+  lc.linv_full = false;
+  struct Ops {
+    LaunchCtx& lc;
+    ncclComm_t comm;
+    int64_t m, ldm;
+    double* Mat;
+    int G, me;
+    cudaStream_t st(int side) const { return side ? lc.side_stream : lc.stream; }
+    int nb(int k) const { return (int)((m - (int64_t)k * NB) < NB ? (m - (int64_t)k * NB) : NB); }
+    double* linv(int k) const { return lc.chol_ws + (int64_t)k * NB * NB; }
+    double* slot(int k) const { return lc.panel_slot[k & 1]; }
+    int potf2(int k, int side) {
+      const PackedPanel pp(m, k);
+      potf2_inv_kernel<<<1, dim3(32, 16), kPotf2InvSmem, st(side)>>>(Mat, ldm, k * NB, nb(k), lc.info_dev, linv(k), 0,
+                                                                     slot(k) + (int64_t)NB * NB, slot(k) + pp.off_linv);
+      LPB_KCHECK(lc);
+      return LPB_OK;
+    }
+    int trsm(int k) {
+      const int64_t rem = m - (int64_t)k * NB - nb(k);
+      if (rem <= 0) return LPB_OK;
+      trsm_dmma_blocked_kernel<<<(unsigned)ceil_div(rem, TBR), 256, kTrsmDmmaSmem, lc.stream>>>(Mat, ldm, k * NB, (int)m,
+                                                                                               linv(k), slot(k));
+      LPB_KCHECK(lc);
+      return LPB_OK;
+    }
+    int bcast(double* p, int64_t count, int owner, int k, const char* what) {
+      if (count <= 0) return LPB_OK;
+      const ncclResult_t r = ncclBroadcast(p, p, (size_t)count, ncclDouble, owner, comm, lc.stream);
+      if (r != ncclSuccess) {
+        set_last_error("potrf_dist2: ncclBroadcast (%s) of panel %d -> %s", what, k, ncclGetErrorString(r));
+        return LPB_ERR_NCCL;
+      }
+      return LPB_OK;
+    }
+    int bcast_small(int k, int owner) { return bcast(slot(k), PackedPanel(m, k).r1 * NB, owner, k, "block k+1"); }
+    int bcast_large(int k, int owner) {
+      return bcast(slot(k) + (int64_t)NB * NB, PackedPanel(m, k).large_count, owner, k, "rest of the panel");
+    }
+    int record(int ev, int side) {
+      LPB_CUDA(cudaEventRecord(lc.ev_dist[ev], st(side)));
+      return LPB_OK;
+    }
+    int wait(int ev, int side) {
+      LPB_CUDA(cudaStreamWaitEvent(st(side), lc.ev_dist[ev], 0));
+      return LPB_OK;
+    }
+    int update(int p, int tile0, int single_col, int mod, int rem, int side) {
+      lc.launch_on_side = side != 0;
+      const int rc = k_trailing_update_part(lc, m, Mat, ldm, (int64_t)p * NB, nb(p), tile0, single_col, mod, rem, slot(p),
+                                            PackedPanel(m, p).map_rows);
+      lc.launch_on_side = false;
+      return rc;
+    }
+    int update_diag(int p, int col, int side) { return update(p, col, 2, 1, 0, side); }
+    int update_col_below(int p, int col) { return update(p, col, 3, 1, 0, 0); }
+    int update_owned(int p, int tile0) { return update(p, tile0, 0, G, me, 0); }
+    int unpack(int k) {
+      const PackedPanel pp(m, k);
+      const int64_t total = pp.rows_total * NB + (int64_t)NB * NB;
+      const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256 * 4), kNumSMs * 4);
+      panel_unpack2_kernel<<<grid, 256, 0, lc.stream>>>(Mat, ldm, pp.k0, m, slot(k), pp.off_linv, linv(k));
+      LPB_KCHECK(lc);
+      return LPB_OK;
+    }
+  } ops{lc, comm, m, ldm, Mat, G, me};
+  const int rc = potrf_dist_schedule2(T, G, me, ops);
+  lc.launch_on_side = false;
+  LPB_TRY(rc);
   return finish_factor(lc, m, Mat, ldm);
 }
 

@@ -84,13 +84,18 @@ struct LaunchCtx {
   // column-sharded contexts: the distributed factorisation (k_potrf_dist) broadcasts panels over NCCL
   void* nccl_comm = nullptr;       // ncclComm_t of this process, or null
   int rank = 0, world = 1;
-  int potrf_dist = 1;              // 0 = every rank factors the whole of M itself (replicated)
+  int potrf_dist = 2;              // 0 = replicated on every rank, 1 = one broadcast per panel, 2 = two broadcasts +
+                                   // side-stream potf2 + packed panels (dist_schedule.hpp, schedule v2)
   double* panel_buf = nullptr;     // packed panel + inverted diagonal block, the broadcast payload
   int64_t panel_buf_cap = 0;       // in doubles
   // single-GPU look-ahead of k_potrf: potf2 of panel k+1 runs on `side_stream` beside the trailing update of panel k
   int potrf_lookahead = 1;         // 0 = strictly sequential panels on `stream`
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_col[2] = {nullptr, nullptr}, ev_pan[2] = {nullptr, nullptr};
+  bool launch_on_side = false;     // the next trailing-update launch goes to side_stream (k_potrf_dist2)
+  cudaEvent_t ev_dist[4] = {nullptr, nullptr, nullptr, nullptr};  // kEvSmall / kEvPotf2 of dist_schedule.hpp
+  double* panel_slot[2] = {nullptr, nullptr};  // packed panels of the two-broadcast distributed factorisation
+  int64_t panel_slot_cap = 0;      // doubles per slot
   int update_grid_cap = 0;         // > 0: CTAs of the trailing update (leaves SMs free for the side stream)
   int* info_dev = nullptr;         // potrf info flag
   int* info_host = nullptr;        // pinned

@@ -78,4 +78,68 @@ int potrf_dist_schedule(int T, int G, int me, Ops& ops) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ schedule v2
+// The same factorisation with a shorter serial chain per panel.  What sits between "panel k finished on its
+// owner" and "panel k+1 finished on ITS owner" in the schedule above is
+//     pack -> broadcast (whole panel) -> unpack -> column update -> potf2 -> TRSM ,
+// here it is
+//     broadcast of ONE 128 x 128 block -> diagonal-tile update -> potf2 -> TRSM :
+//  * the panel is produced straight into a packed send buffer (potf2 / TRSM write M and the buffer), and the
+//    updates read it from there (TMA map over the buffer), so pack and unpack leave the chain (non-owners copy
+//    the panel into their M after the updates that read it);
+//  * the panel travels as TWO broadcasts: first the rows of block k+1 -- all the next owner needs to bring its
+//    DIAGONAL tile up to date and start potf2(k+1) -- then the rest.  potf2(k+1) runs on a side stream while the
+//    rest of the panel arrives and the column below the diagonal tile is updated on the main stream.
+// Buffers: panel p lives in slot p & 1.  Every tile still sees the same updates in the same order as in the
+// single-GPU loop, so the factor stays bit-identical.
+// Ops (all return an lpb status, 0 = ok; `side` = 1 selects the side stream):
+//   potf2(k, side)  trsm(k)  bcast_small(k, owner)  bcast_large(k, owner)
+//   record(ev, side)  wait(ev, side)            ev = kEvSmall + (k & 1)  or  kEvPotf2 + (k & 1)
+//   update_diag(p, col, side)  update_col_below(p, col)  update_owned(p, tile0)  unpack(k)
+enum { kEvSmall = 0, kEvPotf2 = 2, kNumDistEvents = 4 };
+
+template <class Ops>
+int potrf_dist_schedule2(int T, int G, int me, Ops& ops) {
+#define LPB_S2(call)            \
+  do {                          \
+    const int rc__ = (call);    \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+  int pending = -1;  // panel whose update of the owned columns >= pending + 2 (and whose unpack) this rank still owes
+  for (int k = 0; k < T; ++k) {
+    const int owner = k % G;
+    if (owner == me) {
+      if (k == 0)
+        LPB_S2(ops.potf2(0, 0));
+      else
+        LPB_S2(ops.wait(kEvPotf2 + (k & 1), 0));  // potf2(k) ran on the side stream during step k - 1
+      LPB_S2(ops.trsm(k));
+    }
+    if (k + 1 < T) {
+      LPB_S2(ops.bcast_small(k, owner));
+      LPB_S2(ops.record(kEvSmall + (k & 1), 0));
+    }
+    LPB_S2(ops.bcast_large(k, owner));
+    if (pending >= 0) {
+      LPB_S2(ops.update_owned(pending, pending + 2));
+      if (pending % G != me) LPB_S2(ops.unpack(pending));
+      pending = -1;
+    }
+    if (k + 1 < T && (k + 1) % G == me) {
+      LPB_S2(ops.wait(kEvSmall + (k & 1), 1));
+      LPB_S2(ops.update_diag(k, k + 1, 1));
+      LPB_S2(ops.potf2(k + 1, 1));
+      LPB_S2(ops.record(kEvPotf2 + ((k + 1) & 1), 1));
+      LPB_S2(ops.update_col_below(k, k + 1));
+      pending = k;
+    } else {
+      if (k + 1 < T) LPB_S2(ops.update_owned(k, k + 1));
+      if (owner != me) LPB_S2(ops.unpack(k));
+    }
+  }
+  if (pending >= 0 && pending % G != me) LPB_S2(ops.unpack(pending));  // cannot happen (pending < T - 1), kept for safety
+#undef LPB_S2
+  return 0;
+}
+
 }  // namespace lpb

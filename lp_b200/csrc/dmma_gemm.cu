@@ -167,7 +167,7 @@ struct LoadCursor {
 // (ntr x 1: the look-ahead update of the next panel's column); SHAPE_OWNED the block columns this rank
 // owns in the distributed factorisation (OwnedCols).
 enum { MODE_SYRK = 0, MODE_UPDATE = 1, MODE_TRSM = 2 };
-enum { SHAPE_TRI = 0, SHAPE_COL = 1, SHAPE_OWNED = 2 };
+enum { SHAPE_TRI = 0, SHAPE_COL = 1, SHAPE_OWNED = 2, SHAPE_COLB = 3 };  // COLB: column tile0 WITHOUT its diagonal tile
 
 // VAR (experiments on the trailing update): bit 0 = accumulate from zero and read-modify-write C in
 // the epilogue instead of initialising the accumulators from C; bit 1 = CTA barrier at every tile end;
@@ -176,7 +176,10 @@ template <int MODE, bool SCALE, int VAR = 0>
 __global__ void __maxnreg__(255)
 syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  double* __restrict__ C, int64_t ldc, int m_total, int tile0, int ntr, int k_begin, int nkb,
-                 int col_origin, int shape, OwnedCols own) {
+                 int col_origin, int shape, OwnedCols own, int p_row0) {
+  // p_row0 >= 0 (MODE_UPDATE only): the panel P is read from a PACKED buffer (tmA maps it: 128 columns, row
+  // (r - p_row0) of the panel at buffer row (r - p_row0), except that the first two 128-row blocks are swapped:
+  // the rows of block p_row0 / 128 + 1 come first, see k_potrf_dist2) instead of from columns k_begin.. of C.
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base + kSmemA, sB = smem_base + kSmemB, sD = smem_base + kSmemD;
@@ -193,13 +196,16 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
 
   const int ntiles = (MODE == MODE_TRSM || shape == SHAPE_COL) ? ntr
-                     : (shape == SHAPE_OWNED ? own.count() : ntr * (ntr + 1) / 2);
+                     : (shape == SHAPE_COLB ? ntr - 1 : (shape == SHAPE_OWNED ? own.count() : ntr * (ntr + 1) / 2));
   const bool is_producer = threadIdx.x == 0;
   constexpr uint32_t kBytes = 2 * kTileBytes + (SCALE ? kDBytes : 0);
 
   auto decode = [&](int L, int* ti, int* tj) {
     if (MODE == MODE_TRSM || shape == SHAPE_COL) {
       *ti = L;
+      *tj = 0;
+    } else if (shape == SHAPE_COLB) {
+      *ti = L + 1;
       *tj = 0;
     } else if (shape == SHAPE_OWNED) {
       own.decode(L, ti, tj);
@@ -231,11 +237,18 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t full = bar_full + pc.stage * 8;
     mbar_expect_tx(full, kBytes);
     const int k = k_begin + pc.kb * BK;
-    tma_load_2d(sA + pc.stage * kTileBytes, &tmA, k, pc.row_i, full);
+    int ra = pc.row_i, rb = pc.row_j;
+    if (MODE == MODE_UPDATE && p_row0 >= 0) {  // packed panel: block (p_row0 / 128 + 1) sits at buffer row 0
+      ra -= p_row0;
+      rb -= p_row0;
+      if (ra == BM) ra = 0;
+      if (rb == BN) rb = 0;
+    }
+    tma_load_2d(sA + pc.stage * kTileBytes, &tmA, k, ra, full);
     if (MODE == MODE_TRSM)
       tma_load_2d(sB + pc.stage * kTileBytes, &tmB, pc.kb * BK, 0, full);
     else
-      tma_load_2d(sB + pc.stage * kTileBytes, &tmA, k, pc.row_j, full);
+      tma_load_2d(sB + pc.stage * kTileBytes, &tmA, k, rb, full);
     if (SCALE) tma_load_2d(sD + pc.stage * kDBytes, &tmB, k, 0, full);
     if (++pc.stage == kStages) {
       pc.stage = 0;
@@ -419,7 +432,7 @@ int make_tmap(CUtensorMap* tm, const double* base, uint64_t rows, uint64_t cols,
 template <int MODE, bool SCALE, int VAR = 0>
 int launch_dmma(LaunchCtx& lc, const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int m_total,
                 int tile0, int ntr, int k_begin, int nkb, int col_origin, int shape = SHAPE_TRI,
-                OwnedCols own = OwnedCols{1, 0, 0}) {
+                OwnedCols own = OwnedCols{1, 0, 0}, int p_row0 = -1) {
   static PerDeviceOnce once;  // one per template instantiation
   auto kern = syrk_dmma_kernel<MODE, SCALE, VAR>;
   LPB_TRY(once.run([&](int) -> int {
@@ -427,12 +440,13 @@ int launch_dmma(LaunchCtx& lc, const CUtensorMap& tmA, const CUtensorMap& tmB, d
     return LPB_OK;
   }));
   const int ntiles = (MODE == MODE_TRSM || shape == SHAPE_COL) ? ntr
-                     : (shape == SHAPE_OWNED ? own.count() : ntr * (ntr + 1) / 2);
+                     : (shape == SHAPE_COLB ? ntr - 1 : (shape == SHAPE_OWNED ? own.count() : ntr * (ntr + 1) / 2));
   if (ntiles <= 0) return LPB_OK;
   int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
   if (MODE == MODE_UPDATE && lc.update_grid_cap > 0 && grid > lc.update_grid_cap) grid = lc.update_grid_cap;
-  kern<<<grid, kThreads, kSmemAlloc, lc.stream>>>(tmA, tmB, C, ldc, m_total, tile0, ntr, k_begin, nkb, col_origin, shape,
-                                                  own);
+  cudaStream_t st = lc.launch_on_side ? lc.side_stream : lc.stream;
+  kern<<<grid, kThreads, kSmemAlloc, st>>>(tmA, tmB, C, ldc, m_total, tile0, ntr, k_begin, nkb, col_origin, shape, own,
+                                           p_row0);
   lc.launches++;
   LPB_CUDA(cudaGetLastError());
   return LPB_OK;
@@ -490,22 +504,37 @@ int k_trailing_update_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, i
 // single_col: only block column tile0 (look-ahead); otherwise the block columns J >= tile0 with
 // J % own_mod == own_rem (own_mod == 1: all of them).
 int k_trailing_update_part(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb, int tile0,
-                           int single_col, int own_mod, int own_rem) {
-  const int ntr = (int)ceil_div(m, BM) - tile0;
+                           int single_col, int own_mod, int own_rem, const double* packed, int64_t packed_rows) {
+  int ntr = (int)ceil_div(m, BM) - tile0;
   if (ntr <= 0) return LPB_OK;
   if ((kb % BK) || (ldm & 1) || (reinterpret_cast<uintptr_t>(Mat) & 15) || (int64_t)tile0 * BM < k0 + kb) {
     set_last_error("trailing_update_part: bad panel / tile origin");
     return LPB_ERR_BAD_ARGUMENT;
   }
   CUtensorMap tm;
-  LPB_TRY(make_tmap(&tm, Mat, (uint64_t)m, (uint64_t)m, (uint64_t)ldm, BM, BK, true));
-  const int shape = single_col ? SHAPE_COL : (own_mod <= 1 ? SHAPE_TRI : SHAPE_OWNED);
+  int k_begin = (int)k0, p_row0 = -1;
+  if (packed) {  // the panel comes from a packed buffer (128 doubles per row), see syrk_dmma_kernel::p_row0
+    LPB_TRY(make_tmap(&tm, packed, (uint64_t)packed_rows, (uint64_t)BN, (uint64_t)BN, BM, BK, true));
+    k_begin = 0;
+    p_row0 = (int)k0;
+  } else {
+    LPB_TRY(make_tmap(&tm, Mat, (uint64_t)m, (uint64_t)m, (uint64_t)ldm, BM, BK, true));
+  }
+  // single_col: 1 = the whole block column tile0, 2 = only its diagonal tile, 3 = the column without its diagonal tile
+  int shape = SHAPE_TRI;
+  if (single_col == 1) shape = SHAPE_COL;
+  if (single_col == 2) {
+    shape = SHAPE_COL;
+    ntr = 1;
+  }
+  if (single_col == 3) shape = SHAPE_COLB;
+  if (!single_col && own_mod > 1) shape = SHAPE_OWNED;
   const OwnedCols own = shape == SHAPE_OWNED ? OwnedCols::make(own_mod, own_rem, tile0, ntr) : OwnedCols{1, 0, 0};
   if (lc.update_impl == 2)  // products accumulated from zero, C read-modify-written once per panel (see VAR)
-    return launch_dmma<MODE_UPDATE, false, 1>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, (int)k0, (int)(kb / BK), 0, shape,
-                                              own);
-  return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, (int)k0, (int)(kb / BK), 0, shape,
-                                         own);
+    return launch_dmma<MODE_UPDATE, false, 1>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, k_begin, (int)(kb / BK), 0, shape,
+                                              own, p_row0);
+  return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, k_begin, (int)(kb / BK), 0, shape, own,
+                                         p_row0);
 }
 
 // Panel TRSM as a GEMM: Mat[row0.., k0..k0+128) <- Mat[row0.., k0..k0+128) * Linv^T, row0 = k0 + 128,

@@ -88,8 +88,13 @@ int k_syrk_dmma(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t ld
                 int64_t ldc);
 int k_trailing_update_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb);
 // C -= P P^T restricted to a tile list (look-ahead column / the block columns one rank owns): see dmma_gemm.cu
+// single_col: 0 = a triangle / the owned columns, 1 = the whole block column tile0, 2 = only its diagonal tile,
+// 3 = the column without its diagonal tile.  packed != null: the panel is read from a packed buffer of
+// `packed_rows` rows of 128 doubles (k_potrf_dist2) instead of from Mat.  Launches on lc.side_stream when
+// lc.launch_on_side is set.
 int k_trailing_update_part(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb, int tile0,
-                           int single_col, int own_mod, int own_rem);
+                           int single_col, int own_mod, int own_rem, const double* packed = nullptr,
+                           int64_t packed_rows = 0);
 // panel TRSM as a DMMA GEMM with the inverted 128 x 128 diagonal block (dense, ld 128)
 int k_trsm_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, const double* Linv);
 // DMMA issue peak: register-only loop of independent DMMAs on every SM for ~seconds; TFLOP/s out

@@ -707,6 +707,10 @@ void ctx_free(lpb_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   if (c->lc.chol_ws) cudaFree(c->lc.chol_ws);
   if (c->lc.panel_buf) cudaFree(c->lc.panel_buf);
+  for (int i = 0; i < 2; ++i)
+    if (c->lc.panel_slot[i]) cudaFree(c->lc.panel_slot[i]);
+  for (int e = 0; e < 4; ++e)
+    if (c->lc.ev_dist[e]) cudaEventDestroy(c->lc.ev_dist[e]);
   if (c->lc.side_stream) {
     cudaStreamSynchronize(c->lc.side_stream);
     for (int e = 0; e < 2; ++e) {
@@ -1360,8 +1364,9 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
     c->packed_allreduce = value != 0;
     return LPB_OK;
   }
-  if (k == "potrf_dist") {  // 0: replicated factorisation on every rank of a sharded context
-    c->lc.potrf_dist = value != 0;
+  if (k == "potrf_dist") {  // sharded contexts: 0 = replicated factorisation on every rank, 1 = one broadcast per
+    if (value < 0 || value > 2) return LPB_ERR_BAD_ARGUMENT;  // panel, 2 = two broadcasts + side-stream potf2 (default)
+    c->lc.potrf_dist = (int)value;
     return LPB_OK;
   }
   if (k == "potrf_verify") {

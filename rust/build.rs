@@ -9,7 +9,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let lib = out.join("liblpb200.so");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
-    let sources = ["vec_kernels.cu", "dmma_gemm.cu", "cholesky.cu", "batched.cu", "lpb_api.cu"];
+    let sources = ["vec_kernels.cu", "dmma_gemm.cu", "cholesky.cu", "batched.cu", "presolve.cu", "lpb_api.cu"];
     let mut cmd = Command::new(nvcc);
     cmd.args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-shared",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-o"]).arg(&lib);

@@ -141,10 +141,176 @@ static void test_schedule(int T, int G) {
     }
 }
 
+
+// ---- schedule v2 (two streams, two broadcasts per panel, packed panel buffers): simulated with either stream
+// given priority whenever both can run, so a buffer slot that is overwritten too early shows up as a stale read.
+enum Op2Kind { P2_POTF2, P2_TRSM, P2_BSMALL, P2_BLARGE, P2_RECORD, P2_WAIT, P2_UDIAG, P2_UBELOW, P2_UOWNED, P2_UNPACK };
+struct Op2 {
+  Op2Kind kind;
+  int a, b, side;
+};
+struct Recorder2 {
+  std::vector<Op2> ops;
+  int potf2(int k, int side) { ops.push_back({P2_POTF2, k, 0, side}); return 0; }
+  int trsm(int k) { ops.push_back({P2_TRSM, k, 0, 0}); return 0; }
+  int bcast_small(int k, int owner) { ops.push_back({P2_BSMALL, k, owner, 0}); return 0; }
+  int bcast_large(int k, int owner) { ops.push_back({P2_BLARGE, k, owner, 0}); return 0; }
+  int record(int ev, int side) { ops.push_back({P2_RECORD, ev, 0, side}); return 0; }
+  int wait(int ev, int side) { ops.push_back({P2_WAIT, ev, 0, side}); return 0; }
+  int update_diag(int p, int col, int side) { ops.push_back({P2_UDIAG, p, col, side}); return 0; }
+  int update_col_below(int p, int col) { ops.push_back({P2_UBELOW, p, col, 0}); return 0; }
+  int update_owned(int p, int tile0) { ops.push_back({P2_UOWNED, p, tile0, 0}); return 0; }
+  int unpack(int k) { ops.push_back({P2_UNPACK, k, 0, 0}); return 0; }
+};
+struct Slot {
+  int panel = -1;
+  bool lkk = false, small_ = false, large = false;
+};
+
+static void test_schedule2(int T, int G, int side_first) {
+  std::vector<Recorder2> rec(G);
+  for (int r = 0; r < G; ++r) lpb::potrf_dist_schedule2(T, G, r, rec[r]);
+  std::vector<std::vector<std::vector<int>>> ver(G, std::vector<std::vector<int>>(T, std::vector<int>(T, 0)));
+  std::vector<std::vector<char>> inM(G, std::vector<char>(T, 0)), diag(G, std::vector<char>(T, 0));
+  std::vector<std::vector<Slot>> buf(G, std::vector<Slot>(2));
+  // per rank and stream: queue of op indices; dep[i] = index of the record a wait depends on; done[i]
+  std::vector<std::vector<std::vector<int>>> q(G, std::vector<std::vector<int>>(2));
+  std::vector<std::vector<int>> dep(G);
+  std::vector<std::vector<char>> done(G);
+  std::vector<std::vector<size_t>> head(G, std::vector<size_t>(2, 0));
+  for (int r = 0; r < G; ++r) {
+    const auto& ops = rec[r].ops;
+    dep[r].assign(ops.size(), -1);
+    done[r].assign(ops.size(), 0);
+    int last_rec[lpb::kNumDistEvents];
+    for (int& v : last_rec) v = -1;
+    for (size_t i = 0; i < ops.size(); ++i) {
+      q[r][ops[i].side].push_back((int)i);
+      if (ops[i].kind == P2_RECORD) last_rec[ops[i].a] = (int)i;
+      if (ops[i].kind == P2_WAIT) {
+        dep[r][i] = last_rec[ops[i].a];
+        CHECK(dep[r][i] >= 0, "rank %d waits for event %d that was never recorded (T=%d G=%d)", r, ops[i].a, T, G);
+      }
+    }
+  }
+  auto need = [&](int r, int p, bool small_, bool large, const char* what) {
+    const Slot& s = buf[r][p & 1];
+    CHECK(s.panel == p && (!small_ || s.small_) && (!large || s.large),
+          "rank %d %s reads panel %d from a slot holding panel %d (small %d large %d) (T=%d G=%d prio %d)", r, what, p,
+          s.panel, (int)s.small_, (int)s.large, T, G, side_first);
+  };
+  auto bump = [&](int r, int i, int j, int p) {
+    CHECK(ver[r][i][j] == p, "rank %d tile (%d,%d): panel %d applied out of order (seen %d) (T=%d G=%d)", r, i, j, p,
+          ver[r][i][j], T, G);
+    ver[r][i][j]++;
+  };
+  auto run_local = [&](int r, int idx) {
+    const Op2 op = rec[r].ops[idx];
+    switch (op.kind) {
+      case P2_POTF2: {
+        CHECK(op.a % G == r, "rank %d factors panel %d", r, op.a);
+        CHECK(ver[r][op.a][op.a] == op.a, "potf2(%d) on a diagonal tile with %d updates", op.a, ver[r][op.a][op.a]);
+        diag[r][op.a] = 1;
+        Slot& s = buf[r][op.a & 1];
+        s = Slot();
+        s.panel = op.a;
+        s.lkk = true;
+        break;
+      }
+      case P2_TRSM: {
+        CHECK(diag[r][op.a], "trsm(%d) before potf2", op.a);
+        for (int i = op.a + 1; i < T; ++i)
+          CHECK(ver[r][i][op.a] == op.a, "trsm(%d): tile (%d,%d) has %d updates", op.a, i, op.a, ver[r][i][op.a]);
+        Slot& s = buf[r][op.a & 1];
+        CHECK(s.panel == op.a && s.lkk, "trsm(%d) packs into a slot holding panel %d", op.a, s.panel);
+        s.small_ = s.large = true;
+        inM[r][op.a] = 1;
+        break;
+      }
+      case P2_UDIAG: need(r, op.a, true, false, "update_diag"); bump(r, op.b, op.b, op.a); break;
+      case P2_UBELOW:
+        need(r, op.a, true, true, "update_col_below");
+        for (int i = op.b + 1; i < T; ++i) bump(r, i, op.b, op.a);
+        break;
+      case P2_UOWNED:
+        if (op.b < T) need(r, op.a, true, true, "update_owned");
+        for (int j = op.b; j < T; ++j)
+          if (j % G == r)
+            for (int i = j; i < T; ++i) bump(r, i, j, op.a);
+        break;
+      case P2_UNPACK:
+        need(r, op.a, op.a + 1 < T, true, "unpack");
+        CHECK(buf[r][op.a & 1].lkk, "unpack(%d) without the diagonal block", op.a);
+        inM[r][op.a] = 1;
+        break;
+      default: break;
+    }
+  };
+  for (;;) {
+    bool progress = false;
+    for (int r = 0; r < G; ++r)
+      for (int pass = 0; pass < 2; ++pass) {
+        const int st = side_first ? 1 - pass : pass;
+        while (head[r][st] < q[r][st].size()) {
+          const int idx = q[r][st][head[r][st]];
+          const Op2& op = rec[r].ops[idx];
+          if (op.kind == P2_BSMALL || op.kind == P2_BLARGE) break;
+          if (op.kind == P2_WAIT && dep[r][idx] >= 0 && !done[r][dep[r][idx]]) break;
+          run_local(r, idx);
+          done[r][idx] = 1;
+          head[r][st]++;
+          progress = true;
+          if (side_first && st == 0) break;  // let the side stream catch up after every main-stream op
+        }
+      }
+    // a broadcast completes when every rank's main stream sits at the same one
+    bool all_at = true, any_left = false;
+    int k = -1, kind = -1, owner = -1;
+    for (int r = 0; r < G; ++r) {
+      if (head[r][0] >= q[r][0].size()) { all_at = false; continue; }
+      any_left = true;
+      const Op2& op = rec[r].ops[q[r][0][head[r][0]]];
+      if (op.kind != P2_BSMALL && op.kind != P2_BLARGE) { all_at = false; continue; }
+      if (k < 0) { k = op.a; kind = op.kind; owner = op.b; }
+      if (op.a != k || op.kind != kind) { CHECK(false, "ranks disagree on the next broadcast (T=%d G=%d)", T, G); return; }
+    }
+    if (all_at && any_left) {
+      const Slot& src = buf[owner][k & 1];
+      CHECK(src.panel == k && src.small_ && src.large && src.lkk, "panel %d broadcast before its owner %d finished it", k, owner);
+      for (int r = 0; r < G; ++r) {
+        if (r != owner) {
+          Slot& d = buf[r][k & 1];
+          if (kind == P2_BSMALL) { d = Slot(); d.panel = k; d.small_ = true; }
+          else { if (d.panel != k) { d = Slot(); d.panel = k; } d.large = d.lkk = true; }
+        }
+        done[r][q[r][0][head[r][0]]] = 1;
+        head[r][0]++;
+      }
+      progress = true;
+    }
+    bool finished = true;
+    for (int r = 0; r < G; ++r)
+      for (int st = 0; st < 2; ++st)
+        if (head[r][st] < q[r][st].size()) finished = false;
+    if (finished) break;
+    if (!progress) { CHECK(false, "schedule v2 deadlock (T=%d G=%d prio %d)", T, G, side_first); return; }
+  }
+  for (int r = 0; r < G; ++r)
+    for (int k = 0; k < T; ++k) {
+      CHECK(inM[r][k], "v2: rank %d never stored panel %d (T=%d G=%d)", r, k, T, G);
+      if (k % G == r)
+        for (int i = k; i < T; ++i) CHECK(ver[r][i][k] == k, "v2: owned tile (%d,%d) saw %d panels", i, k, ver[r][i][k]);
+    }
+}
+
 int main() {
   test_decode();
   for (int G : {2, 3, 4, 8})
-    for (int T : {1, 2, 3, 4, 7, 8, 9, 16, 17, 33}) test_schedule(T, G);
+    for (int T : {1, 2, 3, 4, 7, 8, 9, 16, 17, 33}) {
+      test_schedule(T, G);
+      test_schedule2(T, G, 0);
+      test_schedule2(T, G, 1);
+    }
   if (fails) {
     std::printf("%d check(s) failed\n", fails);
     return 1;

@@ -86,7 +86,8 @@ def _worker(rank, world, port, q):
             A_k, b, c_k = sp.download()
             res = solver.solve_resident(sp)
         out["syn"] = (A_k, b, c_k, sp.col0, res.x(), res.fun(), res.iteration())
-        # distributed (panel-broadcast) vs replicated factorisation on the same all-reduced M
+        # distributed factorisation (2: two broadcasts per panel + side-stream potf2 + packed panels, the default;
+        # 1: one broadcast per panel) vs the replicated one (0) on the same all-reduced M
         from lp_b200 import _ffi
         lib = _ffi.load()
         m, n, seed = BIG
@@ -94,7 +95,7 @@ def _worker(rank, world, port, q):
         pb = lp_b200.Problem.target(c).ub(A_ub, b_ub).eq(A_eq, b_eq).build()
         ldm = (m + 15) // 16 * 16
         big = {}
-        for mode in (1, 0):
+        for mode in (2, 1, 0):
             with ShardedProblem(pb, rank, world, dist) as sp:
                 sp.set_option("potrf_dist", mode)
                 sp.set_option("check_replicas", 1)
@@ -146,7 +147,7 @@ def test_two_gpu_column_sharded_solve_matches_oracle_and_one_gpu():
     # the same order of updates as the replicated run -> identical bits across ranks AND across the two modes
     ref = o.InteriorPoint().solve(o.build_problem(*o.synthetic_lp(*BIG)))
     for rank in (0, 1):
-        for mode in (1, 0):
+        for mode in (2, 1, 0):
             L, x, fun, it = results[rank]["big"][mode]
             np.testing.assert_array_equal(L, results[0]["big"][0][0])
             assert abs(it - ref.iteration) <= 1

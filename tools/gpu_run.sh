@@ -2,7 +2,7 @@
 # One parameterised GPU-box script (replaces the per-call scripts of round 1).  Usage, under gpurun:
 #   bash tools/gpu_run.sh TAG step [step ...]
 # Steps:  tests | tests:<pytest -k expr> | smoke | bench:<WL> | benchq:<WL> (1 step, no CPU leg) | diag:<WL>[,<WL>]
-#         | dtau:<WL>:<K> | time:<m>[,<m>] | create:<WL> | launches:<WL> | ncu:<WL>:<kernel regex>:<skip>:<count> | ref:<WL>
+#         | dtau:<WL>:<K> | bias | time:<m>[,<m>] | create:<WL> | launches:<WL> | ncu:<WL>:<kernel regex>:<skip>:<count> | ref:<WL>
 # Everything is written under gpurun_out/ with TAG in the name; a failing step does not stop the later ones.
 set -u
 TAG=$1; shift
@@ -37,6 +37,9 @@ for step in "$@"; do
       IFS=: read -r wl k <<< "$arg"
       timeout 900 python tools/diag_dtau.py $wl $k > gpurun_out/dtau_${wl}_${k}_${TAG}.log 2>&1
       echo "[$step] rc=$?"; cat gpurun_out/dtau_${wl}_${k}_${TAG}.log | tail -40;;
+    bias)
+      timeout 600 python tools/dmma_bias.py > gpurun_out/dmma_bias_${TAG}.log 2>&1
+      echo "[$step] rc=$?"; cat gpurun_out/dmma_bias_${TAG}.log;;
     time)
       timeout 600 python tools/time_kernels.py ${arg//,/ } > gpurun_out/time_${TAG}.log 2>&1
       echo "[$step] rc=$?"; cat gpurun_out/time_${TAG}.log | tail -4;;
