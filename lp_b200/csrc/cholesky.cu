@@ -155,65 +155,100 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
   }
   __syncthreads();
 
-  for (int kb = 0; kb < NSB; ++kb) {
-    const int c0 = kb * SB;
-    if (warp == 0) {
-      // ---- the serial heart of the factorisation: ONE warp factors the 16 x 16 diagonal sub-block and inverts
-      // it in the same 16 pivot steps.  Lanes 0..15 hold row i of the sub-block (v[k] = a[i][k]); lanes 16..31
-      // hold the running sums of the forward substitution L x = e_i for column i of X = inv(L_dd)
-      // (v[r] = sum_{l<r} L[r][l] x_l, replaced by x_r at step r).  Both need exactly column j of L at pivot
-      // step j -- broadcast through shared memory -- and then the same FMA  v[k] += mult * L[k][j], k > j.
-      // sqrt and the divisions are one rsqrt plus Newton corrections (results within an ulp of IEEE).
-      const int i = lane & 15;
-      const bool inv_lane = lane >= SB;
-      double v[SB];
+  // ---- the serial heart of the factorisation: ONE warp factors the 16 x 16 diagonal sub-block at c0 and inverts
+  // it in the same 16 pivot steps.  Lanes 0..15 hold row i of the sub-block (v[k] = a[i][k]); lanes 16..31
+  // hold the running sums of the forward substitution L x = e_i for column i of X = inv(L_dd)
+  // (v[r] = sum_{l<r} L[r][l] x_l, replaced by x_r at step r).  Both need exactly column j of L at pivot
+  // step j -- broadcast through shared memory -- and then the same FMA  v[k] += mult * L[k][j], k > j.
+  // sqrt and the divisions are one rsqrt plus Newton corrections (results within an ulp of IEEE).
+  auto factor_sub = [&](int c0) {
+    const int i = lane & 15;
+    const bool inv_lane = lane >= SB;
+    double v[SB];
 #pragma unroll
-      for (int k = 0; k < SB; ++k) v[k] = (!inv_lane && k <= i) ? S[(c0 + i) * LDS + c0 + k] : 0.0;
-      // the diagonal entry of this lane's row lives in its own register: the next pivot then depends only on
-      // rsqrt -> l -> dg -= l * l, not on the shared-memory round trip of the column broadcast
-      double dg = inv_lane ? 0.0 : S[(c0 + i) * LDS + c0 + i];
-      double myrd = 1.0;
+    for (int k = 0; k < SB; ++k) v[k] = (!inv_lane && k <= i) ? S[(c0 + i) * LDS + c0 + k] : 0.0;
+    // the diagonal entry of this lane's row lives in its own register: the next pivot then depends only on
+    // rsqrt -> l -> dg -= l * l, not on the shared-memory round trip of the column broadcast
+    double dg = inv_lane ? 0.0 : S[(c0 + i) * LDS + c0 + i];
+    double myrd = 1.0;
+    double ajj = __shfl_sync(full, dg, 0);
+    double rs = rsqrt(ajj);
 #pragma unroll
-      for (int j = 0; j < SB; ++j) {
-        const double ajj = __shfl_sync(full, dg, j);
-        const bool bad = !(ajj > 0.0) || !isfinite(ajj);
-        if (bad && lane == 0 && *info == 0) *info = k0 + c0 + j + 1;
-        // rsqrt is accurate to 1 ulp (CUDA math API), so d = a rs and l = a[i][j] rs are within 2 ulp of sqrt and of
-        // the quotient: far below the n eps backward error of the factorisation itself, and the pivot chain
-        // SHFL -> rsqrt -> l -> dg stays short (no divisions, no Newton steps, no divergent branch).
-        double rs = rsqrt(ajj);
-        double d = ajj * rs;
-        if (bad) d = rs = __longlong_as_double(0x7ff8000000000000ll);
-        const double num = inv_lane ? ((i == j ? 1.0 : 0.0) - v[j]) : v[j];  // inverse lanes: x_j of column i
-        double l = num * rs;
-        if (!inv_lane && i == j) l = d;
-        if (i == j) myrd = rs;
-        v[j] = l;
-        if (!inv_lane && i > j) dg = fma(-l, l, dg);
-        double* cb = cbuf + (j & 1) * SB;
-        if (!inv_lane) cb[i] = l;
-        __syncwarp();
-        const double mult = inv_lane ? l : -l;
-#pragma unroll
-        for (int k = 0; k < SB; ++k)
-          if (k > j) v[k] = fma(mult, cb[k], v[k]);  // entries above a row's diagonal are garbage, never read
+    for (int j = 0; j < SB; ++j) {
+      const bool bad = !(ajj > 0.0) || !isfinite(ajj);
+      if (bad && lane == 0 && *info == 0) *info = k0 + c0 + j + 1;
+      // rsqrt is accurate to 1 ulp (CUDA math API), so d = a rs and l = a[i][j] rs are within 2 ulp of sqrt and of
+      // the quotient: far below the n eps backward error of the factorisation itself, and the pivot chain
+      // SHFL -> rsqrt -> l -> dg stays short (no divisions, no Newton steps, no divergent branch).
+      double d = ajj * rs;
+      if (bad) d = rs = __longlong_as_double(0x7ff8000000000000ll);
+      const double num = inv_lane ? ((i == j ? 1.0 : 0.0) - v[j]) : v[j];  // inverse lanes: x_j of column i
+      double l = num * rs;
+      if (!inv_lane && i == j) l = d;
+      if (i == j) myrd = rs;
+      v[j] = l;
+      if (!inv_lane && i > j) dg = fma(-l, l, dg);
+      double* cb = cbuf + (j & 1) * SB;
+      if (!inv_lane) cb[i] = l;
+      __syncwarp();
+      if (j + 1 < SB) {  // the next pivot and its rsqrt start now: their latency hides behind the column update
+        ajj = __shfl_sync(full, dg, j + 1);
+        rs = rsqrt(ajj);
       }
-      if (!inv_lane) {
-        rdiag[c0 + i] = myrd;
+      const double mult = inv_lane ? l : -l;
 #pragma unroll
-        for (int k = 0; k < SB; ++k)
-          if (k <= i) S[(c0 + i) * LDS + c0 + k] = v[k];
-      }
-      __syncwarp();  // the factor rows are written before the transposed inverse lands above the diagonal
-      if (inv_lane) {
+      for (int k = 0; k < SB; ++k)
+        if (k > j) v[k] = fma(mult, cb[k], v[k]);  // entries above a row's diagonal are garbage, never read
+    }
+    if (!inv_lane) {
+      rdiag[c0 + i] = myrd;
 #pragma unroll
-        for (int r = 0; r < SB; ++r) {
-          Xd[r * XDP + i] = (r >= i) ? v[r] : 0.0;          // X[r][c = i], zero above the diagonal
-          if (r > i) S[(c0 + i) * LDS + c0 + r] = v[r];     // X^T in the upper triangle
-        }
+      for (int k = 0; k < SB; ++k)
+        if (k <= i) S[(c0 + i) * LDS + c0 + k] = v[k];
+    }
+    __syncwarp();  // the factor rows are written before the transposed inverse lands above the diagonal
+    if (inv_lane) {
+#pragma unroll
+      for (int r = 0; r < SB; ++r) {
+        Xd[r * XDP + i] = (r >= i) ? v[r] : 0.0;          // X[r][c = i], zero above the diagonal
+        if (r > i) S[(c0 + i) * LDS + c0 + r] = v[r];     // X^T in the upper triangle
       }
     }
-    __syncthreads();
+  };
+  // rank-16 update of the 16 x 16 sub-block t of the trailing lower triangle of step kb (t = 0: the next diagonal one)
+  auto update_sub = [&](int kb, int t) {
+    const int c0 = kb * SB;
+    const int ii = lane & 15, jh = lane >> 4;
+    int bi = 0;
+    while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+    const int bj = t - bi * (bi + 1) / 2;
+    const int ri = (kb + 1 + bi) * SB + ii;
+    const int cj = (kb + 1 + bj) * SB + 8 * jh;
+    double pr[SB];
+#pragma unroll
+    for (int l = 0; l < SB; ++l) pr[l] = S[ri * LDS + c0 + l];
+    double acc[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const double* pj = S + (cj + jj) * LDS + c0;
+      double sum = 0.0;
+#pragma unroll
+      for (int l = 0; l < SB; ++l) sum += pr[l] * pj[l];
+      acc[jj] = sum;
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+      if (cj + jj <= ri) S[ri * LDS + cj + jj] -= acc[jj];
+  };
+
+  // Look-ahead inside the block: after the rows below sub-block kb are solved, warp 0 updates ONLY the next diagonal
+  // sub-block and goes straight on to factor it, while the other 15 warps apply the rank-16 update to the rest of
+  // the trailing triangle -- the serial warp no longer waits for (nor makes everybody wait behind) the bulk update.
+  // Same arithmetic per entry as the plain loop (every sub-block sees the same updates in the same order).
+  if (warp == 0) factor_sub(0);
+  for (int kb = 0; kb < NSB; ++kb) {
+    const int c0 = kb * SB;
+    __syncthreads();  // inv(L_dd) of sub-block kb is in Xd; every update of step kb - 1 has landed
     // ---- rows below the sub-block: P[r][c] = sum_{l<=c} S[r][c0+l] X[c][l]   (4 columns per thread)
     {
       const int r = c0 + SB + (tid >> 2), q = tid & 3;
@@ -226,10 +261,10 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const double* xr = Xd + (4 * q + e) * XDP;
-          double s = 0.0;
+          double sum = 0.0;
 #pragma unroll
-          for (int l = 0; l < SB; ++l) s += row[l] * xr[l];
-          out[e] = s;
+          for (int l = 0; l < SB; ++l) sum += row[l] * xr[l];
+          out[e] = sum;
         }
       }
       __syncwarp();  // the four threads of a row sit in one warp: all reads of the row precede its writes
@@ -239,36 +274,20 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
       }
     }
     __syncthreads();
-    // ---- rank-16 update of the remaining 16 x 16 sub-blocks (lower triangle), one per warp per round
-    {
-      const int nrem = NSB - 1 - kb;
-      const int T = nrem * (nrem + 1) / 2;
-      const int ii = lane & 15, jh = lane >> 4;
-      for (int t = warp; t < T; t += 16) {
-        int bi = 0;
-        while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
-        const int bj = t - bi * (bi + 1) / 2;
-        const int ri = (kb + 1 + bi) * SB + ii;
-        const int cj = (kb + 1 + bj) * SB + 8 * jh;
-        double pr[SB];
-#pragma unroll
-        for (int l = 0; l < SB; ++l) pr[l] = S[ri * LDS + c0 + l];
-        double acc[8];
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const double* pj = S + (cj + jj) * LDS + c0;
-          double s = 0.0;
-#pragma unroll
-          for (int l = 0; l < SB; ++l) s += pr[l] * pj[l];
-          acc[jj] = s;
-        }
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj)
-          if (cj + jj <= ri) S[ri * LDS + cj + jj] -= acc[jj];
+    // ---- rank-16 update of the remaining 16 x 16 sub-blocks (lower triangle)
+    const int nrem = NSB - 1 - kb;
+    const int T = nrem * (nrem + 1) / 2;
+    if (warp == 0) {
+      if (T > 0) {
+        update_sub(kb, 0);
+        __syncwarp();
+        factor_sub(c0 + SB);
       }
+    } else {
+      for (int t = warp; t < T; t += 15) update_sub(kb, t);
     }
-    __syncthreads();
   }
+  __syncthreads();
 
   // ---- L back to Mat (and, for the distributed factorisation, into the packed send buffer: dense 128 x 128, zero
   // above the diagonal and beyond a ragged block)
@@ -1650,7 +1669,7 @@ int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
     lc.ws_m = m;
   }
   LPB_CUDA(cudaMemsetAsync(lc.info_dev, 0, sizeof(int), lc.stream));
-  const bool dmma_update = lc.update_impl == 0 || lc.update_impl == 2;
+  const bool dmma_update = lc.update_impl == 0 || lc.update_impl == 2 || lc.update_impl == 6;
   if (lc.world > 1 && lc.nccl_comm && lc.potrf_dist && syrk_impl == 0 && lc.trsm_impl == 0 && dmma_update &&
       m > NB && !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mat) & 15))
     return lc.potrf_dist == 2 ? k_potrf_dist2(lc, m, Mat, ldm) : k_potrf_dist(lc, m, Mat, ldm);

@@ -43,6 +43,25 @@ constexpr uint32_t kSmemBar = kSmemD + kStages * kDBytes;
 constexpr uint32_t kSmemTotal = kSmemBar + 2 * kStages * 8;
 constexpr uint32_t kSmemAlloc = kSmemTotal + 1024;  // slack for 1024-byte alignment
 
+// Shared-memory plan per kernel variant.  VAR bit 3 (MODE_UPDATE only, "C prefetch"): the 128 x 128 tile of C that
+// seeds the accumulators is fetched by TMA into shared memory (8 boxes of 128 x 16, same swizzled layout as an
+// operand stage) while the PREVIOUS tile is still in its main loop, so its HBM latency no longer sits at the head
+// of every tile (K is only 128 there: 25 % of a tile's time was the exposed load + store of C).  The ring shrinks to
+// 3 stages / a lead of 2 K-blocks to make room: 96 KB ring + 128 KB C tile.
+template <int MODE, int VAR>
+struct Plan {
+  static constexpr bool kCpf = MODE == 1 && (VAR & 8) != 0;
+  static constexpr int kNS = kCpf ? 3 : kStages;
+  static constexpr int kLd = kCpf ? 2 : kLead;
+  static constexpr uint32_t kA = 0;
+  static constexpr uint32_t kB = kA + kNS * kTileBytes;
+  static constexpr uint32_t kC = kB + kNS * kTileBytes;                  // 1024-byte aligned (multiples of 16 KB)
+  static constexpr uint32_t kD = kC + (kCpf ? 8 * kTileBytes : 0);
+  static constexpr uint32_t kBar = kD + kNS * kDBytes;
+  static constexpr uint32_t kTotal = kBar + (2 * kNS + 2) * 8;
+  static constexpr uint32_t kAlloc = kTotal + 1024;
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -180,17 +199,23 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // p_row0 >= 0 (MODE_UPDATE only): the panel P is read from a PACKED buffer (tmA maps it: 128 columns, row
   // (r - p_row0) of the panel at buffer row (r - p_row0), except that the first two 128-row blocks are swapped:
   // the rows of block p_row0 / 128 + 1 come first, see k_potrf_dist2) instead of from columns k_begin.. of C.
+  using P = Plan<MODE, VAR>;
+  constexpr int NS = P::kNS, LEAD = P::kLd;
+  constexpr bool CPF = P::kCpf;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = smem_base + kSmemA, sB = smem_base + kSmemB, sD = smem_base + kSmemD;
-  const uint32_t bar_full = smem_base + kSmemBar, bar_empty = bar_full + kStages * 8;
+  const uint32_t sA = smem_base + P::kA, sB = smem_base + P::kB, sD = smem_base + P::kD, sC = smem_base + P::kC;
+  const uint32_t bar_full = smem_base + P::kBar, bar_empty = bar_full + NS * 8;
+  const uint32_t bar_cfull = bar_empty + NS * 8, bar_cempty = bar_cfull + 8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(bar_full + s * 8, 1);
       mbar_init(bar_empty + s * 8, kConsumerWarps);
     }
+    mbar_init(bar_cfull, 1);
+    mbar_init(bar_cempty, kConsumerWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -250,7 +275,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     else
       tma_load_2d(sB + pc.stage * kTileBytes, &tmA, k, rb, full);
     if (SCALE) tma_load_2d(sD + pc.stage * kDBytes, &tmB, k, 0, full);
-    if (++pc.stage == kStages) {
+    if (++pc.stage == NS) {
       pc.stage = 0;
       pc.phase ^= 1u;
     }
@@ -260,9 +285,25 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       cursor_tile();
     }
   };
+  // C prefetch (CPF): the tile of C for this CTA's n-th tile travels through sC; tmB maps the matrix C lives in.
+  int c_next = blockIdx.x;  // tile whose C is fetched next (producer only)
+  int c_issued = 0;         // number of C tiles requested so far
+  auto produce_c = [&]() {
+    if (!CPF || c_next >= ntiles) return;
+    if (c_issued > 0) mbar_wait(bar_cempty, static_cast<uint32_t>((c_issued - 1) & 1));  // all 8 warps seeded from sC
+    int ti, tj;
+    decode(c_next, &ti, &tj);
+    const int r0 = (tile0 + ti) * BM, c0 = (tile0 + tj) * BN;
+    mbar_expect_tx(bar_cfull, 8 * kTileBytes);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) tma_load_2d(sC + b * kTileBytes, &tmB, c0 + b * BK, r0, bar_cfull);
+    c_next += gridDim.x;
+    ++c_issued;
+  };
   if (is_producer) {
     cursor_tile();
-    for (int i = 0; i < kLead; ++i) produce_one();
+    produce_c();
+    for (int i = 0; i < LEAD; ++i) produce_one();
   }
 
   // -------------------------------------------------------------- DMMA consumers (all 8 warps)
@@ -276,14 +317,34 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t dof[2] = {static_cast<uint32_t>((2 * t + 0) << 4), static_cast<uint32_t>((2 * t + 1) << 4)};
 
   const uint32_t rt_zero = static_cast<uint32_t>(static_cast<uint64_t>(ldc) >> 62);  // 0 at run time, opaque to the compiler
-  for (int L = blockIdx.x; L < ntiles; L += gridDim.x) {
+  int tile_n = 0;  // tiles this CTA has started (parity of the C-prefetch barriers)
+  for (int L = blockIdx.x; L < ntiles; L += gridDim.x, ++tile_n) {
     int ti, tj;
     decode(L, &ti, &tj);
     const int row0 = (tile0 + ti) * BM + wm * 64 + g;
     const int col0 = (MODE == MODE_TRSM ? col_origin : (tile0 + tj) * BN) + wn * 32 + 2 * t;
     const int col_limit = MODE == MODE_TRSM ? col_origin + BN : m_total;
     double acc[8][4][2];
-    if (MODE == MODE_UPDATE && !(VAR & 1)) {
+    if (CPF) {
+      // seed the accumulators from the prefetched tile: box = 16-column group, 128-byte rows, chunk ^ (row & 7)
+      mbar_wait(bar_cfull, static_cast<uint32_t>(tile_n & 1));
+      uint32_t dep = 0;
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi) {
+        const uint32_t rbase = sC + static_cast<uint32_t>(wm * 64 + mi * 8 + g) * 128u;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const uint32_t box = static_cast<uint32_t>(wn * 2 + (ni >> 1)) * kTileBytes;
+          const uint32_t chunk = static_cast<uint32_t>((((ni & 1) * 4 + t) ^ g) << 4);
+          const double2 v = lds_v2(rbase + box + chunk);
+          acc[mi][ni][0] = v.x;
+          acc[mi][ni][1] = v.y;
+          if (mi == 7 && ni == 3) dep = static_cast<uint32_t>(__double2hiint(v.y));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_after_loads(bar_cempty, dep, rt_zero);  // sC may be refilled once all 8 warps are here
+    } else if (MODE == MODE_UPDATE && !(VAR & 1)) {
       // start from C: the loads overlap the wait for the first operand stages
 #pragma unroll
       for (int mi = 0; mi < 8; ++mi) {
@@ -308,7 +369,10 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int kb = 0; kb < nkb; ++kb) {
       // keep the ring kLead iterations ahead: the stage being refilled was released kStages - kLead
       // iterations ago, so this wait does not normally stall
-      if (is_producer) produce_one();
+      if (is_producer) {
+        if (CPF && kb == 0) produce_c();  // next tile's C: lands during this tile's main loop
+        produce_one();
+      }
       mbar_wait(bar_full + stage * 8, phase);
       const uint32_t a_base = sA + stage * kTileBytes + offA;
       const uint32_t b_base = sB + stage * kTileBytes + offB;
@@ -355,7 +419,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         else
           mbar_arrive_after_loads(bar_empty + stage * 8, dep, rt_zero);
       }
-      if (++stage == kStages) {
+      if (++stage == NS) {
         stage = 0;
         phase ^= 1u;
       }
@@ -436,7 +500,7 @@ int launch_dmma(LaunchCtx& lc, const CUtensorMap& tmA, const CUtensorMap& tmB, d
   static PerDeviceOnce once;  // one per template instantiation
   auto kern = syrk_dmma_kernel<MODE, SCALE, VAR>;
   LPB_TRY(once.run([&](int) -> int {
-    LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemAlloc));
+    LPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Plan<MODE, VAR>::kAlloc));
     return LPB_OK;
   }));
   const int ntiles = (MODE == MODE_TRSM || shape == SHAPE_COL) ? ntr
@@ -445,7 +509,7 @@ int launch_dmma(LaunchCtx& lc, const CUtensorMap& tmA, const CUtensorMap& tmB, d
   int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
   if (MODE == MODE_UPDATE && lc.update_grid_cap > 0 && grid > lc.update_grid_cap) grid = lc.update_grid_cap;
   cudaStream_t st = lc.launch_on_side ? lc.side_stream : lc.stream;
-  kern<<<grid, kThreads, kSmemAlloc, st>>>(tmA, tmB, C, ldc, m_total, tile0, ntr, k_begin, nkb, col_origin, shape, own,
+  kern<<<grid, kThreads, Plan<MODE, VAR>::kAlloc, st>>>(tmA, tmB, C, ldc, m_total, tile0, ntr, k_begin, nkb, col_origin, shape, own,
                                            p_row0);
   lc.launches++;
   LPB_CUDA(cudaGetLastError());
@@ -511,14 +575,15 @@ int k_trailing_update_part(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, i
     set_last_error("trailing_update_part: bad panel / tile origin");
     return LPB_ERR_BAD_ARGUMENT;
   }
-  CUtensorMap tm;
+  CUtensorMap tm, tmc;
   int k_begin = (int)k0, p_row0 = -1;
+  LPB_TRY(make_tmap(&tmc, Mat, (uint64_t)m, (uint64_t)m, (uint64_t)ldm, BM, BK, true));  // C tiles (VAR bit 3)
   if (packed) {  // the panel comes from a packed buffer (128 doubles per row), see syrk_dmma_kernel::p_row0
     LPB_TRY(make_tmap(&tm, packed, (uint64_t)packed_rows, (uint64_t)BN, (uint64_t)BN, BM, BK, true));
     k_begin = 0;
     p_row0 = (int)k0;
   } else {
-    LPB_TRY(make_tmap(&tm, Mat, (uint64_t)m, (uint64_t)m, (uint64_t)ldm, BM, BK, true));
+    tm = tmc;
   }
   // single_col: 1 = the whole block column tile0, 2 = only its diagonal tile, 3 = the column without its diagonal tile
   int shape = SHAPE_TRI;
@@ -533,6 +598,11 @@ int k_trailing_update_part(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, i
   if (lc.update_impl == 2)  // products accumulated from zero, C read-modify-written once per panel (see VAR)
     return launch_dmma<MODE_UPDATE, false, 1>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, k_begin, (int)(kb / BK), 0, shape,
                                               own, p_row0);
+  if (lc.update_impl == 6)  // C tile prefetched through shared memory (VAR bit 3): measured NOT faster -- C3 potrf
+    // 53.6 ms against 52.6 ms, C2 2.84 against 2.79 (profiles/README.md): the head-of-tile load already overlapped the
+    // wait for the first operand stage, and the ring shrinks from 5 to 3 stages to make room.  Kept as an option.
+    return launch_dmma<MODE_UPDATE, false, 8>(lc, tm, tmc, Mat, ldm, (int)m, tile0, ntr, k_begin, (int)(kb / BK), 0,
+                                              shape, own, p_row0);
   return launch_dmma<MODE_UPDATE, false>(lc, tm, tm, Mat, ldm, (int)m, tile0, ntr, k_begin, (int)(kb / BK), 0, shape, own,
                                          p_row0);
 }

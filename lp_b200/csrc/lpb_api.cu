@@ -1334,7 +1334,7 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
     return LPB_OK;
   }
   if (k == "trsm_impl" || k == "update_impl") {
-    if (value < 0 || value > 5) return LPB_ERR_BAD_ARGUMENT;
+    if (value < 0 || value > 6) return LPB_ERR_BAD_ARGUMENT;
     (k == "trsm_impl" ? c->lc.trsm_impl : c->lc.update_impl) = (int)value;
     return LPB_OK;
   }

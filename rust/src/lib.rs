@@ -13,13 +13,14 @@
 //! every control-flow decision of `solve_normal_form` (`solvers/interior_point.rs`), and drives the iteration
 //! through the phase calls of `include/lpb200.h` (`ffi.rs`); `A`, `M`, its Cholesky factor and the iterate live in
 //! HBM.  There is no CPU fallback and no backend feature: the one backend is `liblpb200.so`, built by `build.rs`
-//! with nvcc for sm_100a.  `f64` only (the parity bar of the path is FP64); the type parameter `F` is kept so that
-//! `Problem<f64>`, `InteriorPoint<f64>`, `LinearProgramError<f64>` spell exactly as in the reference.
+//! with nvcc for sm_100a.  `Problem<F>` / `InteriorPoint<F>` exist for `F = f64` and `F = f32` like the reference's (`float.rs`); the arithmetic
+//! is FP64 in both cases (an `f32` problem is widened on upload, its result narrowed on the way back).
 #![deny(unsafe_code)] // like the reference's lint set (.cargo/config.toml:6); `ffi` and its two callers opt out
 #![allow(non_snake_case)]
 
 pub mod error;
 pub mod ffi;
+pub mod float;
 pub mod linear_program;
 pub mod prelude;
 pub mod solvers;

@@ -6,8 +6,8 @@
 //! min_x c ' x   st   A x == b,  x >= 0          A = [[A_ub, I], [A_eq, 0]],  b = [b_ub; b_eq],  c = [c; 0]
 //! ```
 use crate::error::LinearProgramError;
+use crate::float::Float;
 use ndarray::{s, Array1, Array2};
-use std::fmt::Debug;
 
 /// A linear program in slack form (only equality constraints, `x >= 0`).
 pub struct Problem<F> {
@@ -18,14 +18,14 @@ pub struct Problem<F> {
     n_slack: usize,
 }
 
-impl Problem<f64> {
+impl<F: Float> Problem<F> {
     /// Start the builder with the cost vector `c` of `min c'x` (reference `linear_program.rs:37-39`).
-    pub fn target(c: &Array1<f64>) -> ProblemBuilder<'_, f64> {
+    pub fn target(c: &Array1<F>) -> ProblemBuilder<'_, F> {
         ProblemBuilder::new(c)
     }
 }
 
-impl<F: Copy + Debug> Problem<F> {
+impl<F: Float> Problem<F> {
     /// The slack-form constraint matrix (row-major, `m x n`).
     pub fn A(&self) -> &Array2<F> {
         &self.A
@@ -63,27 +63,27 @@ pub struct ProblemBuilder<'a, F> {
     eq: Option<(&'a Array2<F>, &'a Array1<F>)>,
 }
 
-impl<'a> ProblemBuilder<'a, f64> {
+impl<'a, F: Float> ProblemBuilder<'a, F> {
     /// Start building a problem with cost vector `c`.
-    pub fn new(c: &'a Array1<f64>) -> Self {
+    pub fn new(c: &'a Array1<F>) -> Self {
         ProblemBuilder { c, ub: None, eq: None }
     }
 
     /// Inequality block `A x <= b`.
-    pub fn ub(mut self, A: &'a Array2<f64>, b: &'a Array1<f64>) -> Self {
+    pub fn ub(mut self, A: &'a Array2<F>, b: &'a Array1<F>) -> Self {
         self.ub = Some((A, b));
         self
     }
 
     /// Equality block `A x == b`.
-    pub fn eq(mut self, A: &'a Array2<f64>, b: &'a Array1<f64>) -> Self {
+    pub fn eq(mut self, A: &'a Array2<F>, b: &'a Array1<F>) -> Self {
         self.eq = Some((A, b));
         self
     }
 
     /// Validate the shapes and assemble the slack form (reference `linear_program.rs:125-169`):
     /// `Unconstrained` without any row, `IncompatibleInputDimensions` on a shape mismatch.
-    pub fn build(self) -> Result<Problem<f64>, LinearProgramError<f64>> {
+    pub fn build(self) -> Result<Problem<F>, LinearProgramError<F>> {
         let n_c = self.c.len();
         let (rows_ub, cols_ub, len_b_ub) = match self.ub {
             Some((A, b)) => (A.nrows(), A.ncols(), b.len()),
@@ -100,13 +100,14 @@ impl<'a> ProblemBuilder<'a, f64> {
             return Err(LinearProgramError::IncompatibleInputDimensions);
         }
         let (m, n) = (rows_ub + rows_eq, n_c + rows_ub);
-        let mut A = Array2::<f64>::zeros((m, n));
-        let mut b = Array1::<f64>::zeros(m);
-        let mut c = Array1::<f64>::zeros(n);
+        let (zero, one) = (F::from_f64(0.0), F::from_f64(1.0));
+        let mut A = Array2::<F>::from_elem((m, n), zero);
+        let mut b = Array1::<F>::from_elem(m, zero);
+        let mut c = Array1::<F>::from_elem(n, zero);
         if let Some((A_ub, b_ub)) = self.ub {
             A.slice_mut(s![..rows_ub, ..n_c]).assign(A_ub);
             for i in 0..rows_ub {
-                A[[i, n_c + i]] = 1.0; // the slack block [I; 0]
+                A[[i, n_c + i]] = one; // the slack block [I; 0]
             }
             b.slice_mut(s![..rows_ub]).assign(b_ub);
         }
@@ -115,6 +116,6 @@ impl<'a> ProblemBuilder<'a, f64> {
             b.slice_mut(s![rows_ub..]).assign(b_eq);
         }
         c.slice_mut(s![..n_c]).assign(self.c);
-        Ok(Problem { A, b, c, c0: 0.0, n_slack: rows_ub })
+        Ok(Problem { A, b, c, c0: zero, n_slack: rows_ub })
     }
 }

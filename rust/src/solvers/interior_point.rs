@@ -18,6 +18,7 @@ use ndarray::Array1;
 use super::{OptimizeResult, Solver};
 use crate::error::LinearProgramError;
 use crate::ffi::{self, CtxGuard};
+use crate::float::Float;
 use crate::linear_program::Problem;
 
 type LpResult<T> = Result<T, LinearProgramError<f64>>;
@@ -55,21 +56,21 @@ pub struct InteriorPointBuilder<F> {
     max_iter: usize,
 }
 
-impl InteriorPointBuilder<f64> {
+impl<F: Float> InteriorPointBuilder<F> {
     pub(crate) fn new() -> Self {
         // reference mod.rs:51-60
         InteriorPointBuilder {
-            tol: 1e-8,
+            tol: F::from_f64(1e-8),
             disp: false,
             ip: true,
             solver_type: EquationSolverType::Cholesky,
-            alpha0: 0.99995,
+            alpha0: F::from_f64(0.99995),
             max_iter: 1000,
         }
     }
 
     /// Convergence tolerance on the indicators (small, positive).
-    pub fn tol(mut self, tol: f64) -> Self {
+    pub fn tol(mut self, tol: F) -> Self {
         self.tol = tol;
         self
     }
@@ -93,7 +94,7 @@ impl InteriorPointBuilder<f64> {
     }
 
     /// Step-size multiplier, `0 < alpha0 < 1`.
-    pub fn alpha0(mut self, alpha0: f64) -> Self {
+    pub fn alpha0(mut self, alpha0: F) -> Self {
         self.alpha0 = alpha0;
         self
     }
@@ -105,11 +106,11 @@ impl InteriorPointBuilder<f64> {
     }
 
     /// Validate (reference `mod.rs:118-128`) and create the solver.
-    pub fn build(self) -> LpResult<InteriorPoint<f64>> {
-        if self.alpha0 <= 0.0 || self.alpha0 >= 1.0 {
+    pub fn build(self) -> Result<InteriorPoint<F>, LinearProgramError<F>> {
+        if self.alpha0.to_f64() <= 0.0 || self.alpha0.to_f64() >= 1.0 {
             return Err(LinearProgramError::InvalidParameter("Alpha0 must be between 0 and 1 (exclusive)"));
         }
-        if self.tol <= 0.0 {
+        if self.tol.to_f64() <= 0.0 {
             return Err(LinearProgramError::InvalidParameter("The tolerance must be nonnegative."));
         }
         Ok(InteriorPoint {
@@ -134,19 +135,40 @@ pub struct InteriorPoint<F> {
     max_iter: usize,
 }
 
-impl Default for InteriorPoint<f64> {
+impl<F: Float> Default for InteriorPoint<F> {
     fn default() -> Self {
         InteriorPointBuilder::new().build().unwrap() // the defaults pass validation (reference mod.rs:157)
     }
 }
 
-impl Solver<f64> for InteriorPoint<f64> {
+impl<F: Float> Solver<F> for InteriorPoint<F> {
     /// Reference `mod.rs:161-169`: run the loop, then `fun = c . x_slack + c0` and strip the slack variables.
     /// `fun` is formed on the device by `lpb_extract_x` (same dot product, `linear_program.rs:61-63`).
-    fn solve(&self, problem: &Problem<f64>) -> LpResult<OptimizeResult<f64>> {
-        let (x_slack, fun, iteration) = self.solve_normal_form(problem)?;
-        let x = problem.denormalize_x_into(x_slack);
-        Ok(OptimizeResult::new(x, fun, iteration))
+    /// `F = f32`: the slack form is widened to FP64 for the upload and `x` / `fun` are narrowed back.
+    fn solve(&self, problem: &Problem<F>) -> Result<OptimizeResult<F>, LinearProgramError<F>> {
+        let a = problem.A().mapv(Float::to_f64);
+        let b = problem.b().mapv(Float::to_f64);
+        let c = problem.c().mapv(Float::to_f64);
+        match self.solve_normal_form(&a, &b, &c, problem.c0().to_f64()) {
+            Ok((x_slack, fun, iteration)) => {
+                let x = problem.denormalize_x_into(x_slack.mapv(F::from_f64));
+                Ok(OptimizeResult::new(x, F::from_f64(fun), iteration))
+            }
+            Err(e) => Err(narrow_error(e)),
+        }
+    }
+}
+
+/// The loop reports in FP64; the caller's error type carries `F`.
+fn narrow_error<F: Float>(e: LinearProgramError<f64>) -> LinearProgramError<F> {
+    match e {
+        LinearProgramError::Unconstrained => LinearProgramError::Unconstrained,
+        LinearProgramError::NumericalProblem => LinearProgramError::NumericalProblem,
+        LinearProgramError::InvalidParameter(s) => LinearProgramError::InvalidParameter(s),
+        LinearProgramError::IncompatibleInputDimensions => LinearProgramError::IncompatibleInputDimensions,
+        LinearProgramError::Infeasible => LinearProgramError::Infeasible,
+        LinearProgramError::Unbounded => LinearProgramError::Unbounded,
+        LinearProgramError::IterationLimitExceeded(x) => LinearProgramError::IterationLimitExceeded(x.mapv(F::from_f64)),
     }
 }
 
@@ -279,45 +301,46 @@ fn extract_x(ctx: &CtxGuard, tau: f64, n: usize) -> LpResult<(Array1<f64>, f64)>
     Ok((Array1::from(x), fun))
 }
 
-impl InteriorPoint<f64> {
+impl<F: Float> InteriorPoint<F> {
     /// Customise the solver through the builder (reference `mod.rs:195-197`).
-    pub fn custom() -> InteriorPointBuilder<f64> {
+    pub fn custom() -> InteriorPointBuilder<F> {
         InteriorPointBuilder::new()
     }
 
     fn options(&self) -> ffi::lpb_options {
         ffi::lpb_options {
-            tol: self.tol,
+            tol: self.tol.to_f64(),
             disp: self.disp as i32,
             ip: self.ip as i32,
             solver_type: self.solver_type.code(),
             reserved: 0,
-            alpha0: self.alpha0,
+            alpha0: self.alpha0.to_f64(),
             max_iter: self.max_iter as i64,
         }
     }
 
     /// The loop of reference `mod.rs:199-240`.  Returns `(x / tau in slack form, c . x / tau + c0, iterations)`.
-    fn solve_normal_form(&self, problem: &Problem<f64>) -> LpResult<(Array1<f64>, f64, usize)> {
+    fn solve_normal_form(&self, a: &ndarray::Array2<f64>, b: &Array1<f64>, c: &Array1<f64>, c0: f64)
+                         -> LpResult<(Array1<f64>, f64, usize)> {
         let opts = self.options();
+        let (tol, alpha0) = (opts.tol, opts.alpha0);
         // SAFETY: opts is a valid, initialised struct.
         check(unsafe { ffi::lpb_options_validate(&opts) })?; // Inverse / LeastSquares -> InvalidParameter
 
-        let (m, n) = problem.A().dim();
-        let a = problem.A().as_standard_layout(); // row-major, as build() made it (no copy)
-        let b = problem.b().as_standard_layout();
-        let c = problem.c().as_standard_layout();
+        let (m, n) = a.dim();
+        let a = a.as_standard_layout(); // row-major, as build() made it (no copy)
+        let b = b.as_standard_layout();
+        let c = c.as_standard_layout();
         let ctx = CtxGuard::create(
             m,
             n,
             a.as_slice().expect("standard layout"),
             b.as_slice().expect("standard layout"),
             c.as_slice().expect("standard layout"),
-            problem.c0(),
+            c0,
         )
         .map_err(device_error)?;
         let h = ctx.raw();
-        let c0 = problem.c0();
 
         let (mut tau, mut kappa) = (1.0f64, 1.0f64); // feasible_point.rs:29-30
         // SAFETY (all phase calls below): `h` is the live context owned by `ctx`; out-pointers are valid locals.
@@ -379,7 +402,7 @@ impl InteriorPoint<f64> {
             check(unsafe { ffi::lpb_assemble_delta(h, d_tau, axz.as_mut_ptr()) })?;
 
             // ---- step (mod.rs:216-223)
-            let alpha = if ip { 1.0 } else { step_size(axz, tau, d_tau, kappa, d_kappa, self.alpha0) };
+            let alpha = if ip { 1.0 } else { step_size(axz, tau, d_tau, kappa, d_kappa, alpha0) };
             check(unsafe { ffi::lpb_do_step(h, alpha, ip as c_int) })?; // feasible_point.rs:76-106
             tau += d_tau * alpha;
             kappa += d_kappa * alpha;
@@ -395,7 +418,7 @@ impl InteriorPoint<f64> {
             if self.disp {
                 println!("{:3.8}\t{}", alpha, indicators); // mod.rs:227-229
             }
-            match indicators.status(tau, kappa, self.tol) {
+            match indicators.status(tau, kappa, tol) {
                 Status::Optimal => {
                     let (x, fun) = extract_x(&ctx, tau, n)?;
                     return Ok((x, fun, iteration)); // mod.rs:231
@@ -420,7 +443,7 @@ mod tests {
 
     #[test]
     fn default_builder_doesnt_panic() {
-        assert_eq!(InteriorPoint::default(), InteriorPoint::custom().build().unwrap());
+        assert_eq!(InteriorPoint::<f64>::default(), InteriorPoint::custom().build().unwrap());
     }
 
     #[test]
@@ -465,6 +488,16 @@ mod tests {
         let problem = Problem::target(&c).ub(&A_ub, &b_ub).build().unwrap();
         let res = InteriorPoint::default().solve(&problem).unwrap();
         assert_abs_diff_eq!(*res.x(), array![0.5, 0.0, 1.25], epsilon = 1e-6);
+    }
+
+    #[test]
+    fn f32_problems_are_solved_in_f64_and_narrowed() {
+        let A_ub = array![[-3f32, 1.], [1., 2.]];
+        let b_ub = array![6f32, 4.];
+        let c = array![-1f32, 4.];
+        let problem = Problem::target(&c).ub(&A_ub, &b_ub).build().unwrap();
+        let res = InteriorPoint::<f32>::default().solve(&problem).unwrap();
+        assert_abs_diff_eq!(*res.x(), array![4f32, 0.], epsilon = 1e-5);
     }
 
     #[test]

@@ -2,7 +2,7 @@
 # One parameterised GPU-box script (replaces the per-call scripts of round 1).  Usage, under gpurun:
 #   bash tools/gpu_run.sh TAG step [step ...]
 # Steps:  tests | tests:<pytest -k expr> | smoke | bench:<WL> | benchq:<WL> (1 step, no CPU leg) | diag:<WL>[,<WL>]
-#         | dtau:<WL>:<K> | bias | time:<m>[,<m>] | create:<WL> | launches:<WL> | ncu:<WL>:<kernel regex>:<skip>:<count> | ref:<WL>
+#         | dtau:<WL>:<K> | bias | benchn:<WL>:<N>:<potrf_dist> | benchfull:<N> | time:<m>[,<m>] | create:<WL> | launches:<WL> | ncu:<WL>:<kernel regex>:<skip>:<count> | ref:<WL>
 # Everything is written under gpurun_out/ with TAG in the name; a failing step does not stop the later ones.
 set -u
 TAG=$1; shift
@@ -27,6 +27,16 @@ for step in "$@"; do
     benchq)
       timeout 600 python bench.py --workload $arg --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/benchq_${arg}_${TAG}.json 2> gpurun_out/benchq_${arg}_${TAG}.err
       echo "[$step] rc=$? $(python tools/phase_line.py gpurun_out/benchq_${arg}_${TAG}.json)";;
+    benchn)   # benchn:<WL>:<N>:<potrf_dist>  -- N ranks on one box through torchrun, 1 step, no CPU leg
+      IFS=: read -r wl ng pd <<< "$arg"
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $ng --master-addr 127.0.0.1 --master-port 29511 \
+        bench.py --gpus $ng --workload $wl --steps 1 --warmup 1 --no-cpu-baseline --potrf-dist $pd --no-c5 \
+        > gpurun_out/benchn_${wl}_n${ng}_d${pd}_${TAG}.json 2> gpurun_out/benchn_${wl}_n${ng}_d${pd}_${TAG}.err
+      echo "[$step] rc=$? $(python tools/phase_line.py gpurun_out/benchn_${wl}_n${ng}_d${pd}_${TAG}.json)";;
+    benchfull)   # benchfull:<N>  -- the driver's own command line at N ranks (C3 headline + C5 record)
+      timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $arg --master-addr 127.0.0.1 --master-port 29512 \
+        bench.py --gpus $arg --steps 2 --warmup 1 > gpurun_out/benchfull_n${arg}_${TAG}.json 2> gpurun_out/benchfull_n${arg}_${TAG}.err
+      echo "[$step] rc=$? $(python tools/phase_line.py gpurun_out/benchfull_n${arg}_${TAG}.json)";;
     ref)
       timeout 900 python bench.py --impl reference --workload $arg --steps 1 --warmup 0 > gpurun_out/ref_${arg}_${TAG}.json 2> gpurun_out/ref_${arg}_${TAG}.err
       echo "[$step] rc=$? $(head -c 700 gpurun_out/ref_${arg}_${TAG}.json)";;
