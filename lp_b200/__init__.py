@@ -14,6 +14,7 @@ from .api import (  # noqa: F401
     pinned_empty,
     presolve,
     Presolved,
+    release_cached_contexts,
     EquationSolverType,
     IncompatibleInputDimensions,
     Infeasible,
@@ -32,7 +33,7 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "BatchedResult", "ResidentProblem", "ShardedProblem", "SyntheticShardedProblem", "solve_batched", "pinned_empty", "presolve", "Presolved",
+    "BatchedResult", "ResidentProblem", "ShardedProblem", "SyntheticShardedProblem", "solve_batched", "pinned_empty", "presolve", "Presolved", "release_cached_contexts",
     "EquationSolverType", "IncompatibleInputDimensions", "Infeasible", "InteriorPoint", "InteriorPointBuilder",
     "InvalidParameter", "IterationLimitExceeded", "LinearProgramError", "NumericalProblem", "OptimizeResult",
     "Problem", "ProblemBuilder", "Solver", "Unbounded", "Unconstrained",

@@ -351,9 +351,29 @@ class InteriorPoint(Solver):
         return hash(self._key())
 
     def solve(self, problem: Problem) -> OptimizeResult:
-        """Solver::solve (mod.rs:161-169): upload, run the loop on the GPU, de-normalise."""
-        with ResidentProblem(problem) as rp:
+        """Solver::solve (mod.rs:161-169): upload, run the loop on the GPU, de-normalise.
+
+        The device context (A, M, the vectors, the factorisation workspaces: ~1.6x the size of A) is kept per host
+        thread between calls and re-used when the next problem has the same shape -- the call then costs the H2D
+        of A, b, c, the solve and the D2H of x, no cudaMalloc / cudaFree.  `release_cached_contexts()` frees it."""
+        cache = _solve_cache.__dict__
+        rp = cache.get("rp")
+        A = problem.A()
+        if rp is not None and rp.handle is not None and (rp.m, rp.n) == A.shape:
+            rp.reupload(problem)
+        else:
+            if rp is not None:
+                rp.close()
+            cache["rp"] = None
+            rp = ResidentProblem(problem)
+            cache["rp"] = rp
+        rp._problem = None        # uploads are synchronous: the cache must not pin the caller's host buffers
+        try:
             return self.solve_resident(rp)
+        except DeviceError:
+            rp.close()            # a context that reported a CUDA / NCCL failure is not re-used
+            cache["rp"] = None
+            raise
 
     def solve_resident(self, rp: "ResidentProblem") -> OptimizeResult:
         lib = _ffi.load()
@@ -371,6 +391,16 @@ class InteriorPoint(Solver):
         if dt != np.float64:  # Problem<f32>: FP64 arithmetic, result narrowed to the caller's float type
             return OptimizeResult(x.astype(dt), float(dt.type(fun.value)), it.value)
         return OptimizeResult(x, fun.value, it.value)
+
+
+_solve_cache = __import__("threading").local()
+
+
+def release_cached_contexts():
+    """Free the device context `InteriorPoint.solve` keeps for the calling thread."""
+    rp = _solve_cache.__dict__.pop("rp", None)
+    if rp is not None:
+        rp.close()
 
 
 class ResidentProblem:
@@ -395,9 +425,14 @@ class ResidentProblem:
 
     def reupload(self, problem: Problem):
         A = problem.A()
+        if A.shape != (self.m, self.n):
+            raise IncompatibleInputDimensions()
         rc = _ffi.load().lpb_set_problem(self.handle, A.ctypes.data, self.n, problem.b().ctypes.data,
                                          problem.c().ctypes.data, problem.c0(), _ffi.LPB_MEM_HOST)
         _raise_for(rc)
+        self.n_slack = problem.n_slack()
+        self.result_dtype = problem.dtype()
+        self._problem = problem
 
     def profile(self) -> dict:
         p = _ffi.lpb_profile()

@@ -266,3 +266,26 @@ def test_f32_problems_are_widened_and_results_narrowed():
     np.testing.assert_allclose(res.x(), [1.0, 0.0], atol=1e-6)
     assert lp_b200.InteriorPoint.default().solve(
         lp_b200.Problem.target(c.astype(np.float64)).ub(A_ub, b_ub).build()).x().dtype == np.float64
+
+
+def test_cached_context_is_reused_across_solves_without_leaking_state():
+    """InteriorPoint.solve keeps the device context per thread and re-uploads into it when the shape repeats: a
+    different LP of the same shape, then one WITHOUT a slack block (structure analysis must be redone), must give
+    exactly what a fresh context gives."""
+    solver = lp_b200.InteriorPoint.default()
+    pbs = []
+    for seed in (0, 1):
+        c, A_ub, b_ub, A_eq, b_eq = o.synthetic_lp(256, 512, seed)
+        pbs.append(lp_b200.Problem.target(c).ub(A_ub, b_ub).eq(A_eq, b_eq).build())
+    rng = np.random.default_rng(9)                       # 256 x 512 again, equality rows only: no singleton columns
+    A = rng.standard_normal((256, 512))
+    pbs.append(lp_b200.Problem.target(A.T @ rng.standard_normal(256) + rng.uniform(0.5, 1.5, 512))
+               .eq(A, A @ rng.uniform(0.5, 1.5, 512)).build())
+    lp_b200.release_cached_contexts()
+    cached = [solver.solve(pb) for pb in pbs + pbs[:1]]
+    for pb, got in zip(pbs + pbs[:1], cached):
+        with ResidentProblem(pb) as rp:
+            want = solver.solve_resident(rp)
+        assert got.iteration() == want.iteration() and got.fun() == want.fun()
+        np.testing.assert_array_equal(got.x(), want.x())
+    lp_b200.release_cached_contexts()
