@@ -81,6 +81,23 @@ constexpr int NSB = NB / SB;  // 8
 constexpr int XDP = SB + 1;   // pitch of the 16 x 16 inverse of the current diagonal sub-block
 constexpr int TWP = 9;        // pitch of the per-warp 16 x 8 scratch of the block-inverse step
 
+// 1 / sqrt(a) for a pivot, on the serial chain of the panel kernel: an FP32 seed (MUFU.RSQ) and three explicit
+// Newton steps in FP64 (23 -> 46 -> 92 -> full bits; the last one makes the result correctly rounded in all but a
+// few cases per million, i.e. within 1 ulp like the library's rsqrt) -- 15 instructions without the special-case
+// handling of the library routine.  Pivots outside the FP32 range take the library path (uniform branch: the pivot
+// is a warp-wide broadcast); non-positive and non-finite pivots come out as NaN / inf / 0 exactly as there.
+__device__ __forceinline__ double pivot_rsqrt(double a) {
+  if (!(a > 1e-30) || !(a < 1e30)) return rsqrt(a);
+  double y = static_cast<double>(rsqrtf(static_cast<float>(a)));
+  const double h = 0.5 * a;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const double e = fma(-h * y, y, 0.5);  // 0.5 (1 - a y^2)
+    y = fma(y, e, y);
+  }
+  return y;
+}
+
 // Off-diagonal 16 x 16 blocks of X = inv(L_kk) from L_kk (lower triangle of S) and the inverted diagonal sub-blocks
 // (X^T in the strictly upper triangle of S, its diagonal in rdiag): one block diagonal at a time,
 //     X_ij = -X_ii (sum_{k=j}^{i-1} L_ik X_kj),
@@ -164,41 +181,44 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
   auto factor_sub = [&](int c0) {
     const int i = lane & 15;
     const bool inv_lane = lane >= SB;
+    // One update rule for both halves of the warp.  Factor lanes: v[k] = running a[i][k].  Inverse lanes: v[k] = running
+    // e_i[k] - sum_{l<k} L[k][l] x_l  (the right-hand side of L x = e_i after eliminating x_0 .. x_{k-1}).  At pivot j
+    // both form  l = v[j] / sqrt(a_jj)  -- L[i][j] resp. x_j, and for lane j itself l = a_jj / sqrt(a_jj) = L[j][j] --
+    // and both subtract  l * L[k][j]  from v[k], k > j.  No per-lane selects on the serial chain.
     double v[SB];
 #pragma unroll
-    for (int k = 0; k < SB; ++k) v[k] = (!inv_lane && k <= i) ? S[(c0 + i) * LDS + c0 + k] : 0.0;
+    for (int k = 0; k < SB; ++k)
+      v[k] = inv_lane ? (k == i ? 1.0 : 0.0) : (k <= i ? S[(c0 + i) * LDS + c0 + k] : 0.0);
     // the diagonal entry of this lane's row lives in its own register: the next pivot then depends only on
     // rsqrt -> l -> dg -= l * l, not on the shared-memory round trip of the column broadcast
-    double dg = inv_lane ? 0.0 : S[(c0 + i) * LDS + c0 + i];
+    double dg = inv_lane ? 1.0 : v[i < SB ? i : 0];
+#pragma unroll
+    for (int k = 0; k < SB; ++k)
+      if (k == i && !inv_lane) dg = v[k];
     double myrd = 1.0;
     double ajj = __shfl_sync(full, dg, 0);
-    double rs = rsqrt(ajj);
+    double rs = pivot_rsqrt(ajj);
+    bool any_bad = false;
 #pragma unroll
     for (int j = 0; j < SB; ++j) {
-      const bool bad = !(ajj > 0.0) || !isfinite(ajj);
-      if (bad && lane == 0 && *info == 0) *info = k0 + c0 + j + 1;
-      // rsqrt is accurate to 1 ulp (CUDA math API), so d = a rs and l = a[i][j] rs are within 2 ulp of sqrt and of
-      // the quotient: far below the n eps backward error of the factorisation itself, and the pivot chain
-      // SHFL -> rsqrt -> l -> dg stays short (no divisions, no Newton steps, no divergent branch).
-      double d = ajj * rs;
-      if (bad) d = rs = __longlong_as_double(0x7ff8000000000000ll);
-      const double num = inv_lane ? ((i == j ? 1.0 : 0.0) - v[j]) : v[j];  // inverse lanes: x_j of column i
-      double l = num * rs;
-      if (!inv_lane && i == j) l = d;
+      // a non-positive / non-finite pivot: flagged, and the arithmetic poisons the block by itself (rsqrt of a
+      // negative number is NaN, of zero +inf)
+      any_bad = any_bad || !(ajj > 0.0) || !(ajj < __longlong_as_double(0x7ff0000000000000ll));
+      if (any_bad && lane == 0 && *info == 0) *info = k0 + c0 + j + 1;
+      const double l = v[j] * rs;
       if (i == j) myrd = rs;
       v[j] = l;
-      if (!inv_lane && i > j) dg = fma(-l, l, dg);
+      if (!inv_lane) dg = fma(-l, l, dg);  // only lanes i > j read it again
       double* cb = cbuf + (j & 1) * SB;
       if (!inv_lane) cb[i] = l;
       __syncwarp();
       if (j + 1 < SB) {  // the next pivot and its rsqrt start now: their latency hides behind the column update
         ajj = __shfl_sync(full, dg, j + 1);
-        rs = rsqrt(ajj);
+        rs = pivot_rsqrt(ajj);
       }
-      const double mult = inv_lane ? l : -l;
 #pragma unroll
       for (int k = 0; k < SB; ++k)
-        if (k > j) v[k] = fma(mult, cb[k], v[k]);  // entries above a row's diagonal are garbage, never read
+        if (k > j) v[k] = fma(-l, cb[k], v[k]);  // entries above a row's diagonal are garbage, never read
     }
     if (!inv_lane) {
       rdiag[c0 + i] = myrd;

@@ -52,7 +52,9 @@ struct lpb_ctx {
   double* sgl_val = nullptr;  // m: that entry
   int* col_row = nullptr;     // n: for columns >= n_dense, the row of their only non-zero, or -1 (all-zero column)
   double* col_val = nullptr;  // n: ... and its value
-  int refine = 1;  // iterative-refinement steps per sym_solve (0 = the plain factor-and-solve of the reference)
+  int refine = 1;  // iterative-refinement steps always taken per sym_solve (0 = the plain factor-and-solve of the reference)
+  int refine_max = 3;  // ... and the most that are taken while the d_tau scalars still move (direction())
+  int64_t refine_steps_taken = 0;
   int regularize = 0;        // 1 = retry a failed factorisation with a shifted diagonal (see form_and_factor)
   bool shifted_now = false;  // the factor of the current iteration belongs to a shifted M
   double *c = nullptr, *x = nullptr, *z = nullptr, *rD = nullptr, *dinv = nullptr, *xs = nullptr, *r1 = nullptr,
@@ -444,12 +446,42 @@ struct CudaDev {
     }
     // Iterative refinement against the OPERATOR A Dinv A^T (not the stored M): the residual of
     //   M v = r2 + A Dinv r1   is   r2 - A u   with u = Dinv (A^T v - r1),   i.e.  rP*eta - A u  and  b - A p,
-    // one more sweep each way and one more solve.  It removes the rounding error of the SYRK accumulation
-    // and of the factorisation from (u, v, p, q): without it -c.p + b.q (a difference of two numbers ~ the
-    // objective that must come out as p' Dinv^-1 p >= 0, delta.rs:32) was 20x noisier than with LAPACK late
-    // in the iteration, and d_tau went wild (C3: 27-28 iterations instead of the oracle's 24).
-    const int refine_steps = c->shifted_now ? std::max(c->refine, 2) : c->refine;
-    for (int step = 0; step < refine_steps; ++step) {
+    // one more sweep each way and one more solve per step.  Why it is there: S = -c.p + b.q (the denominator of
+    // d_tau next to kappa / tau, delta.rs:32; mathematically p' Dinv^-1 p >= 0, numerically a difference of two
+    // numbers ~ the objective) is only well conditioned with respect to backward errors far below eps ||M||; any
+    // eps-grade GPU factorisation -- this one, or cuBLAS + cuSOLVER -- loses it late in the iteration, the CPU
+    // reference's sequential FMA Cholesky does not (profiles/accuracy_r02.txt).
+    // Steps: `refine` are always taken (default 1); up to `refine_max` (default 3) while the scalars the host needs,
+    // S and T = -c.u + b.v, still move by more than 1e-4 relative from one step to the next -- that only happens in
+    // the last few iterations, where cond(M) makes one step contract the error by 1e-1 instead of 1e-3.  All ranks
+    // of a sharded solve see the same all-reduced scalars and take the same decision.
+    auto fetch = [&](double out[6]) -> int {
+      {
+        PhaseTimer tm(c, PH_SWEEP);
+        LPB_TRY(k_dots_m(c->lc, c->m, c->b, W0, W1, with_pq, 3, &nb_m));
+      }
+      spec.nblocks[0] = spec.nblocks[1] = spec.nblocks[2] = nb_n;
+      spec.nblocks[3] = spec.nblocks[4] = spec.nblocks[5] = nb_m;
+      LPB_TRY(finish_scalars(c, spec, 3, ncclSum));
+      for (int k = 0; k < 6; ++k) out[k] = c->lc.red_host[k];
+      return LPB_OK;
+    };
+    const int steps_min = c->shifted_now ? std::max(c->refine, 2) : c->refine;
+    const int steps_max = steps_min > 0 ? std::max(steps_min, c->refine_max) : 0;
+    double cur[6] = {0, 0, 0, 0, 0, 0}, prev[6];
+    bool have_cur = false;
+    for (int step = 0; step < steps_max; ++step) {
+      if (step >= steps_min) {  // an optional step: only if the last one still moved the scalars
+        const double Sc = -cur[1] + cur[4], Sp = -prev[1] + prev[4];
+        const double Tc = -cur[0] + cur[3], Tp = -prev[0] + prev[3];
+        const bool s_ok = !with_pq || std::fabs(Sc - Sp) <= 1e-4 * std::fabs(Sc);
+        const bool t_ok = std::fabs(Tc - Tp) <= 1e-4 * std::fabs(Tc) + 1e-13 * (std::fabs(cur[0]) + std::fabs(cur[3]));
+        if (s_ok && t_ok) break;
+      }
+      if (step + 1 >= steps_min && steps_max > steps_min && !have_cur) {  // the value the next comparison starts from
+        LPB_TRY(fetch(cur));
+        have_cur = true;
+      }
       double* R0 = c->R;
       double* R1 = c->R + c->m;
       {
@@ -475,15 +507,14 @@ struct CudaDev {
         LPB_TRY(sweep_t(W0, W1, nrhs, &nchunks, &tail));
         LPB_TRY(k_sym_back(c->lc, c->n, nchunks, with_pq, c->dinv, c->r1, c->c, c->u, c->p, 0, &nb_n, &tail));
       }
+      c->refine_steps_taken++;
+      if (have_cur) {
+        for (int k = 0; k < 6; ++k) prev[k] = cur[k];
+        LPB_TRY(fetch(cur));
+      }
     }
-    {
-      PhaseTimer tm(c, PH_SWEEP);
-      LPB_TRY(k_dots_m(c->lc, c->m, c->b, W0, W1, with_pq, 3, &nb_m));
-    }
-    spec.nblocks[0] = spec.nblocks[1] = spec.nblocks[2] = nb_n;
-    spec.nblocks[3] = spec.nblocks[4] = spec.nblocks[5] = nb_m;
-    LPB_TRY(finish_scalars(c, spec, 3, ncclSum));
-    const double* h = c->lc.red_host;
+    if (!have_cur) LPB_TRY(fetch(cur));
+    const double* h = cur;
     if (with_pq) {
       c->cp = h[1];
       c->bq = h[4];
@@ -1104,6 +1135,7 @@ int64_t lpb_debug_counter(lpb_ctx* c, const char* name) {
   if (k == "potrf_verify_runs") return c->vfy_runs;
   if (k == "potrf_verify_mismatches") return c->vfy_mismatch;
   if (k == "refactorisations") return c->refactorisations;
+  if (k == "refine_steps") return c->refine_steps_taken;
   return -1;
 }
 
@@ -1346,6 +1378,11 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
   if (k == "refine") {
     if (value < 0 || value > 4) return LPB_ERR_BAD_ARGUMENT;
     c->refine = (int)value;
+    return LPB_OK;
+  }
+  if (k == "refine_max") {
+    if (value < 0 || value > 8) return LPB_ERR_BAD_ARGUMENT;
+    c->refine_max = (int)value;
     return LPB_OK;
   }
   if (k == "regularize") {  // 0 (default, the reference's behaviour): a failed factorisation is NumericalProblem
