@@ -1,34 +1,61 @@
-//! Error type of the solvers: the seven variants of `/root/reference/src/error.rs:7-29`, same order, same messages.
-//! C-ABI status codes 1..7 (`include/lpb200.h`) are these variants in declaration order.
+//! Error type of the solvers.  Same seven variants, in the same order and with the same user-facing messages as
+//! `/root/reference/src/error.rs:7-29`; the C-ABI status codes 1..7 of `include/lpb200.h` are these variants in
+//! declaration order.  `Display` / `Error` are written out by hand (no derive macro dependency).
 use ndarray::Array1;
-use std::fmt::Debug;
-use thiserror::Error;
+use std::fmt::{self, Debug, Display};
 
 /// Problems encountered while building or solving a linear program.
-#[derive(Error, Debug)]
+#[derive(Debug)]
 pub enum LinearProgramError<F: Debug> {
-    /// No constraint rows at all.
-    #[error("The problem is unconstrained, meaning the solution is the all-zeros vector if `c` is nonnegative, or unbounded otherwise.")]
+    /// No constraint rows at all (status 1).
     Unconstrained,
-    /// The factorisation of the normal matrix failed (pivot not > 0 / not finite) or p, q contain NaN.
-    #[error("The solver encountered numerical problems it could not recover from. Likely causes are linearly dependent constraints or variables whose scale differs by multiple orders of magnitude.")]
+    /// The factorisation of the normal matrix failed, or p / q contain NaN (status 2).
     NumericalProblem,
-    /// A builder parameter is out of range -- or the request cannot run on the B200 path (see the message).
-    #[error("A parameter was set to an invalid value: {0}")]
+    /// A builder parameter is out of range -- or the request cannot run on the B200 path, see the text (status 3).
     InvalidParameter(&'static str),
-    /// Shapes of c, A_ub, b_ub, A_eq, b_eq do not agree.
-    #[error("The dimensions of your cost- and constraint arrays do not align.")]
+    /// Shapes of c, A_ub, b_ub, A_eq, b_eq do not agree (status 4).
     IncompatibleInputDimensions,
-    /// The homogeneous model certified primal infeasibility.
-    #[error("The solver finished successfully, it appears that the problem is infeasible.")]
+    /// The homogeneous model certified primal infeasibility (status 5).
     Infeasible,
-    /// The homogeneous model certified unboundedness.
-    #[error("The solver finished successfully, it appears that your problem is unbounded.")]
+    /// The homogeneous model certified unboundedness (status 6).
     Unbounded,
-    /// `max_iter` iterations without meeting the tolerances; carries the best `x / tau` in SLACK form.
-    #[error("The solver failed to converge within the maximum number of iterations. Best solution after the final iteration:\n{0:#?}")]
+    /// `max_iter` iterations without meeting the tolerances; carries the best `x / tau` in SLACK form (status 7).
     IterationLimitExceeded(Array1<F>),
 }
+
+impl<F: Debug> Display for LinearProgramError<F> {
+    fn fmt(&self, f: &mut fmt::Formatter<'_>) -> fmt::Result {
+        use LinearProgramError::*;
+        match self {
+            Unconstrained => f.write_str(
+                "The problem is unconstrained, meaning the solution is the all-zeros vector if `c` is nonnegative, \
+                 or unbounded otherwise.",
+            ),
+            NumericalProblem => f.write_str(
+                "The solver encountered numerical problems it could not recover from. Likely causes are linearly \
+                 dependent constraints or variables whose scale differs by multiple orders of magnitude.",
+            ),
+            InvalidParameter(what) => write!(f, "A parameter was set to an invalid value: {}", what),
+            IncompatibleInputDimensions => {
+                f.write_str("The dimensions of your cost- and constraint arrays do not align.")
+            }
+            Infeasible => {
+                f.write_str("The solver finished successfully, it appears that the problem is infeasible.")
+            }
+            Unbounded => {
+                f.write_str("The solver finished successfully, it appears that your problem is unbounded.")
+            }
+            IterationLimitExceeded(x) => write!(
+                f,
+                "The solver failed to converge within the maximum number of iterations. Best solution after the \
+                 final iteration:\n{:#?}",
+                x
+            ),
+        }
+    }
+}
+
+impl<F: Debug> std::error::Error for LinearProgramError<F> {}
 
 impl<F: Debug> LinearProgramError<F> {
     /// Map a non-zero lpb status code that carries no payload (`include/lpb200.h`): 1..6 are the variants above;

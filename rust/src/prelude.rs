@@ -1,6 +1,10 @@
-//! Commonly used imports; use as `use ripped::prelude::*` (mirrors `/root/reference/src/prelude.rs:3-11`).
-pub use crate::error::LinearProgramError;
-pub use crate::linear_program::Problem;
-pub use crate::solvers::interior_point::EquationSolverType;
-pub use crate::solvers::interior_point::InteriorPoint;
-pub use crate::solvers::Solver;
+//! `use ripped::prelude::*` brings the same five names into scope as the reference's prelude
+//! (`/root/reference/src/prelude.rs:3-11`).
+pub use crate::{
+    error::LinearProgramError,
+    linear_program::Problem,
+    solvers::{
+        interior_point::{EquationSolverType, InteriorPoint},
+        Solver,
+    },
+};
