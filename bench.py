@@ -652,6 +652,9 @@ def main():
         rp.set_option("potrf_dist", args.potrf_dist)
     else:
         rp = ResidentProblem(problem, stream=stream)
+    for kv in filter(None, os.environ.get("LPB_BENCH_OPTS", "").split(",")):  # experiments: "key=value,key=value"
+        k, v = kv.split("=")
+        rp.set_option(k, int(v))
 
     def barrier():
         if dist is not None:

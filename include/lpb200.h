@@ -256,7 +256,10 @@ int64_t lpb_launch_count(lpb_ctx* ctx);
 /* Tuning / debug knobs.  "syrk_impl": 0 = DMMA+TMA, 1 = plain DFMA reference kernels (parity tests
  * bisect with it); "solve_impl": 0 = single-launch pipelined solve (tagged hand-off, full block inverses),
  * 1 = one launch per 128-block step, 2 = plain substitution, 3 = the flag-based pipelined solve with blocked
- * substitution; "refine": iterative-refinement steps per sym_solve (default 1); "solve_grid_cap": > 0 caps the pipelined solve's grid (tests: several block rows per CTA);
+ * substitution; "refine": iterative-refinement steps per sym_solve (default 0 = the reference's plain
+ * factor-and-solve); "syrk_flush_blocks": K-blocks of 16 columns K1 sums in registers between two folds into M
+ * (power of two >= 32, default 32); "syrk_chain": 1 = one register chain over the whole K extent (round-1 kernel);
+ * "solve_grid_cap": > 0 caps the pipelined solve's grid (tests: several block rows per CTA);
  * "profile": 1 = record per-phase events; "structure": 0 = contract the SYRK over every column of A
  * (default 1: trailing singleton columns -- the slack block -- are folded into the diagonal of M).  Unknown key -> BAD_ARGUMENT. */
 int lpb_set_option(lpb_ctx* ctx, const char* key, int64_t value);

@@ -191,10 +191,10 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
       v[k] = inv_lane ? (k == i ? 1.0 : 0.0) : (k <= i ? S[(c0 + i) * LDS + c0 + k] : 0.0);
     // the diagonal entry of this lane's row lives in its own register: the next pivot then depends only on
     // rsqrt -> l -> dg -= l * l, not on the shared-memory round trip of the column broadcast
-    double dg = inv_lane ? 1.0 : v[i < SB ? i : 0];
+    double dg = 1.0;
 #pragma unroll
     for (int k = 0; k < SB; ++k)
-      if (k == i && !inv_lane) dg = v[k];
+      if (k == i && !inv_lane) dg = v[k];  // static indices only: v[] must stay in registers
     double myrd = 1.0;
     double ajj = __shfl_sync(full, dg, 0);
     double rs = pivot_rsqrt(ajj);
@@ -1603,6 +1603,11 @@ static int ensure_chol_ws(LaunchCtx& lc, int64_t m) {
 
 // After a factorisation: complete the 128 x 128 block inverses (all blocks in parallel, ~20 us) for the solves.
 static int finish_factor(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm) {
+  if (lc.potf2_impl == 1) {  // no inverted blocks were produced: the solves fall back to plain substitution
+    lc.linv_valid_m = -1;
+    lc.linv_mat = nullptr;
+    return LPB_OK;
+  }
   if (!lc.linv_full) {
     static PerDeviceOnce once;
     LPB_TRY(once.run([](int) -> int { return set_smem(linv_complete_kernel, kLinvCompleteSmem); }));
@@ -1691,9 +1696,9 @@ int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
   LPB_CUDA(cudaMemsetAsync(lc.info_dev, 0, sizeof(int), lc.stream));
   const bool dmma_update = lc.update_impl == 0 || lc.update_impl == 2 || lc.update_impl == 6;
   if (lc.world > 1 && lc.nccl_comm && lc.potrf_dist && syrk_impl == 0 && lc.trsm_impl == 0 && dmma_update &&
-      m > NB && !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mat) & 15))
+      lc.potf2_impl == 0 && m > NB && !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mat) & 15))
     return lc.potrf_dist == 2 ? k_potrf_dist2(lc, m, Mat, ldm) : k_potrf_dist(lc, m, Mat, ldm);
-  if (lc.potrf_lookahead && syrk_impl == 0 && lc.trsm_impl == 0 && dmma_update &&
+  if (lc.potrf_lookahead && syrk_impl == 0 && lc.trsm_impl == 0 && dmma_update && lc.potf2_impl == 0 &&
       !lc.sync_each_launch && m > 2 * NB && !(ldm & 1) && !(reinterpret_cast<uintptr_t>(Mat) & 15))
     return k_potrf_lookahead(lc, m, Mat, ldm);
   const int full_inverse = lc.trsm_impl == 2 ? 1 : 0;  // the solves complete the inverses themselves (finish_factor)
@@ -1702,8 +1707,11 @@ int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl) {
     const int nb = (int)((m - k0) < NB ? (m - k0) : NB);
     const int64_t rem = m - k0 - nb;
     double* linv = lc.chol_ws + (k0 / NB) * NB * NB;
-    potf2_inv_kernel<<<1, dim3(32, 16), kPotf2InvSmem, lc.stream>>>(Mat, ldm, (int)k0, nb, lc.info_dev, linv,
-                                                                    full_inverse);
+    if (lc.potf2_impl == 1)  // textbook column Cholesky with sqrt and divisions, no inverses (accuracy experiments)
+      potf2_kernel<<<1, dim3(32, 16), kPotf2Smem, lc.stream>>>(Mat, ldm, (int)k0, nb, lc.info_dev);
+    else
+      potf2_inv_kernel<<<1, dim3(32, 16), kPotf2InvSmem, lc.stream>>>(Mat, ldm, (int)k0, nb, lc.info_dev, linv,
+                                                                      full_inverse);
     LPB_KCHECK(lc);
     if (lc.sync_each_launch) LPB_CUDA(cudaStreamSynchronize(lc.stream));
     if (rem > 0) {

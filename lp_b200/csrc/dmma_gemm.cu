@@ -32,6 +32,16 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int kStages = 5;
 constexpr int kLead = 3;  // TMA runs this many K-blocks ahead of the DMMA warps
+// K1 only: the accumulators are folded into C every `fblocks` K-blocks (LaunchCtx::syrk_flush_blocks, default 32 =
+// 512 columns) instead of summing the whole K extent in one register chain.  A chain of n/4 DMMA steps rounds relative
+// to the growing partial sum: 33 ulp rms (117 max) on the same-sign diagonal sums of M at n = 24576 -- a single cuBLAS
+// DGEMM call measures the same -- against 3.1 ulp blocked (cuBLAS called per 1024 columns: 3.6; tools/time_syrk.py).
+// That, not the factorisation or the solves, is what made the unrefined Newton solve lose d_tau's denominator late in
+// the iteration (tools/diag_bisect_host.py: M formed on the host -> every device factor / solve is fine; M formed on
+// the device in one chain, by this kernel or by cuBLAS -> none is).  The flush is staggered over the row groups of a
+// slab and over the two warps of a sub-partition and its reads are asynchronous (see the main loop): +1.0 % at C3.
+// kFlushBlocks is only the fallback period of callers that pass none.
+constexpr int kFlushBlocks = 128;
 constexpr int kConsumerWarps = 8;
 constexpr int kThreads = kConsumerWarps * 32;
 constexpr uint32_t kTileBytes = BM * BK * 8;  // 16 KB
@@ -58,7 +68,8 @@ struct Plan {
   static constexpr uint32_t kC = kB + kNS * kTileBytes;                  // 1024-byte aligned (multiples of 16 KB)
   static constexpr uint32_t kD = kC + (kCpf ? 8 * kTileBytes : 0);
   static constexpr uint32_t kBar = kD + kNS * kDBytes;
-  static constexpr uint32_t kTotal = kBar + (2 * kNS + 2) * 8;
+  static constexpr uint32_t kF = (kBar + (2 * kNS + 2) * 8 + 15u) & ~15u;  // MODE_SYRK: staging of old C for the flushes
+  static constexpr uint32_t kTotal = kF + (MODE == 0 && (VAR & 16) == 0 ? kThreads * 64 : 0);
   static constexpr uint32_t kAlloc = kTotal + 1024;
 };
 
@@ -123,6 +134,11 @@ __device__ __forceinline__ double2 lds_v2(uint32_t addr) {
   asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
       : "+d"(c0), "+d"(c1)
@@ -200,6 +216,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // (r - p_row0) of the panel at buffer row (r - p_row0), except that the first two 128-row blocks are swapped:
   // the rows of block p_row0 / 128 + 1 come first, see k_potrf_dist2) instead of from columns k_begin.. of C.
   using P = Plan<MODE, VAR>;
+  constexpr bool FLUSH = (VAR & 16) == 0;  // VAR bit 4: one register chain over the whole K extent (the round-1 kernel)
   constexpr int NS = P::kNS, LEAD = P::kLd;
   constexpr bool CPF = P::kCpf;
   extern __shared__ uint8_t smem_raw[];
@@ -207,6 +224,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t sA = smem_base + P::kA, sB = smem_base + P::kB, sD = smem_base + P::kD, sC = smem_base + P::kC;
   const uint32_t bar_full = smem_base + P::kBar, bar_empty = bar_full + NS * 8;
   const uint32_t bar_cfull = bar_empty + NS * 8, bar_cempty = bar_cfull + 8;
+  const uint32_t sF = smem_base + P::kF + threadIdx.x * 16u;  // this thread's staging slots: sF + ni * (kThreads * 16)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -316,6 +334,13 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t sw[2] = {static_cast<uint32_t>(((2 * t + 0) ^ g) << 4), static_cast<uint32_t>(((2 * t + 1) ^ g) << 4)};
   const uint32_t dof[2] = {static_cast<uint32_t>((2 * t + 0) << 4), static_cast<uint32_t>((2 * t + 1) << 4)};
 
+  // MODE_SYRK: `col_origin` carries the flush period in K-blocks (a power of two >= 32, kFlushBlocks by default)
+  const int fblocks = MODE == MODE_SYRK && col_origin >= 32 ? col_origin : kFlushBlocks;
+  const int fstride = fblocks >> 3;  // the 8 row groups of a warp's slab flush this many K-blocks apart
+  const int fshift = 31 - __clz(fstride);
+  // warps w and w + 4 share an SM sub-partition: the second four flush half a stride later, so a sub-partition's DMMA
+  // pipe always has one warp issuing while the other folds a row group (both at once idled it ~0.6 us per flush)
+  const int fwarp = (threadIdx.x >> 7) * (fstride >> 1);
   const uint32_t rt_zero = static_cast<uint32_t>(static_cast<uint64_t>(ldc) >> 62);  // 0 at run time, opaque to the compiler
   int tile_n = 0;  // tiles this CTA has started (parity of the C-prefetch barriers)
   for (int L = blockIdx.x; L < ntiles; L += gridDim.x, ++tile_n) {
@@ -423,6 +448,59 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         stage = 0;
         phase ^= 1u;
       }
+      if (MODE == MODE_SYRK && FLUSH) {
+        // Blocked accumulation, staggered and asynchronous: row group mi of the slab (8 doubles per thread) is folded
+        // into C at K-blocks = fstride (mi + 1) - 1 - fwarp (mod fblocks).  Two K-blocks (~4 us) earlier each thread
+        // requests its 4 x 16 bytes of old C with cp.async into a staging slot in shared memory -- no register and no
+        // scoreboard is tied up while 128 DMMAs run (a plain prefetching load was waited for at the next branch
+        // merge: 1.5 us per flush, all eight warps at once) -- and the flush itself is 4 LDS + 8 DADD + 4 STG.
+        // Each element of the tile belongs to exactly one thread, so the read-modify-write needs no
+        // synchronisation; the first flush of a tile is a plain store (C is not read before it is written).
+        // Addresses are rebuilt from row0 behind an opaque move so that the compiler does not keep eight row
+        // pointers alive across the main loop (they cost the fragment double-buffering its registers).
+        const int ph = (kb + fwarp) & (fblocks - 1);
+        const int sub = ph & (fstride - 1);
+        const uint32_t grp_bit = 1u << (ph >> fshift);  // a bit test per row group keeps acc[] statically indexed
+        if (sub == fstride - 3 && kb + 2 >= fblocks) {
+          int rbase = row0;
+          asm volatile("" : "+r"(rbase));
+#pragma unroll
+          for (int mi = 0; mi < 8; ++mi)
+            if ((grp_bit >> mi) & 1u) {
+              const int r = rbase + mi * 8;
+              const double* crow = C + static_cast<int64_t>(r) * ldc;
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni) {
+                const int cc = col0 + ni * 8;
+                if (r < m_total && cc < col_limit) cp_async_16(sF + ni * (kThreads * 16), crow + cc);
+              }
+            }
+          cp_async_commit();
+        } else if (sub == fstride - 1 && kb + 1 < nkb) {
+          const bool first = kb < fblocks;
+          int rbase = row0;
+          asm volatile("" : "+r"(rbase));
+          if (!first) cp_async_wait_all();
+#pragma unroll
+          for (int mi = 0; mi < 8; ++mi)
+            if ((grp_bit >> mi) & 1u) {
+              const int r = rbase + mi * 8;
+              double* crow = C + static_cast<int64_t>(r) * ldc;
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni) {
+                const int cc = col0 + ni * 8;
+                double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                if (!first) {
+                  const double2 o = lds_v2(sF + ni * (kThreads * 16));
+                  v.x += o.x;
+                  v.y += o.y;
+                }
+                if (r < m_total && cc < col_limit) *reinterpret_cast<double2*>(crow + cc) = v;
+                acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+              }
+            }
+        }
+      }
     }
 
     // ------------------------------------------------------------ epilogue: store-only, each warp its own slab
@@ -436,7 +514,9 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int c = col0 + ni * 8;
           if (c < col_limit) {
             double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-            if (MODE == MODE_UPDATE && (VAR & 1)) {
+            // MODE_SYRK: row group mi has been folded into C before iff its first flush point lies inside the tile
+            if ((MODE == MODE_UPDATE && (VAR & 1)) ||
+                (MODE == MODE_SYRK && FLUSH && fstride * (mi + 1) - fwarp < nkb)) {
               const double2 o = *reinterpret_cast<const double2*>(crow + c);
               v.x += o.x;
               v.y += o.y;
@@ -534,8 +614,13 @@ int k_syrk_dmma(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t ld
     tmD = tmA;
   const int ntr = (int)ceil_div(m, BM);
   const int nkb = (int)ceil_div(n, BK);
-  if (d) return launch_dmma<MODE_SYRK, true>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, 0);
-  return launch_dmma<MODE_SYRK, false>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, 0);
+  if (lc.syrk_chain) {  // option "syrk_chain" = 1: no blocked accumulation (accuracy / timing comparison)
+    if (d) return launch_dmma<MODE_SYRK, true, 16>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, 0);
+    return launch_dmma<MODE_SYRK, false, 16>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, 0);
+  }
+  const int fb = lc.syrk_flush_blocks;  // option "syrk_flush_blocks": K-blocks between two flushes (power of two >= 32)
+  if (d) return launch_dmma<MODE_SYRK, true>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, fb);
+  return launch_dmma<MODE_SYRK, false>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, fb);
 }
 
 int k_trailing_update_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb) {

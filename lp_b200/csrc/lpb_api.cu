@@ -52,8 +52,8 @@ struct lpb_ctx {
   double* sgl_val = nullptr;  // m: that entry
   int* col_row = nullptr;     // n: for columns >= n_dense, the row of their only non-zero, or -1 (all-zero column)
   double* col_val = nullptr;  // n: ... and its value
-  int refine = 1;  // iterative-refinement steps always taken per sym_solve (0 = the plain factor-and-solve of the reference)
-  int refine_max = 3;  // ... and the most that are taken while the d_tau scalars still move (direction())
+  int refine = 0;  // iterative-refinement steps taken per sym_solve: 0 (default) = the plain factor-and-solve of the reference
+  int refine_max = 0;  // > refine: take further steps (up to this many) while the d_tau scalars still move (off by default)
   int64_t refine_steps_taken = 0;
   int regularize = 0;        // 1 = retry a failed factorisation with a shifted diagonal (see form_and_factor)
   bool shifted_now = false;  // the factor of the current iteration belongs to a shifted M
@@ -444,17 +444,19 @@ struct CudaDev {
       LPB_TRY(sweep_t(W0, W1, nrhs, &nchunks, &tail));
       LPB_TRY(k_sym_back(c->lc, c->n, nchunks, with_pq, c->dinv, c->r1, c->c, c->u, c->p, 0, &nb_n, &tail));
     }
-    // Iterative refinement against the OPERATOR A Dinv A^T (not the stored M): the residual of
+    // OPTIONAL iterative refinement against the OPERATOR A Dinv A^T (not the stored M): the residual of
     //   M v = r2 + A Dinv r1   is   r2 - A u   with u = Dinv (A^T v - r1),   i.e.  rP*eta - A u  and  b - A p,
-    // one more sweep each way and one more solve per step.  Why it is there: S = -c.p + b.q (the denominator of
-    // d_tau next to kappa / tau, delta.rs:32; mathematically p' Dinv^-1 p >= 0, numerically a difference of two
-    // numbers ~ the objective) is only well conditioned with respect to backward errors far below eps ||M||; any
-    // eps-grade GPU factorisation -- this one, or cuBLAS + cuSOLVER -- loses it late in the iteration, the CPU
-    // reference's sequential FMA Cholesky does not (profiles/accuracy_r02.txt).
-    // Steps: `refine` are always taken (default 1); up to `refine_max` (default 3) while the scalars the host needs,
-    // S and T = -c.u + b.v, still move by more than 1e-4 relative from one step to the next -- that only happens in
-    // the last few iterations, where cond(M) makes one step contract the error by 1e-1 instead of 1e-3.  All ranks
-    // of a sharded solve see the same all-reduced scalars and take the same decision.
+    // one more sweep each way and one more solve per step.  The reference has no such step and neither has the
+    // default path (`refine` = 0).  History: with K1 summing each entry of M in ONE register chain (round 1, and what
+    // a single cuBLAS DGEMM does) S = -c.p + b.q -- the denominator of d_tau next to kappa / tau, delta.rs:32;
+    // mathematically p' Dinv^-1 p >= 0, numerically a difference of two numbers ~ the objective -- lost all its digits
+    // late in the iteration and a refinement step was needed to follow the oracle's trajectory at C3.  The cause was
+    // the summation order of M, not the factor or the solves (tools/diag_bisect_host.py); K1 now blocks the sum over
+    // K (dmma_gemm.cu) and the unrefined solve tracks the oracle to 2e-8 in x.
+    // Steps: `refine` are always taken; up to `refine_max` while the scalars the host needs, S and T = -c.u + b.v,
+    // still move by more than 1e-4 relative from one step to the next.  The regularised refactorisation
+    // (`regularize`) forces two steps, because its factor belongs to a shifted M.  All ranks of a sharded solve see
+    // the same all-reduced scalars and take the same decision.
     auto fetch = [&](double out[6]) -> int {
       {
         PhaseTimer tm(c, PH_SWEEP);
@@ -1368,6 +1370,21 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
   if (k == "trsm_impl" || k == "update_impl") {
     if (value < 0 || value > 6) return LPB_ERR_BAD_ARGUMENT;
     (k == "trsm_impl" ? c->lc.trsm_impl : c->lc.update_impl) = (int)value;
+    return LPB_OK;
+  }
+  if (k == "syrk_chain") {  // 1: K1 without blocked accumulation (the round-1 summation order)
+    c->lc.syrk_chain = value != 0;
+    return LPB_OK;
+  }
+  if (k == "syrk_flush_blocks") {  // K1: K-blocks between two flushes of the accumulators into C (power of two >= 32)
+    if (value < 32 || value > (1 << 20) || (value & (value - 1))) return LPB_ERR_BAD_ARGUMENT;
+    c->lc.syrk_flush_blocks = (int)value;
+    return LPB_OK;
+  }
+  if (k == "potf2_impl") {  // 1: textbook panel factorisation without inverses (forces the substitution TRSM / solves)
+    if (value < 0 || value > 1) return LPB_ERR_BAD_ARGUMENT;
+    c->lc.potf2_impl = (int)value;
+    if (value == 1) c->lc.trsm_impl = 1;
     return LPB_OK;
   }
   if (k == "solve_grid_cap") {

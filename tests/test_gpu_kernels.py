@@ -12,7 +12,10 @@ from tests.gpu_util import BareCtx, ok, pad_cols, to_dev
 
 pytestmark = pytest.mark.gpu
 
-SYRK_SHAPES = [(8, 16), (100, 250), (128, 256), (129, 257), (300, 1000), (513, 1031), (1024, 2048)]
+# the last three cross K1's blocked-accumulation boundaries (a row group of the slab is folded into C every 2048 columns,
+# first at column 256 (mi + 1)): one flush per group, a ragged tail behind a flush, three flushes per group
+SYRK_SHAPES = [(8, 16), (100, 250), (128, 256), (129, 257), (300, 1000), (513, 1031), (1024, 2048), (257, 2320),
+               (129, 4130), (200, 6500)]
 
 
 @pytest.mark.parametrize("impl", [0, 1])
@@ -41,6 +44,31 @@ def test_syrk_adat_matches_numpy(m, n, impl, scaled):
     err = np.abs(M[low] - ref[low]) / scale[low]
     assert np.isfinite(M[low]).all()
     assert err.max() < 1e-12
+
+
+def test_syrk_blocked_accumulation_keeps_long_same_sign_sums_to_a_few_ulp():
+    """The diagonal of M = A D A^T is a sum of n same-sign terms.  One register chain of n / 4 DMMA steps rounds
+    relative to the growing partial sum (measured 26 ulp rms at n = 24576: option "syrk_chain" = 1, the round-1
+    kernel, and cuBLAS DGEMM behave alike); K1 folds its accumulators into C every 2048 columns, which a BLAS that
+    blocks K does implicitly (the CPU oracle's OpenBLAS).  Checked against the diagonal summed in extended precision."""
+    import torch
+    m, n = 256, 24576
+    rng = np.random.default_rng(7)
+    A = rng.standard_normal((m, n))
+    d = np.exp(rng.uniform(-1, 1, n))
+    exact = ((A.astype(np.longdouble) ** 2) * d.astype(np.longdouble)).sum(axis=1)
+    dA, dd = to_dev(A), to_dev(d)
+    rms = {}
+    for chain in (0, 1):
+        dM = torch.full((m, m), float("nan"), dtype=torch.float64, device="cuda")
+        with BareCtx(m, n) as ctx:
+            ctx.set("syrk_chain", chain)
+            ok(ctx.lib.lpb_k_syrk_adat(ctx.h, m, n, dA.data_ptr(), n, dd.data_ptr(), dM.data_ptr(), m))
+        got = np.diagonal(dM.cpu().numpy()).astype(np.longdouble)
+        ulps = np.abs(got - exact) / np.spacing(exact.astype(np.float64))
+        rms[chain] = float(np.sqrt((ulps.astype(np.float64) ** 2).mean()))
+    print("diagonal of M, n = %d same-sign terms: %.2f ulp rms blocked, %.2f ulp rms as one chain" % (n, rms[0], rms[1]))
+    assert rms[0] < 4.0 and rms[0] < 0.5 * rms[1]
 
 
 @pytest.mark.parametrize("impl,trsm", [(0, 0), (0, 1), (0, 2), (0, 3), (1, 0)])

@@ -44,10 +44,13 @@ def main():
         # ---- in-library variants from this iterate (form_and_factor does not move the iterate)
         n_tot = n
         mu = float((x * z).sum().item() + tau * kappa) / (n_tot + 1)
-        for opts in (dict(refine=3), dict(refine=1), dict(refine=0), dict(refine=0, solve_impl=3),
+        for opts in (dict(refine=3), dict(refine=1), dict(refine=0), dict(refine=0, syrk_chain=1), dict(refine=0, solve_impl=3),
                      dict(refine=0, solve_impl=2), dict(refine=0, solve_impl=2, trsm_impl=1),
-                     dict(refine=0, structure=0), dict(refine=0, update_impl=2), dict(refine=0, syrk_impl=1)):
-            base = dict(refine=1, solve_impl=0, trsm_impl=0, structure=1, update_impl=0, syrk_impl=0)
+                     dict(refine=0, update_impl=2), dict(refine=0, syrk_impl=1),
+                     dict(refine=0, potf2_impl=1, solve_impl=2), dict(refine=0, potf2_impl=1, solve_impl=2, update_impl=1),
+                     dict(refine=0, potf2_impl=1, solve_impl=2, update_impl=1, syrk_impl=1), dict(refine=1, refine_max=3),
+                     dict(refine=2)):
+            base = dict(refine=1, refine_max=0, syrk_chain=0, solve_impl=0, trsm_impl=0, structure=1, update_impl=0, syrk_impl=0, potf2_impl=0)
             base.update(opts)
             for k, v in base.items():
                 rp.set_option(k, v)

@@ -2,7 +2,7 @@
 # One parameterised GPU-box script (replaces the per-call scripts of round 1).  Usage, under gpurun:
 #   bash tools/gpu_run.sh TAG step [step ...]
 # Steps:  tests | tests:<pytest -k expr> | smoke | bench:<WL> | benchq:<WL> (1 step, no CPU leg) | diag:<WL>[,<WL>]
-#         | dtau:<WL>:<K> | bias | benchn:<WL>:<N>:<potrf_dist> | benchfull:<N> | time:<m>[,<m>] | create:<WL> | launches:<WL> | ncu:<WL>:<kernel regex>:<skip>:<count> | ref:<WL>
+#         | dtau:<WL>:<K> | bisect:<WL>:<K> | bias | benchn:<WL>:<N>:<potrf_dist> | benchfull:<N> | time:<m>[,<m>] | syrk[:<m>,<n>] | create:<WL> | launches:<WL> | ncu:<WL>:<kernel regex>:<skip>:<count> | ref:<WL>
 # Everything is written under gpurun_out/ with TAG in the name; a failing step does not stop the later ones.
 set -u
 TAG=$1; shift
@@ -13,7 +13,7 @@ for step in "$@"; do
   case $kind in
     tests)
       if [ -n "$arg" ]; then
-        timeout 1500 python -m pytest tests -m gpu -x -q -k "$arg" > gpurun_out/pytest_${TAG}.log 2>&1
+        timeout 1500 python -m pytest tests -m gpu -x -q -rP -k "$arg" > gpurun_out/pytest_${TAG}.log 2>&1
       else
         timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_${TAG}.log 2>&1
       fi
@@ -47,12 +47,19 @@ for step in "$@"; do
       IFS=: read -r wl k <<< "$arg"
       timeout 900 python tools/diag_dtau.py $wl $k > gpurun_out/dtau_${wl}_${k}_${TAG}.log 2>&1
       echo "[$step] rc=$?"; cat gpurun_out/dtau_${wl}_${k}_${TAG}.log | tail -40;;
+    bisect)
+      IFS=: read -r wl k <<< "$arg"
+      timeout 900 python tools/diag_bisect_host.py $wl $k > gpurun_out/bisect_${wl}_${k}_${TAG}.log 2>&1
+      echo "[$step] rc=$?"; cat gpurun_out/bisect_${wl}_${k}_${TAG}.log | tail -30;;
     bias)
       timeout 600 python tools/dmma_bias.py > gpurun_out/dmma_bias_${TAG}.log 2>&1
       echo "[$step] rc=$?"; cat gpurun_out/dmma_bias_${TAG}.log;;
     time)
       timeout 600 python tools/time_kernels.py ${arg//,/ } > gpurun_out/time_${TAG}.log 2>&1
       echo "[$step] rc=$?"; cat gpurun_out/time_${TAG}.log | tail -4;;
+    syrk)
+      timeout 600 python tools/time_syrk.py ${arg//,/ } > gpurun_out/syrk_${TAG}.log 2>&1
+      echo "[$step] rc=$?"; cat gpurun_out/syrk_${TAG}.log | tail -12;;
     create)
       LPB_TIME_CREATE=1 timeout 600 python tools/time_create.py $arg > gpurun_out/create_${arg}_${TAG}.log 2>&1
       echo "[$step] rc=$?"; tail -12 gpurun_out/create_${arg}_${TAG}.log;;
