@@ -19,7 +19,7 @@ LIB = os.path.join(LIBDIR, "liblpb200.so")
 SOURCES = ["vec_kernels.cu", "dmma_gemm.cu", "cholesky.cu", "batched.cu", "presolve.cu", "lpb_api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("LPB_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _deps():

@@ -16,6 +16,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "dist_schedule.hpp"
 #include "kernels.hpp"
@@ -78,24 +79,24 @@ potf2_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __restr
 // the block with NaN; there is no early exit.
 constexpr int SB = 16;        // sub-block
 constexpr int NSB = NB / SB;  // 8
-constexpr int XDP = SB + 1;   // pitch of the 16 x 16 inverse of the current diagonal sub-block
+constexpr int XDP = SB + 1;   // pitch of the 16 x 16 inverse of the current diagonal sub-block (odd: the four row groups a warp reads hit different banks)
 constexpr int TWP = 9;        // pitch of the per-warp 16 x 8 scratch of the block-inverse step
 
-// 1 / sqrt(a) for a pivot, on the serial chain of the panel kernel: an FP32 seed (MUFU.RSQ) and three explicit
-// Newton steps in FP64 (23 -> 46 -> 92 -> full bits; the last one makes the result correctly rounded in all but a
-// few cases per million, i.e. within 1 ulp like the library's rsqrt) -- 15 instructions without the special-case
-// handling of the library routine.  Pivots outside the FP32 range take the library path (uniform branch: the pivot
-// is a warp-wide broadcast); non-positive and non-finite pivots come out as NaN / inf / 0 exactly as there.
+// 1 / sqrt(a) for a pivot, on the serial chain of the panel kernel: the hardware seed (MUFU.RSQ64H: it reads the
+// high word of the double, ~2^-22 relative over the whole FP64 exponent range, no conversions or range branch) and
+// ONE third-order step  y (1 + e/2 + 3 e^2 / 8),  e = 1 - a y^2  (truncation 5 e^3 / 16 ~ 2^-67; the result is within
+// 1 ulp) -- four dependent FP64 operations behind the seed instead of the six of two Newton steps; an FP64
+// operation costs ~20 cycles of latency here and this chain runs once per pivot.  Non-positive / non-finite pivots
+// come out as NaN / +inf / NaN, which is how the caller detects them (potf2_inv_kernel::factor_sub); denormal
+// pivots are flushed to zero by the seed, i.e. reported as bad.
+__device__ __forceinline__ double pivot_rsqrt_refine(double a, double y) {
+  const double e = fma(-(a * y), y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
+}
 __device__ __forceinline__ double pivot_rsqrt(double a) {
-  if (!(a > 1e-30) || !(a < 1e30)) return rsqrt(a);
-  double y = static_cast<double>(rsqrtf(static_cast<float>(a)));
-  const double h = 0.5 * a;
-#pragma unroll
-  for (int it = 0; it < 3; ++it) {
-    const double e = fma(-h * y, y, 0.5);  // 0.5 (1 - a y^2)
-    y = fma(y, e, y);
-  }
-  return y;
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  return pivot_rsqrt_refine(a, y);
 }
 
 // Off-diagonal 16 x 16 blocks of X = inv(L_kk) from L_kk (lower triangle of S) and the inverted diagonal sub-blocks
@@ -152,25 +153,63 @@ __device__ __forceinline__ void complete_block_inverse(double* S, const double* 
   }
 }
 
+#ifdef LPB_POTF2_PROF  // build-time aid: thread 0 (in the serial warp) time-stamps the phases of ONE launch and prints them
+#define P2_T(k) do { if (tid == 0) p2t[k] = clock64(); } while (0)
+#else
+#define P2_T(k) do { } while (0)
+#endif
 __global__ void __launch_bounds__(512)
 potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __restrict__ info,
                  double* __restrict__ Linv, int full_inverse, double* __restrict__ pack_lkk = nullptr,
                  double* __restrict__ pack_linv = nullptr) {
   extern __shared__ double S[];    // NB*LDS block
   double* rdiag = S + NB * LDS;    // NB: 1 / L[i][i]
-  double* Xd = rdiag + NB;         // SB * XDP
-  double* Tw = Xd + SB * XDP;      // 16 warps * SB * TWP
-  double* cbuf = Tw + 16 * SB * TWP;  // 2 * SB: column j of the diagonal sub-block, double-buffered
-  const int tid = threadIdx.y * 32 + threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* Xd = rdiag + NB;         // 2 x SB * XDP: inv(L_dd) of the current and of the next diagonal sub-block
+  double* Tw = Xd + 2 * SB * XDP;  // 16 warps * SB * TWP
+  double* cbuf = Tw + 16 * SB * TWP;  // 2 x (SB + SB padding): column j of the diagonal sub-block, double-buffered; + SB * XDP scratch
   const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.y * 32 + threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(full, tid >> 5, 0);  // through a shuffle: the compiler then knows it is warp-uniform
+#ifdef LPB_POTF2_PROF
+  long long p2t[40];
+#endif
+  P2_T(0);
   double* blk = Mat + (int64_t)k0 * ldm + k0;
-  for (int idx = tid; idx < NB * NB; idx += 512) {
-    const int r = idx >> 7, c = idx & (NB - 1);
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < nb && c <= r) v = blk[(int64_t)r * ldm + c];
-    S[r * LDS + c] = v;
+  // Warp 0 fetches the first 16 x 16 sub-block by itself and starts factoring it (after the definitions below) while
+  // the other 15 warps bring in the rest: 16-byte loads (Mat is 16-byte aligned with an even pitch, k0 a multiple of
+  // 128), identity padding beyond a ragged block.
+  auto load_pair = [&](int r, int c) {  // entries (r, c), (r, c + 1), c even
+    double2 v = make_double2(0.0, 0.0);
+    const bool in = r < nb;
+    if (in && c <= r) v = *reinterpret_cast<const double2*>(blk + (int64_t)r * ldm + c);
+    S[r * LDS + c] = (in && c <= r) ? v.x : (r == c ? 1.0 : 0.0);
+    S[r * LDS + c + 1] = (in && c + 1 <= r) ? v.y : (r == c + 1 ? 1.0 : 0.0);
+  };
+  if (warp == 0) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) load_pair(lane & 15, 2 * (lane >> 4) + 4 * it);
+    __syncwarp();
+  } else {
+    // every load of a thread in flight at once: one L2 round trip instead of five
+    constexpr int kIt = (NB * (NB / 2) + 479) / 480;
+    double2 ld[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int idx = tid - 32 + 480 * it, r = idx >> 6, c = 2 * (idx & 63);
+      ld[it] = make_double2(0.0, 0.0);
+      if (idx < NB * (NB / 2) && r < nb && c <= r && (r >= SB || c >= SB))
+        ld[it] = *reinterpret_cast<const double2*>(blk + (int64_t)r * ldm + c);
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int idx = tid - 32 + 480 * it, r = idx >> 6, c = 2 * (idx & 63);
+      if (idx < NB * (NB / 2) && (r >= SB || c >= SB)) {
+        const bool in = r < nb;
+        S[r * LDS + c] = (in && c <= r) ? ld[it].x : (r == c ? 1.0 : 0.0);
+        S[r * LDS + c + 1] = (in && c + 1 <= r) ? ld[it].y : (r == c + 1 ? 1.0 : 0.0);
+      }
+    }
   }
-  __syncthreads();
 
   // ---- the serial heart of the factorisation: ONE warp factors the 16 x 16 diagonal sub-block at c0 and inverts
   // it in the same 16 pivot steps.  Lanes 0..15 hold row i of the sub-block (v[k] = a[i][k]); lanes 16..31
@@ -178,62 +217,64 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
   // (v[r] = sum_{l<r} L[r][l] x_l, replaced by x_r at step r).  Both need exactly column j of L at pivot
   // step j -- broadcast through shared memory -- and then the same FMA  v[k] += mult * L[k][j], k > j.
   // sqrt and the divisions are one rsqrt plus Newton corrections (results within an ulp of IEEE).
-  auto factor_sub = [&](int c0) {
+  // The pivot loop is ROLLED: this kernel runs once per panel on an SM whose instruction cache is cold, and
+  // straight-line code that is executed once costs a cache-line fetch (~200 cycles) per eight instructions -- the
+  // fully unrolled version spent 18.8 k cycles on its first sub-block and 4.2 k on the later ones
+  // (LPB_POTF2_PROF).  To keep the row in registers under a rolled loop it SHIFTS: at pivot j, v[k] is the entry of
+  // column j + k, the update  v[k] <- v[k+1] - l * L[j+1+k][j]  moves it down by one for free, and v[0] is always the
+  // pivot column's entry.  Entries past the sub-block's last column read padding of the column buffer and are never
+  // consumed.
+  auto factor_sub = [&](int c0, double* xd) {
     const int i = lane & 15;
     const bool inv_lane = lane >= SB;
-    // One update rule for both halves of the warp.  Factor lanes: v[k] = running a[i][k].  Inverse lanes: v[k] = running
-    // e_i[k] - sum_{l<k} L[k][l] x_l  (the right-hand side of L x = e_i after eliminating x_0 .. x_{k-1}).  At pivot j
-    // both form  l = v[j] / sqrt(a_jj)  -- L[i][j] resp. x_j, and for lane j itself l = a_jj / sqrt(a_jj) = L[j][j] --
-    // and both subtract  l * L[k][j]  from v[k], k > j.  No per-lane selects on the serial chain.
+    // One update rule for both halves of the warp.  Factor lanes: v = running a[i][.].  Inverse lanes: v = running
+    // e_i[.] - sum_{l<.} L[.][l] x_l  (the right-hand side of L x = e_i after eliminating x_0 .. x_{j-1}).  At pivot j
+    // both form  l = v[0] / sqrt(a_jj)  -- L[i][j] resp. x_j, and for lane j itself l = a_jj / sqrt(a_jj) = L[j][j] --
+    // and both subtract  l * L[k][j]  from the entry of column k > j.  No per-lane selects on the serial chain.
+    double* srow = S + (c0 + i) * LDS + c0;
     double v[SB];
 #pragma unroll
-    for (int k = 0; k < SB; ++k)
-      v[k] = inv_lane ? (k == i ? 1.0 : 0.0) : (k <= i ? S[(c0 + i) * LDS + c0 + k] : 0.0);
+    for (int k = 0; k < SB; ++k) v[k] = inv_lane ? (k == i ? 1.0 : 0.0) : (k <= i ? srow[k] : 0.0);
     // the diagonal entry of this lane's row lives in its own register: the next pivot then depends only on
     // rsqrt -> l -> dg -= l * l, not on the shared-memory round trip of the column broadcast
-    double dg = 1.0;
-#pragma unroll
-    for (int k = 0; k < SB; ++k)
-      if (k == i && !inv_lane) dg = v[k];  // static indices only: v[] must stay in registers
+    double dg = inv_lane ? 1.0 : srow[i];
+    double* xcol = inv_lane ? xd + i : cbuf + 4 * SB + i;  // factor lanes write a 16 x XDP scratch instead: no branch in the loop
     double myrd = 1.0;
-    double ajj = __shfl_sync(full, dg, 0);
-    double rs = pivot_rsqrt(ajj);
-    bool any_bad = false;
-#pragma unroll
+    double rs = pivot_rsqrt(__shfl_sync(full, dg, 0));
+#pragma unroll 1
     for (int j = 0; j < SB; ++j) {
-      // a non-positive / non-finite pivot: flagged, and the arithmetic poisons the block by itself (rsqrt of a
-      // negative number is NaN, of zero +inf)
-      any_bad = any_bad || !(ajj > 0.0) || !(ajj < __longlong_as_double(0x7ff0000000000000ll));
-      if (any_bad && lane == 0 && *info == 0) *info = k0 + c0 + j + 1;
-      const double l = v[j] * rs;
+      const double l = v[0] * rs;
       if (i == j) myrd = rs;
-      v[j] = l;
-      if (!inv_lane) dg = fma(-l, l, dg);  // only lanes i > j read it again
-      double* cb = cbuf + (j & 1) * SB;
-      if (!inv_lane) cb[i] = l;
+      dg = fma(-l, l, dg);  // only factor lanes i > j read it again (the inverse lanes' copy is never used)
+      // The next pivot starts now.  An FP64 operation has ~20 cycles of latency and the warp issues in order, so the
+      // source order below is the intended issue order: shuffle -> stores and column loads (they fill the
+      // shuffle's latency) -> seed (MUFU) -> the 15 FMAs of the column update (they fill the seed's) -> the four
+      // dependent operations of the refinement step.  j = 15 computes an unused rs.
+      const double ajj = __shfl_sync(full, dg, (j + 1) & (SB - 1));
+      // branch-free stores (a divergent if / else here would fence the rsqrt chain off from the column update):
+      // the inverse lanes' copy of l lands in the padding half of the column buffer
+      double* cb = cbuf + (j & 1) * (2 * SB);
+      cb[lane] = l;
+      if (inv_lane ? (j > i) : (j <= i)) srow[j] = l;          // L[i][j] | X^T in the strictly upper triangle
+      xcol[j * XDP] = (j >= i) ? l : 0.0;                      // X[r = j][c = i], zero above the diagonal (factor lanes: scratch)
       __syncwarp();
-      if (j + 1 < SB) {  // the next pivot and its rsqrt start now: their latency hides behind the column update
-        ajj = __shfl_sync(full, dg, j + 1);
-        rs = pivot_rsqrt(ajj);
-      }
+      const double* cn = cb + j + 1;                  // L[j+1 ..][j]; past row 15: padding, finite or not, never consumed
+      double cv[SB - 1];
 #pragma unroll
-      for (int k = 0; k < SB; ++k)
-        if (k > j) v[k] = fma(-l, cb[k], v[k]);  // entries above a row's diagonal are garbage, never read
-    }
-    if (!inv_lane) {
-      rdiag[c0 + i] = myrd;
+      for (int k = 0; k + 1 < SB; ++k) cv[k] = cn[k];
+      double y;
+      asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(ajj));
 #pragma unroll
-      for (int k = 0; k < SB; ++k)
-        if (k <= i) S[(c0 + i) * LDS + c0 + k] = v[k];
+      for (int k = 0; k + 1 < SB; ++k) v[k] = fma(-l, cv[k], v[k + 1]);
+      rs = pivot_rsqrt_refine(ajj, y);
     }
-    __syncwarp();  // the factor rows are written before the transposed inverse lands above the diagonal
-    if (inv_lane) {
-#pragma unroll
-      for (int r = 0; r < SB; ++r) {
-        Xd[r * XDP + i] = (r >= i) ? v[r] : 0.0;          // X[r][c = i], zero above the diagonal
-        if (r > i) S[(c0 + i) * LDS + c0 + r] = v[r];     // X^T in the upper triangle
-      }
-    }
+    // A non-positive / non-finite pivot leaves 1 / sqrt = NaN or +inf in its lane and NaN in every later one (the
+    // arithmetic poisons the block by itself), so ONE test per sub-block finds the first bad pivot -- nothing on the
+    // per-pivot chain.
+    const bool bad = !inv_lane && !(myrd > 0.0 && myrd < __longlong_as_double(0x7ff0000000000000ll));
+    const unsigned mask = __ballot_sync(full, bad);
+    if (mask && lane == 0 && *info == 0) *info = k0 + c0 + __ffs(mask);
+    if (!inv_lane) rdiag[c0 + i] = myrd;
   };
   // rank-16 update of the 16 x 16 sub-block t of the trailing lower triangle of step kb (t = 0: the next diagonal one)
   auto update_sub = [&](int kb, int t) {
@@ -261,74 +302,131 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
       if (cj + jj <= ri) S[ri * LDS + cj + jj] -= acc[jj];
   };
 
-  // Look-ahead inside the block: after the rows below sub-block kb are solved, warp 0 updates ONLY the next diagonal
-  // sub-block and goes straight on to factor it, while the other 15 warps apply the rank-16 update to the rest of
-  // the trailing triangle -- the serial warp no longer waits for (nor makes everybody wait behind) the bulk update.
-  // Same arithmetic per entry as the plain loop (every sub-block sees the same updates in the same order).
-  if (warp == 0) factor_sub(0);
-  for (int kb = 0; kb < NSB; ++kb) {
+  // rows below sub-block kb:  P[r][c] = sum_{l <= c} S[r][c0 + l] X[c][l]  for `ncol` columns per thread starting at
+  // column cq; the threads of a row sit in one warp: all reads of the row precede its writes
+  auto solve_rows = [&](int kb, const double* xd, int r, int cq, auto ncol_tag) {
+    constexpr int NC = decltype(ncol_tag)::value;
     const int c0 = kb * SB;
-    __syncthreads();  // inv(L_dd) of sub-block kb is in Xd; every update of step kb - 1 has landed
-    // ---- rows below the sub-block: P[r][c] = sum_{l<=c} S[r][c0+l] X[c][l]   (4 columns per thread)
-    {
-      const int r = c0 + SB + (tid >> 2), q = tid & 3;
-      const bool act = r < NB;
-      double out[4] = {0.0, 0.0, 0.0, 0.0};
-      if (act) {
-        double row[SB];
+    const bool act = r < NB;
+    double out[NC];
+    if (act) {
+      double row[SB];
 #pragma unroll
-        for (int l = 0; l < SB; ++l) row[l] = S[r * LDS + c0 + l];
+      for (int l = 0; l < SB; ++l) row[l] = S[r * LDS + c0 + l];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const double* xr = Xd + (4 * q + e) * XDP;
-          double sum = 0.0;
+      for (int e = 0; e < NC; ++e) {
+        const double* xr = xd + (cq + e) * XDP;
+        double sum = 0.0;
 #pragma unroll
-          for (int l = 0; l < SB; ++l) sum += row[l] * xr[l];
-          out[e] = sum;
-        }
-      }
-      __syncwarp();  // the four threads of a row sit in one warp: all reads of the row precede its writes
-      if (act) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) S[r * LDS + c0 + 4 * q + e] = out[e];
+        for (int l = 0; l < SB; ++l) sum += row[l] * xr[l];
+        out[e] = sum;
       }
     }
-    __syncthreads();
-    // ---- rank-16 update of the remaining 16 x 16 sub-blocks (lower triangle)
-    const int nrem = NSB - 1 - kb;
-    const int T = nrem * (nrem + 1) / 2;
+    __syncwarp();
+    if (act) {
+#pragma unroll
+      for (int e = 0; e < NC; ++e) S[r * LDS + c0 + cq + e] = out[e];
+    }
+  };
+  // Block columns [kb_lo, kb_hi) of L (rows on and below the diagonal sub-block) and their inverted diagonal
+  // sub-blocks, written by `nthr` threads (this one is number t).  Used by the three warps that idle during a phase --
+  // block column kb - 1 is final once phase kb - 1 has ended -- and by everybody for the last two after the loop, so
+  // that the kernel does not end on 80 KB of stores from one SM.
+  const bool early_store = !full_inverse && !pack_lkk && !pack_linv;
+  auto store_cols = [&](int kb_lo, int kb_hi, int t, int nthr) {
+    for (int kb = kb_lo; kb < kb_hi; ++kb) {
+      const int c0 = kb * SB;
+      for (int e = t; e < (NB - c0) * SB; e += nthr) {
+        const int r = c0 + (e >> 4), c = c0 + (e & 15);
+        if (r < nb && c <= r) blk[(int64_t)r * ldm + c] = S[r * LDS + c];
+      }
+      for (int e = t; e < SB * SB; e += nthr) {
+        const int i = c0 + (e >> 4), c = c0 + (e & 15);
+        double v = 0.0;
+        if (i < nb && c <= i) v = (c == i) ? rdiag[i] : S[c * LDS + i];
+        Linv[i * NB + c] = v;
+      }
+    }
+  };
+
+  // Schedule.  Sub-block kb is factored by warp 0 alone (the serial chain of the panel); everything else is arranged
+  // so that warp 0 never waits for more than it needs:
+  //   prologue   warp 0: load + factor sub-block 0        | warps 1..15: load the rest of the block
+  //   phase kb   warp 0: the 16 rows of block row kb + 1 times inv(L_kb)^T -> arrive at barrier 1 -> rank-16 update of
+  //              the next diagonal sub-block -> factor it (into the other Xd buffer)
+  //              warps 4, 8, 12: write block column kb - 1 of L and its inverted sub-block to global memory
+  //              12 worker warps (not 4, 8, 12: those share warp 0's sub-partition): the rows of block rows >= kb + 2
+  //              -> wait at barrier 1 (they need warp 0's rows) -> rank-16 update of the rest of the trailing triangle
+  //   one CTA barrier per phase.  Same arithmetic per entry as the plain right-looking loop (every sub-block sees the
+  //   same updates in the same order).  factor_sub has ONE call site (one copy of its code to fetch).
+  for (int kb = -1; kb + 1 < NSB; ++kb) {
+    double* xd_next = Xd + ((kb + 1) & 1) * (SB * XDP);
     if (warp == 0) {
-      if (T > 0) {
+      if (kb >= 0) {
+        solve_rows(kb, Xd + (kb & 1) * (SB * XDP), (kb + 1) * SB + (lane & 15), 8 * (lane >> 4), std::integral_constant<int, 8>{});
+        __threadfence_block();
+        asm volatile("bar.arrive 1, 416;" ::: "memory");  // the 12 workers wait for these rows
+        P2_T(2 + 4 * kb);
+        __syncwarp();
         update_sub(kb, 0);
         __syncwarp();
-        factor_sub(c0 + SB);
+        P2_T(3 + 4 * kb);
       }
-    } else {
-      for (int t = warp; t < T; t += 15) update_sub(kb, t);
+      factor_sub((kb + 1) * SB, xd_next);
+      if (kb >= 0) P2_T(4 + 4 * kb);
+    } else if (kb >= 0 && (warp & 3) != 0) {
+      // ---- 12 workers: the warps that share warp 0's SM sub-partition (4, 8, 12) are not among them -- their FP64 and
+      // shared-memory instructions queued in front of the serial chain's and stretched it by up to 60 %.  (Splitting
+      // warp 0's rows and diagonal update over those three as well was measured: no faster, both are bound by the
+      // latency of their 16-term sums, and the extra code is fetched cold on every launch.)
+      const int w = (warp >> 2) * 3 + (warp & 3) - 1, wt = w * 32 + lane;
+      solve_rows(kb, Xd + (kb & 1) * (SB * XDP), (kb + 2) * SB + (wt >> 2), 4 * (wt & 3), std::integral_constant<int, 4>{});
+      asm volatile("bar.sync 1, 416;" ::: "memory");
+      const int nrem = NSB - 1 - kb;
+      const int T = nrem * (nrem + 1) / 2;
+      for (int t = 1 + w; t < T; t += 12) update_sub(kb, t);
+    } else if (kb >= 1 && early_store) {
+      store_cols(kb - 1, kb, (warp >> 2) * 32 - 32 + lane, 96);  // warps 4, 8, 12: block column kb - 1 is final since the last barrier
     }
+    __syncthreads();  // inv(L_dd) of sub-block kb + 1 is in its Xd buffer; every update of step kb has landed
+    if (kb >= 0) P2_T(5 + 4 * kb); else P2_T(1);
   }
-  __syncthreads();
+  P2_T(35);
 
   // ---- L back to Mat (and, for the distributed factorisation, into the packed send buffer: dense 128 x 128, zero
   // above the diagonal and beyond a ragged block)
-  for (int idx = tid; idx < NB * NB; idx += 512) {
-    const int r = idx >> 7, c = idx & (NB - 1);
-    const bool in = r < nb && c <= r;
-    if (in) blk[(int64_t)r * ldm + c] = S[r * LDS + c];
-    if (pack_lkk) pack_lkk[idx] = in ? S[r * LDS + c] : 0.0;
+  if (early_store) {
+    store_cols(NSB - 2, NSB, tid, 512);  // the last two block columns; the others left during the phases
+  } else {
+    for (int idx = tid; idx < NB * NB; idx += 512) {
+      const int r = idx >> 7, c = idx & (NB - 1);
+      const bool in = r < nb && c <= r;
+      if (in) blk[(int64_t)r * ldm + c] = S[r * LDS + c];
+      if (pack_lkk) pack_lkk[idx] = in ? S[r * LDS + c] : 0.0;
+    }
+    // ---- X to Linv.  Off-diagonal blocks of X: only the full-inverse consumers need them (trsm_impl 2); the default
+    // TRSM uses the 16 x 16 diagonal inverses alone and the solves complete the inverses off the critical path
+    // (linv_complete_kernel reads nothing but the diagonal sub-blocks), so the early-store path writes only those
+    // 8 x 256 entries and the rest of the 128 x 128 slot keeps whatever the previous factorisation left there.
+    if (full_inverse) complete_block_inverse(S, rdiag, Tw, tid);
+    for (int idx = tid; idx < NB * NB; idx += 512) {
+      const int i = idx >> 7, c = idx & (NB - 1);
+      double v = 0.0;
+      if (i < nb && c <= i) v = (c == i) ? rdiag[i] : S[c * LDS + i];
+      Linv[idx] = v;
+      if (pack_linv) pack_linv[idx] = v;
+    }
   }
-
-  // ---- off-diagonal blocks of X: only the full-inverse consumers need them (trsm_impl 2); the default TRSM uses
-  // the 16 x 16 diagonal inverses alone and the solves complete the inverses off the critical path
-  // (linv_complete_kernel), so this stage is normally skipped (the blocks stay zero).
-  if (full_inverse) complete_block_inverse(S, rdiag, Tw, tid);
-  for (int idx = tid; idx < NB * NB; idx += 512) {
-    const int i = idx >> 7, c = idx & (NB - 1);
-    double v = 0.0;
-    if (i < nb && c <= i) v = (c == i) ? rdiag[i] : S[c * LDS + i];
-    Linv[idx] = v;
-    if (pack_linv) pack_linv[idx] = v;
+#ifdef LPB_POTF2_PROF
+  P2_T(36);
+  if (tid == 0 && k0 == 1024) {
+    printf("potf2 k0=%d: load+factor0 %lld |", k0, p2t[1] - p2t[0]);
+    for (int kb = 0; kb + 1 < NSB; ++kb)
+      printf(" kb%d: rows16 %lld upd0 %lld factor %lld sync %lld |", kb, p2t[2 + 4 * kb] - p2t[1 + 4 * kb],
+             p2t[3 + 4 * kb] - p2t[2 + 4 * kb], p2t[4 + 4 * kb] - p2t[3 + 4 * kb], p2t[5 + 4 * kb] - p2t[4 + 4 * kb]);
+    printf(" stores %lld total %lld\n", p2t[36] - p2t[35], p2t[36] - p2t[0]);
   }
+#endif
 }
 
 // ------------------------------------------------------------------ TRSM: X L_kk^T = B, 64 rows per CTA
@@ -1542,7 +1640,7 @@ int set_smem(K kern, size_t bytes) {
 }
 
 constexpr size_t kPotf2Smem = (size_t)(NB * LDS + NB) * sizeof(double);
-constexpr size_t kPotf2InvSmem = (size_t)(NB * LDS + NB + SB * XDP + 16 * SB * TWP + 2 * SB) * sizeof(double);
+constexpr size_t kPotf2InvSmem = (size_t)(NB * LDS + NB + 2 * SB * XDP + 16 * SB * TWP + 4 * SB + SB * XDP) * sizeof(double);
 constexpr size_t kTrsmSmem = (size_t)((NB + TRSM_ROWS) * LDS) * sizeof(double);
 constexpr size_t kTrsvSmem = (size_t)(NB * LDS + NB + 2 * NB) * sizeof(double);
 
