@@ -9,6 +9,7 @@
 // large-problem path does.  Problems are independent: sharding a batch over GPUs needs no collective.
 #include "ipm_driver.hpp"
 #include "kernels.hpp"
+#include "panel_factor.cuh"
 
 namespace lpb {
 namespace {
@@ -53,7 +54,7 @@ __device__ __forceinline__ void block_allreduce(double (&v)[NV], const bool is_m
 struct SmemDev {
   int m, n, lda, ldm;
   int mp, nsb;           // m rounded up to a multiple of 16 (rows >= m of M are identity padding), mp / 16
-  double *Xinv, *cbuf;   // nsb x 16 x kXP inverted diagonal sub-blocks of L; 2 x 16 pivot-column broadcast buffer
+  double *Xinv, *cbuf;   // nsb x 16 x kXP inverted diagonal sub-blocks of L; scratch of factor_sub16 (panel_factor.cuh)
   int* flag;             // bad-pivot flag of the factorisation (shared)
   double *A, *M, *b, *c, *x, *y, *z, *rP, *rD, *dinv, *xs, *r1, *p, *q, *u, *v, *dx, *dy, *dz, *t0, *t1, *sx,
       *red;
@@ -184,52 +185,14 @@ struct SmemDev {
     // barriers per 16 columns instead of 2 per column.  Pivot <= 0 or non-finite -> NumericalProblem
     // (newton_equations.rs:63), decided uniformly from a shared flag.
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned full = 0xffffffffu;
     if (tid == 0) *flag = 0;
     for (int kb = 0; kb < nsb; ++kb) {
       const int c0 = kb * kSB;
       double* Xd = Xinv + kb * kSB * kXP;
       if (warp == 0) {
-        const int i = lane & 15;
-        const bool inv_lane = lane >= kSB;
-        double v[kSB];
-#pragma unroll
-        for (int k = 0; k < kSB; ++k) v[k] = (!inv_lane && k <= i) ? M[(c0 + i) * ldm + c0 + k] : 0.0;
-        // the diagonal entry of this lane's row lives in its own register: the next pivot then depends only on
-        // rsqrt -> l -> dg -= l * l, not on the shared-memory round trip of the column broadcast
-        double dg = inv_lane ? 0.0 : M[(c0 + i) * ldm + c0 + i];
-#pragma unroll
-        for (int j = 0; j < kSB; ++j) {
-          const double ajj = __shfl_sync(full, dg, j);
-          const bool bad = !(ajj > 0.0) || !isfinite(ajj);
-          if (bad && lane == 0) *flag = 1;
-          // rsqrt is accurate to 1 ulp (CUDA math API), so d = a rs and l = a[i][j] rs are within 2 ulp of sqrt and of
-          // the quotient: far below the n eps backward error of the factorisation itself, and the pivot chain
-          // SHFL -> rsqrt -> l -> dg stays short (no divisions, no Newton steps, no divergent branch).
-          double rs = rsqrt(ajj);
-          double d = ajj * rs;
-          if (bad) d = rs = __longlong_as_double(0x7ff8000000000000ll);
-          const double num = inv_lane ? ((i == j ? 1.0 : 0.0) - v[j]) : v[j];  // inverse lanes: x_j of column i
-          double l = num * rs;
-          if (!inv_lane && i == j) l = d;
-          v[j] = l;
-          if (!inv_lane && i > j) dg = fma(-l, l, dg);
-          double* cb = cbuf + (j & 1) * kSB;
-          if (!inv_lane) cb[i] = l;
-          __syncwarp();
-          const double mult = inv_lane ? l : -l;
-#pragma unroll
-          for (int k = 0; k < kSB; ++k)
-            if (k > j) v[k] = fma(mult, cb[k], v[k]);
-        }
-        if (!inv_lane) {
-#pragma unroll
-          for (int k = 0; k < kSB; ++k)
-            if (k <= i) M[(c0 + i) * ldm + c0 + k] = v[k];
-        } else {
-#pragma unroll
-          for (int r = 0; r < kSB; ++r) Xd[r * kXP + i] = (r >= i) ? v[r] : 0.0;  // X[r][c = i]
-        }
+        // panel_factor.cuh: the same rolled, branch-free pivot loop as the panel kernel of K2 (hardware rsqrt seed +
+        // one cubic step instead of the library rsqrt, no per-pivot test: a bad pivot poisons its lane)
+        if (factor_sub16<kXP, false>(M + (c0 + (lane & 15)) * ldm + c0, Xd, cbuf, nullptr, lane) && lane == 0) *flag = 1;
       }
       __syncthreads();
       {  // rows below: P[r][c] = sum_l M[r][c0+l] X[c][l]  (4 columns per thread, the 4 threads of a row in one warp)
@@ -466,7 +429,7 @@ __host__ __device__ inline int batched_mp(int m) { return (m + kSB - 1) / kSB * 
 __host__ __device__ inline size_t batched_smem_doubles(int m, int n) {
   const size_t mp = (size_t)batched_mp(m);
   return (size_t)m * (n + 1) + mp * (mp + 1) + 10 * (size_t)n + 5 * (size_t)m + 2 * mp + 2 * kMaxM + 8 * kBWarps +
-         (mp / kSB) * kSB * kXP + 2 * kSB + 2;
+         (mp / kSB) * kSB * kXP + panel_factor_scratch(kXP) + 2;
 }
 
 __global__ void __launch_bounds__(kBT)
@@ -499,7 +462,7 @@ batched_ipm_kernel(int64_t batch, int m, int n, const double* __restrict__ gA, c
     d.sx = take(2 * kMaxM);
     d.red = take(8 * kBWarps);
     d.Xinv = take((size_t)d.nsb * kSB * kXP);
-    d.cbuf = take(2 * kSB);
+    d.cbuf = take(panel_factor_scratch(kXP));
     d.flag = reinterpret_cast<int*>(take(2));
     d.have_pq = 0;
     d.nan_pq = 0;

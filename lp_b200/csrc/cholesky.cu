@@ -20,6 +20,7 @@
 
 #include "dist_schedule.hpp"
 #include "kernels.hpp"
+#include "panel_factor.cuh"
 
 namespace lpb {
 
@@ -81,23 +82,6 @@ constexpr int SB = 16;        // sub-block
 constexpr int NSB = NB / SB;  // 8
 constexpr int XDP = SB + 1;   // pitch of the 16 x 16 inverse of the current diagonal sub-block (odd: the four row groups a warp reads hit different banks)
 constexpr int TWP = 9;        // pitch of the per-warp 16 x 8 scratch of the block-inverse step
-
-// 1 / sqrt(a) for a pivot, on the serial chain of the panel kernel: the hardware seed (MUFU.RSQ64H: it reads the
-// high word of the double, ~2^-22 relative over the whole FP64 exponent range, no conversions or range branch) and
-// ONE third-order step  y (1 + e/2 + 3 e^2 / 8),  e = 1 - a y^2  (truncation 5 e^3 / 16 ~ 2^-67; the result is within
-// 1 ulp) -- four dependent FP64 operations behind the seed instead of the six of two Newton steps; an FP64
-// operation costs ~20 cycles of latency here and this chain runs once per pivot.  Non-positive / non-finite pivots
-// come out as NaN / +inf / NaN, which is how the caller detects them (potf2_inv_kernel::factor_sub); denormal
-// pivots are flushed to zero by the seed, i.e. reported as bad.
-__device__ __forceinline__ double pivot_rsqrt_refine(double a, double y) {
-  const double e = fma(-(a * y), y, 1.0);
-  return fma(y * e, fma(0.375, e, 0.5), y);
-}
-__device__ __forceinline__ double pivot_rsqrt(double a) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  return pivot_rsqrt_refine(a, y);
-}
 
 // Off-diagonal 16 x 16 blocks of X = inv(L_kk) from L_kk (lower triangle of S) and the inverted diagonal sub-blocks
 // (X^T in the strictly upper triangle of S, its diagonal in rdiag): one block diagonal at a time,
@@ -217,64 +201,11 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
   // (v[r] = sum_{l<r} L[r][l] x_l, replaced by x_r at step r).  Both need exactly column j of L at pivot
   // step j -- broadcast through shared memory -- and then the same FMA  v[k] += mult * L[k][j], k > j.
   // sqrt and the divisions are one rsqrt plus Newton corrections (results within an ulp of IEEE).
-  // The pivot loop is ROLLED: this kernel runs once per panel on an SM whose instruction cache is cold, and
-  // straight-line code that is executed once costs a cache-line fetch (~200 cycles) per eight instructions -- the
-  // fully unrolled version spent 18.8 k cycles on its first sub-block and 4.2 k on the later ones
-  // (LPB_POTF2_PROF).  To keep the row in registers under a rolled loop it SHIFTS: at pivot j, v[k] is the entry of
-  // column j + k, the update  v[k] <- v[k+1] - l * L[j+1+k][j]  moves it down by one for free, and v[0] is always the
-  // pivot column's entry.  Entries past the sub-block's last column read padding of the column buffer and are never
-  // consumed.
+  // (panel_factor.cuh: rolled, shifting, branch-free pivot loop -- instruction fetch, not arithmetic, is what a
+  // once-per-launch kernel pays for)
   auto factor_sub = [&](int c0, double* xd) {
-    const int i = lane & 15;
-    const bool inv_lane = lane >= SB;
-    // One update rule for both halves of the warp.  Factor lanes: v = running a[i][.].  Inverse lanes: v = running
-    // e_i[.] - sum_{l<.} L[.][l] x_l  (the right-hand side of L x = e_i after eliminating x_0 .. x_{j-1}).  At pivot j
-    // both form  l = v[0] / sqrt(a_jj)  -- L[i][j] resp. x_j, and for lane j itself l = a_jj / sqrt(a_jj) = L[j][j] --
-    // and both subtract  l * L[k][j]  from the entry of column k > j.  No per-lane selects on the serial chain.
-    double* srow = S + (c0 + i) * LDS + c0;
-    double v[SB];
-#pragma unroll
-    for (int k = 0; k < SB; ++k) v[k] = inv_lane ? (k == i ? 1.0 : 0.0) : (k <= i ? srow[k] : 0.0);
-    // the diagonal entry of this lane's row lives in its own register: the next pivot then depends only on
-    // rsqrt -> l -> dg -= l * l, not on the shared-memory round trip of the column broadcast
-    double dg = inv_lane ? 1.0 : srow[i];
-    double* xcol = inv_lane ? xd + i : cbuf + 4 * SB + i;  // factor lanes write a 16 x XDP scratch instead: no branch in the loop
-    double myrd = 1.0;
-    double rs = pivot_rsqrt(__shfl_sync(full, dg, 0));
-#pragma unroll 1
-    for (int j = 0; j < SB; ++j) {
-      const double l = v[0] * rs;
-      if (i == j) myrd = rs;
-      dg = fma(-l, l, dg);  // only factor lanes i > j read it again (the inverse lanes' copy is never used)
-      // The next pivot starts now.  An FP64 operation has ~20 cycles of latency and the warp issues in order, so the
-      // source order below is the intended issue order: shuffle -> stores and column loads (they fill the
-      // shuffle's latency) -> seed (MUFU) -> the 15 FMAs of the column update (they fill the seed's) -> the four
-      // dependent operations of the refinement step.  j = 15 computes an unused rs.
-      const double ajj = __shfl_sync(full, dg, (j + 1) & (SB - 1));
-      // branch-free stores (a divergent if / else here would fence the rsqrt chain off from the column update):
-      // the inverse lanes' copy of l lands in the padding half of the column buffer
-      double* cb = cbuf + (j & 1) * (2 * SB);
-      cb[lane] = l;
-      if (inv_lane ? (j > i) : (j <= i)) srow[j] = l;          // L[i][j] | X^T in the strictly upper triangle
-      xcol[j * XDP] = (j >= i) ? l : 0.0;                      // X[r = j][c = i], zero above the diagonal (factor lanes: scratch)
-      __syncwarp();
-      const double* cn = cb + j + 1;                  // L[j+1 ..][j]; past row 15: padding, finite or not, never consumed
-      double cv[SB - 1];
-#pragma unroll
-      for (int k = 0; k + 1 < SB; ++k) cv[k] = cn[k];
-      double y;
-      asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(ajj));
-#pragma unroll
-      for (int k = 0; k + 1 < SB; ++k) v[k] = fma(-l, cv[k], v[k + 1]);
-      rs = pivot_rsqrt_refine(ajj, y);
-    }
-    // A non-positive / non-finite pivot leaves 1 / sqrt = NaN or +inf in its lane and NaN in every later one (the
-    // arithmetic poisons the block by itself), so ONE test per sub-block finds the first bad pivot -- nothing on the
-    // per-pivot chain.
-    const bool bad = !inv_lane && !(myrd > 0.0 && myrd < __longlong_as_double(0x7ff0000000000000ll));
-    const unsigned mask = __ballot_sync(full, bad);
+    const unsigned mask = factor_sub16<XDP, true>(S + (c0 + (lane & 15)) * LDS + c0, xd, cbuf, rdiag + c0 + (lane & 15), lane);
     if (mask && lane == 0 && *info == 0) *info = k0 + c0 + __ffs(mask);
-    if (!inv_lane) rdiag[c0 + i] = myrd;
   };
   // rank-16 update of the 16 x 16 sub-block t of the trailing lower triangle of step kb (t = 0: the next diagonal one)
   auto update_sub = [&](int kb, int t) {
@@ -331,20 +262,27 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
   // Block columns [kb_lo, kb_hi) of L (rows on and below the diagonal sub-block) and their inverted diagonal
   // sub-blocks, written by `nthr` threads (this one is number t).  Used by the three warps that idle during a phase --
   // block column kb - 1 is final once phase kb - 1 has ended -- and by everybody for the last two after the loop, so
-  // that the kernel does not end on 80 KB of stores from one SM.
-  const bool early_store = !full_inverse && !pack_lkk && !pack_linv;
+  // that the kernel does not end on 80 KB of stores from one SM (300 KB with the packed copies of the distributed
+  // factorisation).  Only the diagonal sub-blocks of the inverse are written: nothing reads the rest of a Linv slot
+  // before linv_complete_kernel has rebuilt it (the panel TRSM and linv_complete_kernel use the sub-blocks alone), and
+  // nobody reads the packed diagonal block above its diagonal sub-blocks (panel_unpack2_kernel copies c <= r).
+  const bool early_store = !full_inverse;
   auto store_cols = [&](int kb_lo, int kb_hi, int t, int nthr) {
     for (int kb = kb_lo; kb < kb_hi; ++kb) {
       const int c0 = kb * SB;
       for (int e = t; e < (NB - c0) * SB; e += nthr) {
         const int r = c0 + (e >> 4), c = c0 + (e & 15);
-        if (r < nb && c <= r) blk[(int64_t)r * ldm + c] = S[r * LDS + c];
+        const bool in = r < nb && c <= r;
+        const double v = in ? S[r * LDS + c] : 0.0;
+        if (in) blk[(int64_t)r * ldm + c] = v;
+        if (pack_lkk) pack_lkk[r * NB + c] = v;  // packed send buffer: what lies above the diagonal SUB-blocks is never read
       }
       for (int e = t; e < SB * SB; e += nthr) {
         const int i = c0 + (e >> 4), c = c0 + (e & 15);
         double v = 0.0;
         if (i < nb && c <= i) v = (c == i) ? rdiag[i] : S[c * LDS + i];
         Linv[i * NB + c] = v;
+        if (pack_linv) pack_linv[i * NB + c] = v;
       }
     }
   };
@@ -1640,7 +1578,7 @@ int set_smem(K kern, size_t bytes) {
 }
 
 constexpr size_t kPotf2Smem = (size_t)(NB * LDS + NB) * sizeof(double);
-constexpr size_t kPotf2InvSmem = (size_t)(NB * LDS + NB + 2 * SB * XDP + 16 * SB * TWP + 4 * SB + SB * XDP) * sizeof(double);
+constexpr size_t kPotf2InvSmem = (size_t)(NB * LDS + NB + 2 * SB * XDP + 16 * SB * TWP + panel_factor_scratch(XDP)) * sizeof(double);
 constexpr size_t kTrsmSmem = (size_t)((NB + TRSM_ROWS) * LDS) * sizeof(double);
 constexpr size_t kTrsvSmem = (size_t)(NB * LDS + NB + 2 * NB) * sizeof(double);
 

@@ -121,10 +121,11 @@ def test_optional_refinement_steps_leave_the_answer_within_the_bar(wl):
 def test_summing_M_in_one_chain_is_what_loses_the_trajectory_at_C3():
     """Round 1 summed every entry of M in one register chain over K (option "syrk_chain" = 1; a single cuBLAS DGEMM
     rounds the same way: 33 ulp rms on the diagonal at C3 against 3 ulp blocked, tools/time_syrk.py).  With that M
-    the unrefined solve still meets the bar on status, iterations and objective, but from rho_mu ~ 1e-4 on its step
-    lengths leave the oracle's and x at the default tolerance is only 1e-5-close (measured 1.07e-5); with K1's
-    blocked accumulation -- everything else equal -- it is 2e-8-close (test_every_entry_of_x_matches_the_oracle).
-    The looser bound asserted here is the round-1 one; the print shows both runs."""
+    the unrefined solve still reaches the optimum (objective to 1e-8), but from rho_mu ~ 1e-4 on its step lengths leave
+    the oracle's: measured 24 ... 28 iterations depending on the rounding of the other kernels, x at the default
+    tolerance 1e-5-close.  With K1's blocked accumulation -- everything else equal -- the run follows the oracle: 24
+    iterations, x 2e-8-close.  Asserted: the bar for the default, and that the one-chain control is at least 30x
+    further from the oracle's x (the finding this round's change of default rests on)."""
     g, xs, its = gold("C3")
     out = {}
     with ResidentProblem(problem("C3")) as rp:
@@ -134,8 +135,9 @@ def test_summing_M_in_one_chain_is_what_loses_the_trajectory_at_C3():
             out[chain] = (res.iteration(), np.abs(res.x() - xs[1e-8]).max(), abs(res.fun() - g["fun"]) / abs(g["fun"]))
             print("C3 syrk_chain=%d refine=0: iterations %d (oracle %d), max|dx| %.3e, rel. objective difference %.2e" % (
                 (chain,) + (out[chain][0], its[1e-8]) + out[chain][1:]))
-    assert abs(out[1][0] - its[1e-8]) <= 1 and out[1][2] <= 1e-8 and out[1][1] <= 5e-4
     assert abs(out[0][0] - its[1e-8]) <= 1 and out[0][2] <= 1e-8 and out[0][1] <= 1e-6
+    assert out[1][2] <= 1e-8 and out[1][0] <= its[1e-8] + 8
+    assert out[1][1] >= 30 * out[0][1]
 
 
 def test_two_host_threads_each_with_its_own_context():
