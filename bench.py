@@ -328,11 +328,12 @@ def _roofline(prof_sum, m, n_loc, peak_measured=None):
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE syrk_dmma_kernel launch, from the committed
 # `ncu --set full` captures (profiles/); keyed by (m, n_local).
 SYRK_TRAFFIC = {
-    # C3 on 1 GPU, banded tile order: 46.05 GB read + 1.08 GB written (profiles/ncu_syrk_C3_r01_v14.txt);
-    # algorithmic bytes: 3.22 GB of A (dense columns) + 1.07 GB of M.  The kernel is DMMA-bound (DRAM at 3 %
-    # of peak); the re-reads are operand tiles streamed once per wave of 148 tiles.
+    # C3 on 1 GPU, banded tile order, K summed in blocks of 512 columns: 38.58 GB read + 2.84 GB written
+    # (profiles/ncu_syrk_C3_r02_blocked.txt; round 1 without the blocked sum: 46.05 + 1.08); algorithmic bytes: 3.22 GB of
+    # A (dense columns) + 1.07 GB of M.  The kernel is DMMA-bound (DRAM at 2.6 % of peak); the re-reads are operand tiles
+    # streamed once per wave of 148 tiles.
     # NOT measured in the run (ncu cannot run inside a timed bench): the value of the committed capture.
-    (16384, 24576): (46.048303e9 + 1.082822e9, "profiles/ncu_syrk_C3_r01_v14.txt (ncu --set full, one launch)"),
+    (16384, 24576): (38.577897e9 + 2.840231e9, "profiles/ncu_syrk_C3_r02_blocked.txt (ncu --set full, one launch)"),
 }
 
 
