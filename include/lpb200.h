@@ -136,6 +136,21 @@ int lpb_create_sharded_synthetic(lpb_ctx** ctx, int64_t m, int64_t n_global, int
                                  int64_t n_local, uint64_t seed, int rank, int world,
                                  const void* nccl_unique_id, void* stream);
 
+/* Peer-memory hand-off inside the distributed factorisation (optional; no reference counterpart).  The owner of a
+ * panel writes the 128 rows the next owner needs straight into every peer's panel slot over NVLink and raises a flag
+ * there, instead of an ncclBroadcast of 128 KB (cholesky.cu: peer_push_kernel / wait_flag_kernel).  The ring of
+ * 2 x world panel slots and the mappings of the other ranks' rings belong to the PROCESS (one process per GPU), like
+ * the NCCL communicator; a context attaches to them while it lives.
+ *   lpb_peer_export: *state_out = 0: attached to a ring this process has mapped before -- nothing to do;
+ *                    1: a new ring was allocated, handle64_out holds its cudaIpcMemHandle: all-gather the handles in
+ *                       rank order and call lpb_peer_import with all `world` of them (64 bytes each);
+ *                    2: another live context of this process holds the ring -- this one keeps ncclBroadcast.
+ *   Every rank must reach the same verdict: unless ALL ranks exported and imported successfully, all of them call
+ *   lpb_set_option(ctx, "peer_panels", -1) (give the ring up).  "peer_panels" = 0 / 1 switches the hand-off off / on
+ *   for a context whose peers are mapped.  lpb_comm_finalize frees the ring. */
+int lpb_peer_export(lpb_ctx* ctx, void* handle64_out, int* state_out);
+int lpb_peer_import(lpb_ctx* ctx, const void* handles, int world);
+
 /* Copy this context's (shard of the) slack-form problem back to the host: A_out m x n_local
  * (leading dimension lda_out >= n_local), b_out m, c_out n_local; any pointer may be NULL.
  * (Accessors Problem::A()/b()/c(), linear_program.rs:42-54, for device-generated shards.) */

@@ -94,6 +94,8 @@ SIGNATURES = {
     "lpb_destroy": (C.c_int, [C.c_void_p]),
     "lpb_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "lpb_comm_ready": (C.c_int, [C.c_int, C.c_int]),
+    "lpb_peer_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "lpb_peer_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "lpb_comm_finalize": (C.c_int, []),
     "lpb_create_sharded": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_int,

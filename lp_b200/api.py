@@ -12,6 +12,7 @@ All numerical work happens inside liblpb200.so on the GPU; this file only marsha
 from __future__ import annotations
 
 import ctypes as C
+import os
 import enum
 from typing import Optional
 
@@ -599,6 +600,45 @@ class ShardedProblem(ResidentProblem):
                                     uid, C.c_void_p(stream))
         _raise_for(rc)
         self.handle = h
+        self._map_peer_memory(lib)
+
+    def _map_peer_memory(self, lib):
+        """Peer-memory hand-off of the distributed factorisation (include/lpb200.h: lpb_peer_export / _import).  The
+        ring and the mappings belong to the process: the first sharded context exports the cudaIpc handle of its ring,
+        the handles are all-gathered and every rank maps the others (~0.4 s, once); later contexts of the same shape
+        just attach.  All ranks take the same decision: unless EVERY rank exported and imported successfully, the ring
+        is given up and the ncclBroadcast path stays.  LPB_PEER_PANELS=0 switches it off; a gloo (CPU) group has no
+        device memory to map."""
+        self.peer_panels = False
+        if self.world < 2 or self.world > 8 or self._dist.get_backend() != "nccl":
+            return
+        if os.environ.get("LPB_PEER_PANELS", "1") == "0":
+            return
+        import torch
+        buf = (C.c_ubyte * 64)()
+        state = C.c_int(-1)
+        exported = lib.lpb_peer_export(self.handle, buf, C.byref(state)) == _ffi.LPB_OK
+        if exported and state.value == 0:   # attached to what this process mapped before (same verdict on every rank:
+            self.peer_panels = True         # the ranks share the history of contexts)
+            return
+        if exported and state.value == 2:
+            return
+        mine = torch.zeros(65, dtype=torch.uint8)
+        if exported:
+            mine[0] = 1
+            mine[1:] = torch.tensor(list(buf), dtype=torch.uint8)
+        outs = [torch.zeros(65, dtype=torch.uint8, device="cuda") for _ in range(self.world)]
+        self._dist.all_gather(outs, mine.cuda())
+        outs = [o.cpu() for o in outs]
+        ok = all(int(o[0]) == 1 for o in outs)
+        if ok:
+            allh = (C.c_ubyte * (64 * self.world))(*[int(v) for o in outs for v in o[1:].tolist()])
+            ok = lib.lpb_peer_import(self.handle, allh, self.world) == _ffi.LPB_OK
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        self._dist.all_reduce(flag, op=self._dist.ReduceOp.MIN)
+        self.peer_panels = bool(int(flag.item()))
+        if not self.peer_panels:             # somebody failed: every rank gives the ring up
+            lib.lpb_set_option(self.handle, b"peer_panels", -1)
 
     def _broadcast_unique_id(self, lib):
         if self.world == 1 or lib.lpb_comm_ready(self.rank, self.world):
@@ -657,6 +697,7 @@ class SyntheticShardedProblem(ShardedProblem):
                                               world, uid, C.c_void_p(stream))
         _raise_for(rc)
         self.handle = h
+        self._map_peer_memory(lib)
 
     def download(self):
         """(A_local, b, c_local) as host arrays -- parity tests hand these to the CPU oracle."""

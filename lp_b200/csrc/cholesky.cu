@@ -16,6 +16,8 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstring>
+#include <mutex>
 #include <type_traits>
 
 #include "dist_schedule.hpp"
@@ -1802,6 +1804,199 @@ static int ensure_dist_streams(LaunchCtx& lc) {
   return LPB_OK;
 }
 
+// ------------------------------------------------------------------ peer-memory hand-off of the first 128 panel rows
+// The chain of the distributed factorisation runs  owner(k): potf2 -> TRSM -> [128 rows of block k + 1 to everybody]
+// -> owner(k + 1): one-tile update -> potf2 ...  Through ncclBroadcast the bracket costs ~30 us at 8 ranks (launch and
+// protocol latency for 128 KB); here the owner's stream runs peer_push_kernel, which writes the rows into every
+// peer's panel slot over NVLink (16-byte stores to cudaIpc-mapped memory), and the last CTA to finish raises a flag in
+// each peer's memory; the peers' streams run wait_flag_kernel.  No receive-side kernel, no staging buffer.
+// Flow control is by data dependency: the ring holds 2 x world slots, and the push of panel k + 2 world cannot start
+// before every rank has pushed a panel of its own in between -- which, in stream order, comes after all its reads of
+// panel k.  Consecutive factorisations are separated by a collective (k_potrf_dist2 starts with a 1-word all-reduce).
+constexpr int kPushCtasPerPeer = 4;
+constexpr int kRingHeaderDoubles = 128;  // 1 KB: flags (one u64 per slot) + the push kernel's CTA counter
+struct PeerPush {
+  double* dst[LaunchCtx::kMaxPeers - 1];
+  unsigned long long* flag[LaunchCtx::kMaxPeers - 1];
+  int n;
+};
+__global__ void __launch_bounds__(256)
+peer_push_kernel(const double* __restrict__ src, int64_t count2, PeerPush pp, unsigned long long value,
+                 unsigned* __restrict__ counter) {
+  const int peer = blockIdx.x / kPushCtasPerPeer, part = blockIdx.x % kPushCtasPerPeer;
+  const double2* s = reinterpret_cast<const double2*>(src);
+  double2* d = reinterpret_cast<double2*>(pp.dst[peer]);
+  for (int64_t e = part * 256 + threadIdx.x; e < count2; e += kPushCtasPerPeer * 256) d[e] = s[e];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(counter, 1u);
+    if (done == gridDim.x - 1) {  // every CTA's stores are fenced and counted: publish
+      *counter = 0;               // for the next launch (stream-ordered behind this one)
+      __threadfence_system();
+      for (int g = 0; g < pp.n; ++g)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pp.flag[g]), "l"(value) : "memory");
+    }
+  }
+}
+// One thread polls this rank's flag of the slot; a lost hand-off raises the context's fault word after ~10 s instead
+// of hanging (the host then reports LPB_ERR_CUDA at its next scalar fetch), and a fault raised elsewhere ends the wait.
+__global__ void wait_flag_kernel(const unsigned long long* __restrict__ flag, unsigned long long value,
+                                 unsigned long long* __restrict__ fault) {
+  if (threadIdx.x != 0) return;
+  unsigned long long t0, t1, v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= value) return;
+    __nanosleep(100);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 10000000000ull) {
+      if (fault) atomicExch(fault, 1ull);
+      return;
+    }
+    if (fault && *reinterpret_cast<volatile unsigned long long*>(fault) != 0ull) return;
+  }
+}
+
+static int64_t dist_slot_doubles(int64_t m) { return 3 * (int64_t)NB * NB + round_up(m, NB) * NB; }
+
+// The ring and its mappings belong to the PROCESS (one process per GPU), like the NCCL communicator: cudaMalloc +
+// cudaIpcOpenMemHandle + the handle exchange cost ~0.4 s, far too much for a context that lives for one solve
+// (InteriorPoint.solve on a sharded problem creates one per call).  A context attaches to the ring while it lives;
+// a second live context of the same process finds it busy and keeps the ncclBroadcast path.  The epoch of the flag
+// values is process-wide too: the flags in the ring outlive contexts.
+struct ProcessRing {
+  std::mutex mu;
+  double* base = nullptr;
+  int64_t slot_doubles = 0;
+  int slots = 0, world = 0, rank = -1;
+  double* peer[LaunchCtx::kMaxPeers] = {};
+  bool mapped = false;
+  const LaunchCtx* owner = nullptr;
+  uint32_t epoch = 0;
+};
+static ProcessRing g_ring;
+
+static void ring_free_locked() {
+  for (int g = 0; g < LaunchCtx::kMaxPeers; ++g) {
+    if (g_ring.peer[g] && g_ring.peer[g] != g_ring.base) cudaIpcCloseMemHandle(g_ring.peer[g]);
+    g_ring.peer[g] = nullptr;
+  }
+  if (g_ring.base) cudaFree(g_ring.base);
+  g_ring.base = nullptr;
+  g_ring.slots = 0;
+  g_ring.slot_doubles = 0;
+  g_ring.mapped = false;
+}
+
+static void ring_attach_locked(LaunchCtx& lc) {
+  lc.ring_base = g_ring.base;
+  lc.ring_slots = g_ring.slots;
+  lc.ring_slot_doubles = g_ring.slot_doubles;
+  for (int g = 0; g < LaunchCtx::kMaxPeers; ++g) lc.peer_base[g] = g_ring.peer[g];
+  lc.peer_mapped = g_ring.mapped;
+  lc.peer_ready = g_ring.mapped;
+  g_ring.owner = &lc;
+}
+
+void k_peer_release(LaunchCtx& lc) {
+  std::lock_guard<std::mutex> lk(g_ring.mu);
+  if (g_ring.owner == &lc) g_ring.owner = nullptr;
+  lc.ring_base = nullptr;
+  for (int g = 0; g < LaunchCtx::kMaxPeers; ++g) lc.peer_base[g] = nullptr;
+  lc.ring_slots = 0;
+  lc.ring_slot_doubles = 0;
+  lc.peer_mapped = false;
+  lc.peer_ready = false;
+}
+
+void k_peer_free_process() {
+  std::lock_guard<std::mutex> lk(g_ring.mu);
+  if (!g_ring.owner) ring_free_locked();
+}
+
+// *state_out: 0 = attached to the ring this process has already mapped (nothing to exchange); 1 = a new ring was
+// allocated, exchange the handles and call k_peer_import; 2 = another live context of this process holds the ring:
+// no peer hand-off for this one.  Ranks with the same history of contexts get the same answer.
+int k_peer_export(LaunchCtx& lc, int64_t m, unsigned char* handle_out, int* state_out) {
+  if (lc.world < 2 || lc.world > LaunchCtx::kMaxPeers || !handle_out || !state_out) {
+    set_last_error("peer_export: needs a sharded context of 2..%d ranks", LaunchCtx::kMaxPeers);
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  std::lock_guard<std::mutex> lk(g_ring.mu);
+  if (g_ring.owner && g_ring.owner != &lc) {
+    *state_out = 2;
+    return LPB_OK;
+  }
+  const int64_t per = dist_slot_doubles(m);
+  if (g_ring.base && g_ring.mapped && g_ring.world == lc.world && g_ring.rank == lc.rank && g_ring.slot_doubles >= per) {
+    ring_attach_locked(lc);
+    *state_out = 0;
+    return LPB_OK;
+  }
+  ring_free_locked();
+  const int slots = 2 * lc.world;
+  const size_t bytes = sizeof(double) * (size_t)(kRingHeaderDoubles + slots * per);
+  void* p = nullptr;
+  LPB_CUDA(cudaMalloc(&p, bytes));
+  LPB_CUDA(cudaMemsetAsync(p, 0, bytes, lc.stream));
+  LPB_CUDA(cudaStreamSynchronize(lc.stream));  // the peers may write as soon as they have the handle
+  g_ring.base = static_cast<double*>(p);
+  g_ring.slots = slots;
+  g_ring.slot_doubles = per;
+  g_ring.world = lc.world;
+  g_ring.rank = lc.rank;
+  g_ring.owner = &lc;
+  cudaIpcMemHandle_t h;
+  LPB_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle_out, &h, sizeof(h));
+  *state_out = 1;
+  return LPB_OK;
+}
+
+int k_peer_import(LaunchCtx& lc, const unsigned char* handles, int world) {
+  std::lock_guard<std::mutex> lk(g_ring.mu);
+  if (!g_ring.base || g_ring.owner != &lc || world != lc.world || !handles) {
+    set_last_error("peer_import: call peer_export first (world %d)", lc.world);
+    return LPB_ERR_BAD_ARGUMENT;
+  }
+  for (int g = 0; g < world; ++g) {
+    if (g == lc.rank) {
+      g_ring.peer[g] = g_ring.base;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)g, sizeof(h));
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_last_error("peer_import: cudaIpcOpenMemHandle of rank %d -> %s", g, cudaGetErrorString(e));
+      ring_free_locked();
+      g_ring.owner = nullptr;
+      return LPB_ERR_CUDA;
+    }
+    g_ring.peer[g] = static_cast<double*>(p);
+  }
+  g_ring.mapped = true;
+  ring_attach_locked(lc);
+  return LPB_OK;
+}
+
+// every rank decided to drop the ring (somebody failed to export or import)
+void k_peer_abandon(LaunchCtx& lc) {
+  {
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    if (g_ring.owner == &lc || !g_ring.owner) {
+      g_ring.owner = nullptr;
+      ring_free_locked();
+    }
+  }
+  k_peer_release(lc);
+}
+
 int k_potrf_dist_reserve(LaunchCtx& lc, int64_t m) {
   const int64_t slot = 3 * (int64_t)NB * NB + round_up(m, NB) * NB;
   if (lc.panel_slot_cap < slot) {
@@ -1893,16 +2088,34 @@ static int k_potrf_dist2(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm) {
   LPB_TRY(k_potrf_dist_reserve(lc, m));
   const int T = (int)ceil_div(m, NB);
   lc.linv_full = false;
+  // peer-memory hand-off of the first 128 rows of every panel (see peer_push_kernel): only if every rank mapped every
+  // other rank's ring and the ring's slots hold a panel of this m
+  const bool peer = lc.peer_ready && lc.ring_slots >= 2 * G && lc.ring_slot_doubles >= dist_slot_doubles(m);
+  if (peer) {
+    // no rank may push into a slot a slower rank still reads from the PREVIOUS factorisation: a 1-word all-reduce is
+    // stream-ordered behind every rank's earlier kernels (the normal iteration has collectives in between anyway)
+    {
+      std::lock_guard<std::mutex> lk(g_ring.mu);
+      lc.dist_epoch = ++g_ring.epoch;
+    }
+    unsigned long long* scratch = reinterpret_cast<unsigned long long*>(lc.ring_base) + 64;  // header word, unused otherwise
+    if (ncclAllReduce(scratch, scratch, 1, ncclUint64, ncclMax, comm, lc.stream) != ncclSuccess) {
+      set_last_error("potrf_dist2: barrier all-reduce failed");
+      return LPB_ERR_NCCL;
+    }
+  }
   struct Ops {
     LaunchCtx& lc;
     ncclComm_t comm;
     int64_t m, ldm;
     double* Mat;
     int G, me;
+    bool peer;
     cudaStream_t st(int side) const { return side ? lc.side_stream : lc.stream; }
     int nb(int k) const { return (int)((m - (int64_t)k * NB) < NB ? (m - (int64_t)k * NB) : NB); }
     double* linv(int k) const { return lc.chol_ws + (int64_t)k * NB * NB; }
-    double* slot(int k) const { return lc.panel_slot[k & 1]; }
+    int64_t slot_off(int k) const { return kRingHeaderDoubles + (int64_t)(k % lc.ring_slots) * lc.ring_slot_doubles; }
+    double* slot(int k) const { return peer ? lc.ring_base + slot_off(k) : lc.panel_slot[k & 1]; }
     int potf2(int k, int side) {
       const PackedPanel pp(m, k);
       potf2_inv_kernel<<<1, dim3(32, 16), kPotf2InvSmem, st(side)>>>(Mat, ldm, k * NB, nb(k), lc.info_dev, linv(k), 0,
@@ -1927,7 +2140,30 @@ static int k_potrf_dist2(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm) {
       }
       return LPB_OK;
     }
-    int bcast_small(int k, int owner) { return bcast(slot(k), PackedPanel(m, k).r1 * NB, owner, k, "block k+1"); }
+    int bcast_small(int k, int owner) {
+      const int64_t count = PackedPanel(m, k).r1 * NB;
+      if (!peer) return bcast(slot(k), count, owner, k, "block k+1");
+      if (count <= 0) return LPB_OK;
+      const unsigned long long value = ((unsigned long long)lc.dist_epoch << 32) | (unsigned)(k + 1);
+      const int fl = k % lc.ring_slots;
+      if (owner == me) {
+        PeerPush pp;
+        pp.n = 0;
+        for (int g = 0; g < G; ++g) {
+          if (g == me) continue;
+          pp.dst[pp.n] = lc.peer_base[g] + slot_off(k);
+          pp.flag[pp.n] = reinterpret_cast<unsigned long long*>(lc.peer_base[g]) + fl;
+          ++pp.n;
+        }
+        unsigned* counter = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned long long*>(lc.ring_base) + 96);
+        peer_push_kernel<<<kPushCtasPerPeer * pp.n, 256, 0, lc.stream>>>(slot(k), count / 2, pp, value, counter);
+      } else {
+        wait_flag_kernel<<<1, 32, 0, lc.stream>>>(reinterpret_cast<unsigned long long*>(lc.ring_base) + fl, value,
+                                                  lc.fault_dev);
+      }
+      LPB_KCHECK(lc);
+      return LPB_OK;
+    }
     int bcast_large(int k, int owner) {
       return bcast(slot(k) + (int64_t)NB * NB, PackedPanel(m, k).large_count, owner, k, "rest of the panel");
     }
@@ -1957,7 +2193,7 @@ static int k_potrf_dist2(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm) {
       LPB_KCHECK(lc);
       return LPB_OK;
     }
-  } ops{lc, comm, m, ldm, Mat, G, me};
+  } ops{lc, comm, m, ldm, Mat, G, me, peer};
   const int rc = potrf_dist_schedule2(T, G, me, ops);
   lc.launch_on_side = false;
   LPB_TRY(rc);

@@ -99,6 +99,18 @@ struct LaunchCtx {
   cudaEvent_t ev_dist[4] = {nullptr, nullptr, nullptr, nullptr};  // kEvSmall / kEvPotf2 of dist_schedule.hpp
   double* panel_slot[2] = {nullptr, nullptr};  // packed panels of the two-broadcast distributed factorisation
   int64_t panel_slot_cap = 0;      // doubles per slot
+  // Peer-memory panel hand-off (k_potrf_dist2, optional): ONE allocation per rank = [flags][ring of 2 x world panel
+  // slots], exported with cudaIpcGetMemHandle and mapped by every other rank of the box.  The owner of panel k writes
+  // the 128 rows the next owner needs straight into every peer's slot k % ring over NVLink and raises the peer's flag;
+  // see peer_push_kernel in cholesky.cu.
+  static constexpr int kMaxPeers = 8;
+  double* ring_base = nullptr;     // this rank's allocation (cudaMalloc)
+  int64_t ring_slot_doubles = 0;   // capacity of one slot
+  int ring_slots = 0;              // 2 x world
+  double* peer_base[kMaxPeers] = {};  // the same allocation of rank g, mapped here (own rank: ring_base)
+  bool peer_mapped = false;        // k_peer_import succeeded on this rank
+  bool peer_ready = false;         // ... and the hand-off is switched on (option "peer_panels"): bcast_small goes through peer memory
+  uint32_t dist_epoch = 0;         // factorisations done through k_potrf_dist2 (upper half of the flag values)
   int update_grid_cap = 0;         // > 0: CTAs of the trailing update (leaves SMs free for the side stream)
   int* info_dev = nullptr;         // potrf info flag
   int* info_host = nullptr;        // pinned

@@ -109,6 +109,13 @@ int k_trailing_update_simple(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm,
 int k_potrf(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int syrk_impl);
 // Allocate the panel buffers of the distributed factorisation for order m up front (column-sharded contexts).
 int k_potrf_dist_reserve(LaunchCtx& lc, int64_t m);
+// Peer-memory panel hand-off of the distributed factorisation: allocate this rank's ring and export its IPC handle
+// (64 bytes); map the other ranks' rings (handles = world x 64 bytes, in rank order); unmap / free.
+int k_peer_export(LaunchCtx& lc, int64_t m, unsigned char* handle_out, int* state_out);
+int k_peer_import(LaunchCtx& lc, const unsigned char* handles, int world);
+void k_peer_release(LaunchCtx& lc);       // detach this context (the ring stays with the process)
+void k_peer_abandon(LaunchCtx& lc);       // every rank agreed to give the ring up
+void k_peer_free_process();               // free the process ring if no context holds it
 // Solve L L^T X = B in place; B column-major m x nrhs.  use_linv: use the inverted diagonal blocks the
 // last k_potrf on this context left behind (L must be that factor); otherwise plain substitution.
 int k_potrs(LaunchCtx& lc, int64_t m, const double* L, int64_t ldm, double* B, int nrhs, bool use_linv);

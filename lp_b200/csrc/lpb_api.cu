@@ -740,6 +740,7 @@ void ctx_free(lpb_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   if (c->lc.chol_ws) cudaFree(c->lc.chol_ws);
   if (c->lc.panel_buf) cudaFree(c->lc.panel_buf);
+  k_peer_release(c->lc);
   for (int i = 0; i < 2; ++i)
     if (c->lc.panel_slot[i]) cudaFree(c->lc.panel_slot[i]);
   for (int e = 0; e < 4; ++e)
@@ -938,7 +939,18 @@ int lpb_comm_finalize(void) {
   }
   if (g_comm.comm) ncclCommDestroy(g_comm.comm);
   g_comm = ProcessComm();
+  k_peer_free_process();  // the panel ring and the mappings of the other ranks' rings go with the communicator
   return LPB_OK;
+}
+
+int lpb_peer_export(lpb_ctx* c, void* handle64_out, int* state_out) {
+  if (!c || !handle64_out || !state_out) return LPB_ERR_BAD_ARGUMENT;
+  return k_peer_export(c->lc, c->m, static_cast<unsigned char*>(handle64_out), state_out);
+}
+
+int lpb_peer_import(lpb_ctx* c, const void* handles, int world) {
+  if (!c || !handles) return LPB_ERR_BAD_ARGUMENT;
+  return k_peer_import(c->lc, static_cast<const unsigned char*>(handles), world);
 }
 
 int lpb_comm_ready(int rank, int world) { return g_comm.comm && g_comm.rank == rank && g_comm.world == world ? 1 : 0; }
@@ -1374,6 +1386,15 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
   }
   if (k == "syrk_chain") {  // 1: K1 without blocked accumulation (the round-1 summation order)
     c->lc.syrk_chain = value != 0;
+    return LPB_OK;
+  }
+  if (k == "peer_panels") {  // 0: ncclBroadcast for the first rows of every panel; 1: peer memory (only if mapped);
+                             // -1: every rank agreed to give the ring up (a failed export / import somewhere)
+    if (value > 0 && !c->lc.peer_mapped) return LPB_ERR_BAD_ARGUMENT;
+    if (value < 0)
+      k_peer_abandon(c->lc);
+    else
+      c->lc.peer_ready = value != 0;
     return LPB_OK;
   }
   if (k == "syrk_flush_blocks") {  // K1: K-blocks between two flushes of the accumulators into C (power of two >= 32)

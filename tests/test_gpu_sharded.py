@@ -95,9 +95,13 @@ def _worker(rank, world, port, q):
         pb = lp_b200.Problem.target(c).ub(A_ub, b_ub).eq(A_eq, b_eq).build()
         ldm = (m + 15) // 16 * 16
         big = {}
-        for mode in (2, 1, 0):
+        for mode in (2, "nccl", 1, 0):   # 2: first panel rows through peer memory (cudaIpc) | "nccl": through ncclBroadcast
             with ShardedProblem(pb, rank, world, dist) as sp:
-                sp.set_option("potrf_dist", mode)
+                if mode == 2:
+                    assert sp.peer_panels, "the peers' panel rings were not mapped: " + _ffi.last_error()
+                if mode == "nccl":
+                    sp.set_option("peer_panels", 0)
+                sp.set_option("potrf_dist", 2 if mode == "nccl" else mode)
                 sp.set_option("check_replicas", 1)
                 assert lib.lpb_blind_start(sp.handle) == 0
                 assert lib.lpb_form_and_factor(sp.handle) == 0, _ffi.last_error()
@@ -147,7 +151,7 @@ def test_two_gpu_column_sharded_solve_matches_oracle_and_one_gpu():
     # the same order of updates as the replicated run -> identical bits across ranks AND across the two modes
     ref = o.InteriorPoint().solve(o.build_problem(*o.synthetic_lp(*BIG)))
     for rank in (0, 1):
-        for mode in (2, 1, 0):
+        for mode in (2, "nccl", 1, 0):
             L, x, fun, it = results[rank]["big"][mode]
             np.testing.assert_array_equal(L, results[0]["big"][0][0])
             assert abs(it - ref.iteration) <= 1
