@@ -651,8 +651,10 @@ def main():
     if world > 1:
         rp = ShardedProblem(problem, rank, world, dist, stream=stream)
         rp.set_option("potrf_dist", args.potrf_dist)
+        peer_panels = bool(rp.peer_panels)
     else:
         rp = ResidentProblem(problem, stream=stream)
+        peer_panels = False
     for kv in filter(None, os.environ.get("LPB_BENCH_OPTS", "").split(",")):  # experiments: "key=value,key=value"
         k, v = kv.split("=")
         rp.set_option(k, int(v))
@@ -756,7 +758,8 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": bench_config(args.workload, m, n, args.seed, world, args.potrf_dist),
             "details": {"iterations_per_solve": total_iters / args.steps, "objective": fun, "host_generation_s": gen_s,
-                        "step": "one complete solve (blind start -> Optimal)"},
+                        "step": "one complete solve (blind start -> Optimal)",
+                        "peer_panels": peer_panels},  # first panel rows handed over through cudaIpc-mapped peer memory
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "phases_ms_per_solve": phases, "cpu_baseline": cpu, "c5": c5,
         }
