@@ -141,41 +141,58 @@ struct SmemDev {
   __device__ int form_and_factor() {  // newton_equations.rs:48-64
     for (int j = threadIdx.x; j < n; j += kBT) dinv[j] = x[j] / z[j];
     __syncthreads();
-    {  // M = A diag(dinv) A^T : 4x4 strided register tile per thread (rows ty+16i, cols tx+16j)
-      const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-      double acc[4][4];
+    {  // lower(M) = A diag(dinv) A^T on the FP64 tensor path (mma.m8n8k4.f64), 8 x 8 tiles of the lower triangle dealt
+       // round-robin to the warps.  The DFMA version it replaces (4 x 4 register tile per thread, the full square)
+       // was bound by shared-memory bandwidth: 8 loads per 16 FMAs and thread, 22 % of the kernel's samples
+       // (profiles/ncu_batched_C4_r02.txt); a fragment load feeds 8 x as many FMAs, and the upper triangle -- never
+       // read -- is no longer formed.  A warp keeps up to kTilesPerWarp accumulator pairs in flight so that the
+       // DMMAs of one K-step are independent.  The pitch of A (batched_lda: = 4 mod 16) makes the fragment loads --
+       // lane (g, t) reads A[row0 + g][k0 + t] -- bank-conflict free.  Rows >= m of the last tile row read whatever
+       // follows A in shared memory (possibly NaN patterns): they only reach entries that are not stored.
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const int g = lane >> 2, t = lane & 3;
+      const int nt = (m + 7) >> 3, ntiles = nt * (nt + 1) / 2;
+      constexpr int kTilesPerWarp = (kMaxM / 8) * (kMaxM / 8 + 1) / 2 / kBWarps + 1;  // 36 tiles / 8 warps -> 5
+      const double* ap[kTilesPerWarp];
+      const double* bp[kTilesPerWarp];
+      int trow[kTilesPerWarp], tcol[kTilesPerWarp];
+      double c0[kTilesPerWarp], c1[kTilesPerWarp];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-      const double* ar[4];
-      const double* br[4];
-      bool av[4], bv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        av[i] = ty + 16 * i < m;
-        bv[i] = tx + 16 * i < m;
-        ar[i] = A + (av[i] ? ty + 16 * i : 0) * lda;
-        br[i] = A + (bv[i] ? tx + 16 * i : 0) * lda;
+      for (int q = 0; q < kTilesPerWarp; ++q) {
+        int tile = warp + q * kBWarps;
+        const bool live = tile < ntiles;
+        if (!live) tile = 0;
+        int bi = 0;
+        while ((bi + 1) * (bi + 2) / 2 <= tile) ++bi;
+        const int bj = tile - bi * (bi + 1) / 2;
+        ap[q] = A + (bi * 8 + g) * lda + t;
+        bp[q] = A + (bj * 8 + g) * lda + t;
+        trow[q] = live ? bi * 8 + g : m;  // m: nothing is stored
+        tcol[q] = bj * 8 + 2 * t;
+        c0[q] = c1[q] = 0.0;
       }
-      for (int k = 0; k < n; ++k) {
-        const double d = dinv[k];
-        double a[4], bb[4];
+      // No per-lane select may feed the mma: ptxas if-converts `kin ? mma(a, b) : mma(0, 0)` into two DMMAs predicated
+      // per LANE, each behind a predicated WARPSYNC.ALL -- a deadlock as soon as n is not a multiple of 4 (found the
+      // hard way).  Instead the padding columns n .. lda-1 of A are zero (written at load) and the index of dinv is
+      // clamped, so the K tail contributes exact zeros.
+      for (int k0 = 0; k0 < n; k0 += 4) {
+        const double dk = dinv[min(k0 + t, n - 1)];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          a[i] = ar[i][k];
-          bb[i] = br[i][k] * d;
+        for (int q = 0; q < kTilesPerWarp; ++q) {
+          const double a = ap[q][k0];
+          const double bv = bp[q][k0] * dk;
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                       : "+d"(c0[q]), "+d"(c1[q])
+                       : "d"(a), "d"(bv));
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * bb[j];
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (av[i] && bv[j]) M[(ty + 16 * i) * ldm + tx + 16 * j] = acc[i][j];
+      for (int q = 0; q < kTilesPerWarp; ++q) {
+        if (trow[q] < m) {
+          if (tcol[q] < m) M[trow[q] * ldm + tcol[q]] = c0[q];
+          if (tcol[q] + 1 < m) M[trow[q] * ldm + tcol[q] + 1] = c1[q];
+        }
+      }
     }
     __syncthreads();
     // In-place lower Cholesky, blocked by 16 columns like potf2_inv_kernel (cholesky.cu): per block ONE warp
@@ -426,9 +443,12 @@ struct SmemDev {
 };
 
 __host__ __device__ inline int batched_mp(int m) { return (m + kSB - 1) / kSB * kSB; }
+// pitch of A in shared memory: = 4 (mod 16) doubles, so that the 8 x 4 DMMA fragment loads of the in-CTA SYRK (row g,
+// column t of a tile: 8 (g) + 2 (t) words apart) fall into 32 different banks per half-warp
+__host__ __device__ inline int batched_lda(int n) { return (n + 15) / 16 * 16 + 4; }
 __host__ __device__ inline size_t batched_smem_doubles(int m, int n) {
   const size_t mp = (size_t)batched_mp(m);
-  return (size_t)m * (n + 1) + mp * (mp + 1) + 10 * (size_t)n + 5 * (size_t)m + 2 * mp + 2 * kMaxM + 8 * kBWarps +
+  return (size_t)m * batched_lda(n) + mp * (mp + 1) + 10 * (size_t)n + 5 * (size_t)m + 2 * mp + 2 * kMaxM + 8 * kBWarps +
          (mp / kSB) * kSB * kXP + panel_factor_scratch(kXP) + 2;
 }
 
@@ -441,7 +461,7 @@ batched_ipm_kernel(int64_t batch, int m, int n, const double* __restrict__ gA, c
     SmemDev d;
     d.m = m;
     d.n = n;
-    d.lda = n + 1;
+    d.lda = batched_lda(n);
     d.mp = batched_mp(m);
     d.nsb = d.mp / kSB;
     d.ldm = d.mp + 1;
@@ -472,6 +492,10 @@ batched_ipm_kernel(int64_t batch, int m, int n, const double* __restrict__ gA, c
     for (int idx = threadIdx.x; idx < m * n; idx += kBT) {
       const int i = idx / n, j = idx - i * n;
       d.A[i * d.lda + j] = A[idx];
+    }
+    for (int idx = threadIdx.x; idx < m * (d.lda - n); idx += kBT) {  // zero padding columns: the K tail of the DMMA SYRK
+      const int i = idx / (d.lda - n), j = n + idx - i * (d.lda - n);
+      d.A[i * d.lda + j] = 0.0;
     }
     for (int idx = threadIdx.x; idx < d.mp * d.mp; idx += kBT) {  // identity padding of M beyond m (kept by the factorisation)
       const int r = idx / d.mp, cc = idx - r * d.mp;
