@@ -61,39 +61,81 @@ struct SmemDev {
   int have_pq, nan_pq;
   double cp, bq;
 
-  // t_k[i] = sum_j A[i][j] * (w_k[j] * (scale ? dinv[j] : 1)); warp per row
+  // t_k[i] = sum_j A[i][j] * (w_k[j] * (scale ? dinv[j] : 1)).  A warp owns the rows warp, warp + 8, ... (8 of them at
+  // m = 64) and sums them TOGETHER: 8 accumulators per lane over its columns, then a transposing butterfly -- at offset
+  // 16 / 8 / 4 each lane keeps half of its rows and adds the partner's partial sums of those, after which lane l holds
+  // row (l >> 2) summed over the lanes with its bits 4..2, and two more exchanges finish it: 9 shuffled doubles per
+  // warp and right-hand side instead of 8 rows x 5 (one full warp reduction per row was a chain of 40 dependent
+  // shuffles; the three sweeps of an iteration were ~20 % of the kernel's samples, profiles/ncu_batched_C4_r02.txt).
   template <int NRHS, bool SCALE>
   __device__ __forceinline__ void rows_dot(const double* w0, const double* w1, double* o0, double* o1) const {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = warp; i < m; i += kBWarps) {
-      const double* ar = A + i * lda;
-      double s0 = 0.0, s1 = 0.0;
-      for (int j = lane; j < n; j += 32) {
-        const double a = ar[j];
-        const double d = SCALE ? dinv[j] : 1.0;
-        s0 += a * (SCALE ? d * w0[j] : w0[j]);
-        if (NRHS == 2) s1 += a * (SCALE ? d * w1[j] : w1[j]);
+    const unsigned full = 0xffffffffu;
+    constexpr int R = kMaxM / kBWarps;  // 8 rows per warp
+    double s0[R], s1[R];
+    const double* ar[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      s0[r] = s1[r] = 0.0;
+      const int row = warp + kBWarps * r;
+      ar[r] = A + (row < m ? row : 0) * lda;  // rows >= m: a valid row, result dropped
+    }
+    for (int j = lane; j < n; j += 32) {
+      const double d = SCALE ? dinv[j] : 1.0;
+      const double x0 = SCALE ? d * w0[j] : w0[j];
+      const double x1 = NRHS == 2 ? (SCALE ? d * w1[j] : w1[j]) : 0.0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double a = ar[r][j];
+        s0[r] += a * x0;
+        if (NRHS == 2) s1[r] += a * x1;
       }
-      s0 = bw_sum(s0);
-      if (NRHS == 2) s1 = bw_sum(s1);
-      if (lane == 0) {
-        o0[i] = s0;
-        if (NRHS == 2) o1[i] = s1;
+    }
+    auto fold = [&](double (&s)[R]) {
+#pragma unroll
+      for (int half = R / 2, off = 16; half >= 1; half >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int r = 0; r < half; ++r) {
+          const double send = up ? s[r] : s[r + half];
+          const double keep = up ? s[r + half] : s[r];
+          s[r] = keep + __shfl_xor_sync(full, send, off);
+        }
       }
+      s[0] += __shfl_xor_sync(full, s[0], 2);
+      s[0] += __shfl_xor_sync(full, s[0], 1);
+    };
+    fold(s0);
+    if (NRHS == 2) fold(s1);
+    const int row = warp + kBWarps * (lane >> 2);
+    if ((lane & 3) == 0 && row < m) {
+      o0[row] = s0[0];
+      if (NRHS == 2) o1[row] = s1[0];
     }
   }
 
-  // s_k[j] = sum_i A[i][j] v_k[i]; thread per column
+  // s_k[j] = sum_i A[i][j] v_k[i]; thread per column, four interleaved partial sums (one chain of m dependent FMAs at
+  // ~20 cycles each was the cost of this pass, not its loads)
   template <int NRHS>
   __device__ __forceinline__ void col_dot(int j, const double* v0, const double* v1, double* s0, double* s1) const {
-    double a0 = 0.0, a1 = 0.0;
-    for (int i = 0; i < m; ++i) {
-      const double a = A[i * lda + j];
-      a0 += a * v0[i];
-      if (NRHS == 2) a1 += a * v1[i];
+    double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+    const double* col = A + j;
+    int i = 0;
+    for (; i + 3 < m; i += 4) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double a = col[(i + e) * lda];
+        a0[e] += a * v0[i + e];
+        if (NRHS == 2) a1[e] += a * v1[i + e];
+      }
     }
-    *s0 = a0;
-    if (NRHS == 2) *s1 = a1;
+    for (; i < m; ++i) {
+      const double a = col[i * lda];
+      a0[0] += a * v0[i];
+      if (NRHS == 2) a1[0] += a * v1[i];
+    }
+    *s0 = (a0[0] + a0[1]) + (a0[2] + a0[3]);
+    if (NRHS == 2) *s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
   }
 
   __device__ int blind_start() {  // feasible_point.rs:24-39
