@@ -46,6 +46,32 @@ def test_syrk_adat_matches_numpy(m, n, impl, scaled):
     assert err.max() < 1e-12
 
 
+@pytest.mark.parametrize("period", [32, 64, 128, 1024])
+@pytest.mark.parametrize("m,n", [(129, 4130), (300, 2049), (64, 513)])
+def test_syrk_every_flush_period_gives_the_same_matrix_up_to_rounding(m, n, period):
+    """Option "syrk_flush_blocks": the period of K1's blocked accumulation (K-blocks of 16 columns; a power of two
+    >= 32; longer than the K extent = never).  Shapes put the first / second flush of every row group, the ragged last
+    K-block and the half-period offset of the second four warps on and next to a boundary."""
+    import torch
+    rng = np.random.default_rng(m + n + period)
+    A = rng.standard_normal((m, n))
+    d = np.exp(rng.uniform(-3, 3, n))
+    Ap, lda = pad_cols(A)
+    dA, dd = to_dev(Ap), to_dev(d)
+    dM = torch.full((m, m + (m & 1)), float("nan"), dtype=torch.float64, device="cuda")
+    with BareCtx(m, n) as ctx:
+        ctx.set("syrk_flush_blocks", period)
+        assert ctx.lib.lpb_set_option(ctx.h, b"syrk_flush_blocks", 48) != 0       # not a power of two
+        assert ctx.lib.lpb_set_option(ctx.h, b"syrk_flush_blocks", 16) != 0       # too short
+        ok(ctx.lib.lpb_k_syrk_adat(ctx.h, m, n, dA.data_ptr(), lda, dd.data_ptr(), dM.data_ptr(), m + (m & 1)))
+    M = dM.cpu().numpy()[:, :m]
+    ref = (A * d) @ A.T
+    scale = (np.abs(A) * d) @ np.abs(A).T
+    low = np.tril_indices(m)
+    assert np.isfinite(M[low]).all()
+    assert (np.abs(M[low] - ref[low]) / scale[low]).max() < 1e-13
+
+
 def test_syrk_blocked_accumulation_keeps_long_same_sign_sums_to_a_few_ulp():
     """The diagonal of M = A D A^T is a sum of n same-sign terms.  One register chain of n / 4 DMMA steps rounds
     relative to the growing partial sum (measured 26 ulp rms at n = 24576: option "syrk_chain" = 1, the round-1

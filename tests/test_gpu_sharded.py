@@ -60,6 +60,28 @@ def test_device_synthetic_generator_world1_matches_oracle():
     assert abs(res.fun() - ref.fun) <= 1e-8 * max(1.0, abs(ref.fun))
 
 
+def test_peer_memory_entry_points_refuse_unsharded_contexts():
+    """lpb_peer_export / lpb_peer_import (the cudaIpc panel ring of the distributed factorisation) only make sense on
+    a context of 2..8 ranks: a world-1 context gets LPB_ERR_BAD_ARGUMENT, keeps working, and "peer_panels" = 1 is
+    refused while nothing is mapped."""
+    import ctypes as C
+    import lp_b200
+    from lp_b200 import _ffi
+    from lp_b200.api import SyntheticShardedProblem
+    lib = _ffi.load()
+    m, n, seed = SYN
+    with SyntheticShardedProblem(m, n, seed) as sp:
+        assert sp.peer_panels is False
+        buf = (C.c_ubyte * 64)()
+        state = C.c_int(-1)
+        assert lib.lpb_peer_export(sp.handle, buf, C.byref(state)) == _ffi.LPB_ERR_BAD_ARGUMENT
+        assert lib.lpb_peer_import(sp.handle, (C.c_ubyte * 64)(), 1) == _ffi.LPB_ERR_BAD_ARGUMENT
+        assert lib.lpb_set_option(sp.handle, b"peer_panels", 1) == _ffi.LPB_ERR_BAD_ARGUMENT
+        assert lib.lpb_set_option(sp.handle, b"peer_panels", 0) == _ffi.LPB_OK
+        res = lp_b200.InteriorPoint.default().solve_resident(sp)
+        assert res.iteration() > 0
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
