@@ -13,10 +13,11 @@
 using lpb::OwnedCols;
 
 static int fails = 0;
+static bool quiet = false;  // the expected failures of a negative control are counted, not printed
 #define CHECK(cond, ...)                 \
   do {                                   \
     if (!(cond)) {                       \
-      if (fails < 20) {                  \
+      if (fails < 20 && !quiet) {        \
         std::printf("FAIL %s: ", #cond); \
         std::printf(__VA_ARGS__);        \
         std::printf("\n");               \
@@ -303,6 +304,161 @@ static void test_schedule2(int T, int G, int side_first) {
     }
 }
 
+// ---- schedule v2 with the PEER-MEMORY hand-off of the small part (cholesky.cu: peer_push_kernel / wait_flag_kernel):
+// the owner of panel k writes the rows of block k + 1 into every other rank's slot k % ring the moment its own main
+// stream gets there -- one-sided, NOT ordered with anything on the receiver -- and the receivers' bcast_small is a wait
+// for that flag.  The large part is modelled as an EAGER broadcast: the root never blocks, a receiver completes when
+// it reaches the op and the root has issued it (the loosest behaviour NCCL may show).  Ranks and streams advance in a
+// random interleaving (many seeds).  A slot that is overwritten while its rank still has a read of the old panel
+// ahead shows up as a stale read in `need`.  Returns the number of failed checks it produced.
+static int test_schedule2_peer(int T, int G, int ring, unsigned seed) {
+  const int fails_before = fails;
+  std::vector<Recorder2> rec(G);
+  for (int r = 0; r < G; ++r) lpb::potrf_dist_schedule2(T, G, r, rec[r]);
+  std::vector<std::vector<std::vector<int>>> ver(G, std::vector<std::vector<int>>(T, std::vector<int>(T, 0)));
+  std::vector<std::vector<char>> inM(G, std::vector<char>(T, 0)), diag(G, std::vector<char>(T, 0));
+  std::vector<std::vector<Slot>> buf(G, std::vector<Slot>(ring));
+  std::vector<char> pushed(T, 0), large_issued(T, 0);
+  std::vector<std::vector<std::vector<int>>> q(G, std::vector<std::vector<int>>(2));
+  std::vector<std::vector<int>> dep(G);
+  std::vector<std::vector<char>> done(G);
+  std::vector<std::vector<size_t>> head(G, std::vector<size_t>(2, 0));
+  for (int r = 0; r < G; ++r) {
+    const auto& ops = rec[r].ops;
+    dep[r].assign(ops.size(), -1);
+    done[r].assign(ops.size(), 0);
+    int last_rec[lpb::kNumDistEvents];
+    for (int& v : last_rec) v = -1;
+    for (size_t i = 0; i < ops.size(); ++i) {
+      q[r][ops[i].side].push_back((int)i);
+      if (ops[i].kind == P2_RECORD) last_rec[ops[i].a] = (int)i;
+      if (ops[i].kind == P2_WAIT) dep[r][i] = last_rec[ops[i].a];
+    }
+  }
+  auto slot = [&](int r, int k) -> Slot& { return buf[r][k % ring]; };
+  auto need = [&](int r, int p, bool small_, bool large, const char* what) {
+    const Slot& s = slot(r, p);
+    CHECK(s.panel == p && (!small_ || s.small_) && (!large || s.large),
+          "peer: rank %d %s reads panel %d from a slot holding panel %d (small %d large %d) (T=%d G=%d ring=%d seed=%u)", r,
+          what, p, s.panel, (int)s.small_, (int)s.large, T, G, ring, seed);
+  };
+  auto bump = [&](int r, int i, int j, int p) {
+    CHECK(ver[r][i][j] == p, "peer: rank %d tile (%d,%d): panel %d applied out of order (seen %d)", r, i, j, p, ver[r][i][j]);
+    ver[r][i][j]++;
+  };
+  // try to execute the op at the head of (rank r, stream st); false = blocked
+  auto step = [&](int r, int st) -> bool {
+    if (head[r][st] >= q[r][st].size()) return false;
+    const int idx = q[r][st][head[r][st]];
+    const Op2 op = rec[r].ops[idx];
+    switch (op.kind) {
+      case P2_WAIT:
+        if (dep[r][idx] >= 0 && !done[r][dep[r][idx]]) return false;
+        break;
+      case P2_BSMALL:
+        if (op.b == r) {  // the owner pushes: one-sided writes into every peer's slot, whatever the peer is doing
+          const Slot& src = slot(r, op.a);
+          CHECK(src.panel == op.a && src.small_ && src.lkk, "peer: panel %d pushed before its owner finished it", op.a);
+          for (int g = 0; g < G; ++g)
+            if (g != r) {
+              Slot& d = slot(g, op.a);
+              d = Slot();
+              d.panel = op.a;
+              d.small_ = true;
+            }
+          pushed[op.a] = 1;
+        } else if (!pushed[op.a]) {
+          return false;  // wait_flag_kernel
+        }
+        break;
+      case P2_BLARGE:
+        if (op.b == r) {
+          large_issued[op.a] = 1;
+        } else {
+          if (!large_issued[op.a]) return false;
+          Slot& d = slot(r, op.a);  // the receive is ordered on the receiver's stream
+          if (d.panel != op.a) {
+            d = Slot();
+            d.panel = op.a;
+          }
+          d.large = d.lkk = true;
+        }
+        break;
+      case P2_POTF2: {
+        CHECK(op.a % G == r, "peer: rank %d factors panel %d", r, op.a);
+        CHECK(ver[r][op.a][op.a] == op.a, "peer: potf2(%d) on a diagonal tile with %d updates", op.a, ver[r][op.a][op.a]);
+        diag[r][op.a] = 1;
+        Slot& s = slot(r, op.a);
+        s = Slot();
+        s.panel = op.a;
+        s.lkk = true;
+        break;
+      }
+      case P2_TRSM: {
+        CHECK(diag[r][op.a], "peer: trsm(%d) before potf2", op.a);
+        for (int i = op.a + 1; i < T; ++i)
+          CHECK(ver[r][i][op.a] == op.a, "peer: trsm(%d): tile (%d,%d) has %d updates", op.a, i, op.a, ver[r][i][op.a]);
+        Slot& s = slot(r, op.a);
+        CHECK(s.panel == op.a && s.lkk, "peer: trsm(%d) packs into a slot holding panel %d", op.a, s.panel);
+        s.small_ = s.large = true;
+        inM[r][op.a] = 1;
+        break;
+      }
+      case P2_UDIAG: need(r, op.a, true, false, "update_diag"); bump(r, op.b, op.b, op.a); break;
+      case P2_UBELOW:
+        need(r, op.a, true, true, "update_col_below");
+        for (int i = op.b + 1; i < T; ++i) bump(r, i, op.b, op.a);
+        break;
+      case P2_UOWNED:
+        if (op.b < T) need(r, op.a, true, true, "update_owned");
+        for (int j = op.b; j < T; ++j)
+          if (j % G == r)
+            for (int i = j; i < T; ++i) bump(r, i, j, op.a);
+        break;
+      case P2_UNPACK:
+        need(r, op.a, op.a + 1 < T, true, "unpack");
+        CHECK(slot(r, op.a).lkk, "peer: unpack(%d) without the diagonal block", op.a);
+        inM[r][op.a] = 1;
+        break;
+      default: break;
+    }
+    done[r][idx] = 1;
+    head[r][st]++;
+    return true;
+  };
+  unsigned rng = seed * 2654435761u + 12345u;
+  auto next = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
+  for (;;) {
+    bool finished = true;
+    for (int r = 0; r < G; ++r)
+      for (int st = 0; st < 2; ++st)
+        if (head[r][st] < q[r][st].size()) finished = false;
+    if (finished) break;
+    // a random rank / stream runs a random burst; if the pick is blocked, sweep everything once to detect deadlock
+    const int r = (int)(next() % (unsigned)G), st = (int)(next() % 2u);
+    int burst = 1 + (int)(next() % 12u);
+    bool progress = false;
+    while (burst-- > 0 && step(r, st)) progress = true;
+    if (!progress) {
+      for (int rr = 0; rr < G && !progress; ++rr)
+        for (int s2 = 0; s2 < 2 && !progress; ++s2) progress = step(rr, s2);
+      if (!progress) {
+        CHECK(false, "peer: deadlock (T=%d G=%d ring=%d seed=%u)", T, G, ring, seed);
+        break;
+      }
+    }
+    if (fails - fails_before > 50) break;
+  }
+  if (fails == fails_before)
+    for (int r = 0; r < G; ++r)
+      for (int k = 0; k < T; ++k) {
+        CHECK(inM[r][k], "peer: rank %d never stored panel %d (T=%d G=%d)", r, k, T, G);
+        if (k % G == r)
+          for (int i = k; i < T; ++i) CHECK(ver[r][i][k] == k, "peer: owned tile (%d,%d) saw %d panels", i, k, ver[r][i][k]);
+      }
+  return fails - fails_before;
+}
+
 int main() {
   test_decode();
   for (int G : {2, 3, 4, 8})
@@ -311,6 +467,25 @@ int main() {
       test_schedule2(T, G, 0);
       test_schedule2(T, G, 1);
     }
+  // peer-memory hand-off: a ring of 2 G slots is safe under every interleaving tried; two slots (what the stream-ordered
+  // ncclBroadcast path gets away with) are NOT once the small part arrives one-sided -- the control shows the
+  // simulation can see the hazard at all
+  for (int G : {2, 3, 4, 8})
+    for (int T : {3, 4, 7, 9, 16, 17, 33, 40})
+      for (unsigned seed = 0; seed < 40; ++seed) test_schedule2_peer(T, G, 2 * G, seed);
+  {
+    const int before = fails;
+    int seen = 0;
+    quiet = true;
+    for (int G : {2, 4, 8})
+      for (unsigned seed = 0; seed < 40; ++seed) seen += test_schedule2_peer(33, G, 2, seed);
+    quiet = false;
+    fails = before;  // expected failures of the control do not count
+    if (seen == 0) {
+      std::printf("FAIL: the two-slot control of the peer hand-off never produced a stale read\n");
+      ++fails;
+    }
+  }
   if (fails) {
     std::printf("%d check(s) failed\n", fails);
     return 1;

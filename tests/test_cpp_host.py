@@ -46,7 +46,10 @@ def test_cpp_host_mirror_reference_known_answers_on_gpu():
 
 def test_distributed_cholesky_schedule_and_tile_lists():
     """lp_b200/csrc/dist_schedule.hpp on the CPU for world sizes 2, 3, 4, 8 (tests/cpp/test_dist_schedule.cpp):
-    the owned-column tile decode and the per-rank operation order of the panel-broadcast factorisation."""
+    the owned-column tile decode and the per-rank operation order of the panel-broadcast factorisation -- and, for the
+    peer-memory hand-off of the first panel rows (one-sided writes into the peers' slot rings, eager large broadcast),
+    1280 random interleavings of ranks and streams per world size: no stale read with a ring of 2 x world slots, and a
+    two-slot control that must (and does) produce them."""
     src = os.path.join(HERE, "cpp", "test_dist_schedule.cpp")
     out = os.path.join(HERE, "cpp", "_build", "test_dist_schedule")
     os.makedirs(os.path.dirname(out), exist_ok=True)
