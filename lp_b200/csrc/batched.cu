@@ -53,6 +53,7 @@ __device__ __forceinline__ void block_allreduce(double (&v)[NV], const bool is_m
 
 struct SmemDev {
   int m, n, lda, ldm;
+  int nd, ns;  // A holds the nd = n - ns leading columns; the ns trailing ones are the implicit identity block e_0 .. e_{ns-1}
   int mp, nsb;           // m rounded up to a multiple of 16 (rows >= m of M are identity padding), mp / 16
   double *Xinv, *cbuf;   // nsb x 16 x kXP inverted diagonal sub-blocks of L; scratch of factor_sub16 (panel_factor.cuh)
   int* flag;             // bad-pivot flag of the factorisation (shared)
@@ -80,7 +81,7 @@ struct SmemDev {
       const int row = warp + kBWarps * r;
       ar[r] = A + (row < m ? row : 0) * lda;  // rows >= m: a valid row, result dropped
     }
-    for (int j = lane; j < n; j += 32) {
+    for (int j = lane; j < nd; j += 32) {
       const double d = SCALE ? dinv[j] : 1.0;
       const double x0 = SCALE ? d * w0[j] : w0[j];
       const double x1 = NRHS == 2 ? (SCALE ? d * w1[j] : w1[j]) : 0.0;
@@ -109,6 +110,12 @@ struct SmemDev {
     if (NRHS == 2) fold(s1);
     const int row = warp + kBWarps * (lane >> 2);
     if ((lane & 3) == 0 && row < m) {
+      if (row < ns) {  // the implicit slack column nd + row is e_row
+        const int j = nd + row;
+        const double d = SCALE ? dinv[j] : 1.0;
+        s0[0] += SCALE ? d * w0[j] : w0[j];
+        if (NRHS == 2) s1[0] += SCALE ? d * w1[j] : w1[j];
+      }
       o0[row] = s0[0];
       if (NRHS == 2) o1[row] = s1[0];
     }
@@ -118,6 +125,11 @@ struct SmemDev {
   // ~20 cycles each was the cost of this pass, not its loads)
   template <int NRHS>
   __device__ __forceinline__ void col_dot(int j, const double* v0, const double* v1, double* s0, double* s1) const {
+    if (j >= nd) {  // implicit slack column e_{j - nd}
+      *s0 = v0[j - nd];
+      if (NRHS == 2) *s1 = v1[j - nd];
+      return;
+    }
     double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
     const double* col = A + j;
     int i = 0;
@@ -215,10 +227,10 @@ struct SmemDev {
       }
       // No per-lane select may feed the mma: ptxas if-converts `kin ? mma(a, b) : mma(0, 0)` into two DMMAs predicated
       // per LANE, each behind a predicated WARPSYNC.ALL -- a deadlock as soon as n is not a multiple of 4 (found the
-      // hard way).  Instead the padding columns n .. lda-1 of A are zero (written at load) and the index of dinv is
+      // hard way).  Instead the padding columns nd .. lda-1 of A are zero (written at load) and the index of dinv is
       // clamped, so the K tail contributes exact zeros.
-      for (int k0 = 0; k0 < n; k0 += 4) {
-        const double dk = dinv[min(k0 + t, n - 1)];
+      for (int k0 = 0; k0 < nd; k0 += 4) {
+        const double dk = dinv[min(k0 + t, nd - 1)];
 #pragma unroll
         for (int q = 0; q < kTilesPerWarp; ++q) {
           const double a = ap[q][k0];
@@ -231,6 +243,9 @@ struct SmemDev {
 #pragma unroll
       for (int q = 0; q < kTilesPerWarp; ++q) {
         if (trow[q] < m) {
+          // the implicit slack column nd + r contributes dinv[nd + r] to M[r][r] and nothing else
+          if (trow[q] < ns && trow[q] == tcol[q]) c0[q] += dinv[nd + trow[q]];
+          if (trow[q] < ns && trow[q] == tcol[q] + 1) c1[q] += dinv[nd + trow[q]];
           if (tcol[q] < m) M[trow[q] * ldm + tcol[q]] = c0[q];
           if (tcol[q] + 1 < m) M[trow[q] * ldm + tcol[q] + 1] = c1[q];
         }
@@ -488,14 +503,18 @@ __host__ __device__ inline int batched_mp(int m) { return (m + kSB - 1) / kSB * 
 // pitch of A in shared memory: = 4 (mod 16) doubles, so that the 8 x 4 DMMA fragment loads of the in-CTA SYRK (row g,
 // column t of a tile: 8 (g) + 2 (t) words apart) fall into 32 different banks per half-warp
 __host__ __device__ inline int batched_lda(int n) { return (n + 15) / 16 * 16 + 4; }
-__host__ __device__ inline size_t batched_smem_doubles(int m, int n) {
+__host__ __device__ inline size_t batched_smem_doubles(int m, int n, int ns) {
   const size_t mp = (size_t)batched_mp(m);
-  return (size_t)m * batched_lda(n) + mp * (mp + 1) + 10 * (size_t)n + 5 * (size_t)m + 2 * mp + 2 * kMaxM + 8 * kBWarps +
+  return (size_t)m * batched_lda(n - ns) + mp * (mp + 1) + 10 * (size_t)n + 5 * (size_t)m + 2 * mp + 2 * kMaxM + 8 * kBWarps +
          (mp / kSB) * kSB * kXP + panel_factor_scratch(kXP) + 2;
 }
 
-__global__ void __launch_bounds__(kBT)
-batched_ipm_kernel(int64_t batch, int m, int n, const double* __restrict__ gA, const double* __restrict__ gb,
+// Two CTAs per SM (128 registers, <= 113 KB of shared memory each) whenever the batch has the slack structure: one LP's
+// serial sections -- the factoring warp above all, 22 % of the time with seven warps waiting -- are then covered by
+// the other LP's parallel ones.  `ns` (from batched_structure_kernel, the same for every LP of the batch) is the
+// number of trailing columns that are e_0 .. e_{ns-1} in EVERY problem; they are not stored.
+__global__ void __launch_bounds__(kBT, 2)
+batched_ipm_kernel(int64_t batch, int m, int n, int ns, const double* __restrict__ gA, const double* __restrict__ gb,
                    const double* __restrict__ gc, lpb_options opts, double* __restrict__ x_out,
                    double* __restrict__ fun_out, int64_t* __restrict__ it_out, int32_t* __restrict__ st_out) {
   extern __shared__ double sm[];
@@ -503,7 +522,9 @@ batched_ipm_kernel(int64_t batch, int m, int n, const double* __restrict__ gA, c
     SmemDev d;
     d.m = m;
     d.n = n;
-    d.lda = batched_lda(n);
+    d.ns = ns;
+    d.nd = n - ns;
+    d.lda = batched_lda(d.nd);
     d.mp = batched_mp(m);
     d.nsb = d.mp / kSB;
     d.ldm = d.mp + 1;
@@ -531,12 +552,12 @@ batched_ipm_kernel(int64_t batch, int m, int n, const double* __restrict__ gA, c
     d.cp = d.bq = 0.0;
 
     const double* A = gA + lp * (int64_t)m * n;
-    for (int idx = threadIdx.x; idx < m * n; idx += kBT) {
-      const int i = idx / n, j = idx - i * n;
-      d.A[i * d.lda + j] = A[idx];
+    for (int idx = threadIdx.x; idx < m * d.nd; idx += kBT) {
+      const int i = idx / d.nd, j = idx - i * d.nd;
+      d.A[i * d.lda + j] = A[i * n + j];
     }
-    for (int idx = threadIdx.x; idx < m * (d.lda - n); idx += kBT) {  // zero padding columns: the K tail of the DMMA SYRK
-      const int i = idx / (d.lda - n), j = n + idx - i * (d.lda - n);
+    for (int idx = threadIdx.x; idx < m * (d.lda - d.nd); idx += kBT) {  // zero padding columns: the K tail of the DMMA SYRK
+      const int i = idx / (d.lda - d.nd), j = d.nd + idx - i * (d.lda - d.nd);
       d.A[i * d.lda + j] = 0.0;
     }
     for (int idx = threadIdx.x; idx < d.mp * d.mp; idx += kBT) {  // identity padding of M beyond m (kept by the factorisation)
@@ -573,18 +594,65 @@ batched_ipm_kernel(int64_t batch, int m, int n, const double* __restrict__ gA, c
   }
 }
 
+// Largest ns such that in EVERY problem of the batch the last ns columns are exactly e_0 .. e_{ns-1} (the slack block
+// ProblemBuilder::build appends, linear_program.rs:145-156).  Detected from the data, never assumed: one CTA per
+// problem finds its own run (columns from the right while column n - ns_lp + r is the unit vector e_r for a
+// consistent ns_lp), the batch takes the minimum.  A batch without the structure gets 0 and the kernel stores all of A.
+__global__ void __launch_bounds__(256)
+batched_structure_kernel(int64_t batch, int m, int n, const double* __restrict__ gA, int* __restrict__ ns_out) {
+  __shared__ int urow[kMaxM];  // urow[t]: column n - smax + t is the unit vector e_{urow[t]} (entry exactly 1), else -1
+  __shared__ int best;
+  const int smax = m < n ? m : n;
+  for (int64_t lp = blockIdx.x; lp < batch; lp += gridDim.x) {
+    const double* A = gA + lp * (int64_t)m * n;
+    if (threadIdx.x == 0) best = 0;
+    for (int t = threadIdx.x; t < smax; t += blockDim.x) {  // adjacent threads read adjacent columns of a row: coalesced
+      const int j = n - smax + t;
+      int r = -1;
+      for (int i = 0; i < m; ++i) {
+        const double v = A[(int64_t)i * n + j];
+        if (v != 0.0) r = (v == 1.0 && r == -1) ? i : -2;
+      }
+      urow[t] = r >= 0 ? r : -1;
+    }
+    __syncthreads();
+    for (int s = 1 + threadIdx.x; s <= smax; s += blockDim.x) {  // candidate: the last s columns are e_0 .. e_{s-1}
+      bool good = true;
+      for (int r = 0; r < s; ++r) good = good && urow[smax - s + r] == r;
+      if (good) atomicMax(&best, s);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMin(ns_out, best);
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 int batched_launch(int64_t batch, int m, int n, const double* dA, const double* db, const double* dc,
                    const lpb_options& o, double* dx, double* dfun, int64_t* dit, int32_t* dst, cudaStream_t stream) {
-  const size_t smem = batched_smem_doubles(m, n) * sizeof(double);
-  if (m > kMaxM || smem > 227 * 1024) {
-    set_last_error("solve_batched: needs m <= %d and %zu bytes of shared memory <= 227 KB", kMaxM, smem);
+  if (m > kMaxM) {
+    set_last_error("solve_batched: needs m <= %d", kMaxM);
+    return LPB_ERR_UNSUPPORTED;
+  }
+  // structure scan: dit (int64 per problem, written by the solve afterwards) lends its first word for the result
+  int* ns_dev = reinterpret_cast<int*>(dit);
+  int ns = m < n ? m : n;
+  LPB_CUDA(cudaMemcpyAsync(ns_dev, &ns, sizeof(int), cudaMemcpyHostToDevice, stream));
+  const int64_t sgrid = batch < (int64_t)kNumSMs * 8 ? batch : (int64_t)kNumSMs * 8;
+  batched_structure_kernel<<<(unsigned)sgrid, 256, 0, stream>>>(batch, m, n, dA, ns_dev);
+  LPB_CUDA(cudaGetLastError());
+  LPB_CUDA(cudaMemcpyAsync(&ns, ns_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  LPB_CUDA(cudaStreamSynchronize(stream));
+  if (ns < 0 || ns > m || ns >= n) ns = 0;
+  const size_t smem = batched_smem_doubles(m, n, ns) * sizeof(double);
+  if (smem > 227 * 1024) {
+    set_last_error("solve_batched: %zu bytes of shared memory > 227 KB", smem);
     return LPB_ERR_UNSUPPORTED;
   }
   LPB_CUDA(cudaFuncSetAttribute(batched_ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = batch < (int64_t)kNumSMs * 64 ? batch : (int64_t)kNumSMs * 64;
-  batched_ipm_kernel<<<(unsigned)grid, kBT, smem, stream>>>(batch, m, n, dA, db, dc, o, dx, dfun, dit, dst);
+  batched_ipm_kernel<<<(unsigned)grid, kBT, smem, stream>>>(batch, m, n, ns, dA, db, dc, o, dx, dfun, dit, dst);
   LPB_CUDA(cudaGetLastError());
   return LPB_OK;
 }

@@ -45,6 +45,29 @@ def test_batched_equals_single_problem_path():
         assert abs(res.fun[i] - single.fun()) <= 1e-8 * max(1.0, abs(single.fun()))
 
 
+def test_batched_slack_structure_is_detected_from_the_data_not_assumed():
+    """The batched kernel does not store the trailing identity block of slack-form problems (then two CTAs fit on an
+    SM).  The structure is read off the data per batch: (a) the same LPs with their columns permuted -- slack columns
+    first, so there is no trailing identity -- take the store-everything path and must give the same solutions;
+    (b) a batch in which ONE problem breaks the pattern (a 2 in the identity block) falls back as a whole.  (Batches
+    with other numbers of inequality rows, i.e. other run lengths, are the parametrised cases above.)"""
+    A, b, c, n_slack = make_batch(6, 64, 128, 4000)
+    ref = lp_b200.solve_batched(A, b, c, n_slack=n_slack)
+    assert all(ref.status == _ffi.LPB_OK)
+    perm = np.concatenate([np.arange(128 - n_slack, 128), np.arange(128 - n_slack)])
+    got = lp_b200.solve_batched(A[:, :, perm], b, c[:, perm])
+    assert np.array_equal(got.iteration, ref.iteration) or np.abs(got.iteration - ref.iteration).max() <= 1
+    np.testing.assert_allclose(got.x_slack[:, np.argsort(perm)], ref.x_slack, rtol=0, atol=1e-7)
+    np.testing.assert_allclose(got.fun, ref.fun, rtol=1e-9)
+    A2 = A.copy()
+    A2[3, 5, 128 - n_slack + 5] = 2.0             # problem 3: that slack column is 2 e_5 now, a different (still valid) LP
+    mixed = lp_b200.solve_batched(A2, b, c, n_slack=n_slack)
+    one = o.InteriorPoint().solve(o.Problem(A2[3], b[3], c[3], 0.0, n_slack))
+    assert abs(int(mixed.iteration[3]) - one.iteration) <= 1 and np.abs(mixed.x[3] - one.x).max() < 1e-6
+    keep = [i for i in range(6) if i != 3]
+    np.testing.assert_allclose(mixed.x_slack[keep], ref.x_slack[keep], rtol=0, atol=1e-7)
+
+
 def test_batched_statuses_and_limits():
     # problem 0 infeasible (x1 + x2 + s = -1), problem 1 unbounded, problem 2 fine; all 1 x 3 slack form
     A = np.array([[[1.0, 1.0, 1.0]], [[1.0, -1.0, 1.0]], [[1.0, 1.0, 1.0]]])
