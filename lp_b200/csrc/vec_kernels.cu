@@ -31,6 +31,13 @@ const char* get_last_error() { return g_last_error; }
 
 constexpr int kVecThreads = 256;
 
+// one column per thread: the epilogues that fold the row-chunk partials of A^T v are latency-bound per column
+static inline int vec_blocks_thin(int64_t n) {
+  int64_t b = ceil_div(n, (int64_t)kVecThreads);
+  if (b < 1) b = 1;
+  if (b > kMaxRedBlocks) b = kMaxRedBlocks;
+  return (int)b;
+}
 static inline int vec_blocks(int64_t n) {
   int64_t b = ceil_div(n, (int64_t)kVecThreads * 4);
   if (b < 1) b = 1;
@@ -535,9 +542,18 @@ int k_gemv_t_partials(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int6
 
 __device__ __forceinline__ double sum_chunks(const double* __restrict__ partials, int nchunks, int nrhs, int k,
                                              int64_t n_pad, int64_t j) {
-  double s = 0.0;
-  for (int c = 0; c < nchunks; ++c) s += partials[((size_t)c * nrhs + k) * n_pad + j];
-  return s;
+  // four interleaved partial sums in a fixed order: one chain of nchunks dependent L2 loads + adds per column was what
+  // these epilogues cost at C2 (50 chunks: 62 us for sym_back_kernel on 8 CTAs; launches_C2_r02_final.txt)
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  const double* pk = partials + (size_t)k * n_pad + j;
+  const size_t step = (size_t)nrhs * n_pad;
+  int c = 0;
+  for (; c + 3 < nchunks; c += 4) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s[e] += pk[(size_t)(c + e) * step];
+  }
+  for (; c < nchunks; ++c) s[0] += pk[(size_t)c * step];
+  return (s[0] + s[1]) + (s[2] + s[3]);
 }
 
 // (A^T v_k)[j] for the epilogues: columns below tc.nd come from the row-chunk partials (pitch round_up(nd, 2));
@@ -583,7 +599,7 @@ __global__ void resid_d_kernel(int64_t n, TailCols tc, int nchunks, double tau,
 }
 int k_resid_d(LaunchCtx& lc, int64_t n, int nchunks, double tau, const double* c, const double* z, const double* x,
               double* rD, int val_base, int* nblocks, const TailCols* tail) {
-  const int nb = vec_blocks(n);
+  const int nb = vec_blocks_thin(n);
   const TailCols tc = tail ? *tail : TailCols{n, nullptr, nullptr, nullptr, nullptr};
   resid_d_kernel<<<nb, kVecThreads, 0, lc.stream>>>(n, tc, nchunks, tau, lc.gemv_partials, c, z, x, rD,
                                                     lc.red_partials, val_base);
@@ -617,7 +633,7 @@ __global__ void sym_back_kernel(int64_t n, TailCols tc, int nchunks, int with_pq
 }
 int k_sym_back(LaunchCtx& lc, int64_t n, int nchunks, int with_pq, const double* dinv, const double* r1,
                const double* c, double* u, double* p, int val_base, int* nblocks, const TailCols* tail) {
-  const int nb = vec_blocks(n);
+  const int nb = vec_blocks_thin(n);
   const TailCols tc = tail ? *tail : TailCols{n, nullptr, nullptr, nullptr, nullptr};
   sym_back_kernel<<<nb, kVecThreads, 0, lc.stream>>>(n, tc, nchunks, with_pq, lc.gemv_partials, dinv, r1,
                                                      c, u, p, lc.red_partials, val_base);
