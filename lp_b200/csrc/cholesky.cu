@@ -202,7 +202,7 @@ potf2_inv_kernel(double* __restrict__ Mat, int64_t ldm, int k0, int nb, int* __r
   // hold the running sums of the forward substitution L x = e_i for column i of X = inv(L_dd)
   // (v[r] = sum_{l<r} L[r][l] x_l, replaced by x_r at step r).  Both need exactly column j of L at pivot
   // step j -- broadcast through shared memory -- and then the same FMA  v[k] += mult * L[k][j], k > j.
-  // sqrt and the divisions are one rsqrt plus Newton corrections (results within an ulp of IEEE).
+  // sqrt and the divisions are one rsqrt: the hardware seed plus one third-order step (within an ulp of IEEE).
   // (panel_factor.cuh: rolled, shifting, branch-free pivot loop -- instruction fetch, not arithmetic, is what a
   // once-per-launch kernel pays for)
   auto factor_sub = [&](int c0, double* xd) {
