@@ -80,6 +80,9 @@ struct LaunchCtx {
   int solve_impl = 0;              // 0 = solve_ll_kernel, 1 = one launch per block step, 2 = substitution, 3 = flag-based pipelined
   int sync_each_launch = 0;        // debug: stream-synchronise after every launch of k_potrf
   int syrk_flush_blocks = 32;      // K1: K-blocks (16 columns each) summed in registers between two flushes into C
+  int syrk_tail_split = 1;         // K1: cut the tiles of a short last wave into K-parts (dmma_gemm.cu: TailSplit)
+  double* syrk_ws = nullptr;       // ... their private 128 x 128 slots
+  int64_t syrk_ws_cap = 0;
   int syrk_chain = 0;              // 1 = K1 sums the whole K extent in one register chain (no blocked accumulation)
   int potf2_impl = 0;              // 1 = textbook potf2 (sqrt, divisions, no inverses): needs trsm_impl 1; solves substitute
   int trsm_impl = 0, update_impl = 0;  // bisecting knobs of k_potrf: 1 = plain DFMA kernel for that step

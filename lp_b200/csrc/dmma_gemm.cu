@@ -189,7 +189,18 @@ __device__ __forceinline__ void band_decode(int L, int ntr, int* ti, int* tj) {
 // so a ninth warp would not fit next to eight 200-register DMMA warps).
 struct LoadCursor {
   int L, kb, row_i, row_j, stage;
+  int kb_lo, kb_n;  // K-block range of the work item (a whole tile: 0, nkb)
   uint32_t phase;
+};
+
+// MODE_SYRK, tail of the persistent schedule: when the tile count leaves a short last wave (C2: 528 tiles on 148 SMs =
+// 3.57 waves, the fourth one 57 % full but a whole tile-time long), the last `ntiles - n_full` tiles are cut into
+// `nsplit` K-ranges each.  Every part is an item of its own with a private 128 x 128 slot in `ws`
+// (syrk_tail_fixup_kernel adds the parts in order afterwards: deterministic, no atomics), so the last wave's work
+// spreads over all SMs.  nsplit = 1: every item is a whole tile.
+struct TailSplit {
+  int n_full, nsplit;
+  double* ws;
 };
 
 // MODE_SYRK   : C = A diag(d) A^T (d optional), lower-triangular tile list, K = [k_begin, k_begin + 16 nkb).
@@ -211,7 +222,7 @@ template <int MODE, bool SCALE, int VAR = 0>
 __global__ void __maxnreg__(255)
 syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  double* __restrict__ C, int64_t ldc, int m_total, int tile0, int ntr, int k_begin, int nkb,
-                 int col_origin, int shape, OwnedCols own, int p_row0) {
+                 int col_origin, int shape, OwnedCols own, int p_row0, TailSplit ts) {
   // p_row0 >= 0 (MODE_UPDATE only): the panel P is read from a PACKED buffer (tmA maps it: 128 columns, row
   // (r - p_row0) of the panel at buffer row (r - p_row0), except that the first two 128-row blocks are swapped:
   // the rows of block p_row0 / 128 + 1 come first, see k_potrf_dist2) instead of from columns k_begin.. of C.
@@ -238,8 +249,25 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   __syncthreads();
 
-  const int ntiles = (MODE == MODE_TRSM || shape == SHAPE_COL) ? ntr
+  constexpr bool SPLIT = MODE == MODE_SYRK && FLUSH;  // tail tiles may be cut along K (TailSplit)
+  const int ntiles_whole = (MODE == MODE_TRSM || shape == SHAPE_COL) ? ntr
                      : (shape == SHAPE_COLB ? ntr - 1 : (shape == SHAPE_OWNED ? own.count() : ntr * (ntr + 1) / 2));
+  // work items: whole tiles, then (SPLIT only) the K-parts of the tail tiles
+  const int ntiles = SPLIT ? ts.n_full + (ntiles_whole - ts.n_full) * ts.nsplit : ntiles_whole;
+  auto item = [&](int I, int* L, int* part, int* kb_lo, int* kb_n) {
+    if (!SPLIT || I < ts.n_full) {
+      *L = I;
+      *part = -1;
+      *kb_lo = 0;
+      *kb_n = nkb;
+    } else {
+      const int q = I - ts.n_full;
+      *L = ts.n_full + q / ts.nsplit;
+      *part = q % ts.nsplit;
+      *kb_lo = (int)((int64_t)nkb * *part / ts.nsplit);
+      *kb_n = (int)((int64_t)nkb * (*part + 1) / ts.nsplit) - *kb_lo;
+    }
+  };
   const bool is_producer = threadIdx.x == 0;
   constexpr uint32_t kBytes = 2 * kTileBytes + (SCALE ? kDBytes : 0);
 
@@ -265,10 +293,13 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   pc.stage = 0;
   pc.phase = 0;
   pc.row_i = pc.row_j = 0;
+  pc.kb_lo = 0;
+  pc.kb_n = nkb;
   auto cursor_tile = [&]() {
     if (pc.L < ntiles) {
-      int ti, tj;
-      decode(pc.L, &ti, &tj);
+      int ti, tj, Lt, part;
+      item(pc.L, &Lt, &part, &pc.kb_lo, &pc.kb_n);
+      decode(Lt, &ti, &tj);
       pc.row_i = (tile0 + ti) * BM;
       pc.row_j = MODE == MODE_TRSM ? 0 : (tile0 + tj) * BN;
     }
@@ -279,7 +310,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_wait(bar_empty + pc.stage * 8, pc.phase ^ 1u);
     const uint32_t full = bar_full + pc.stage * 8;
     mbar_expect_tx(full, kBytes);
-    const int k = k_begin + pc.kb * BK;
+    const int k = k_begin + (pc.kb_lo + pc.kb) * BK;
     int ra = pc.row_i, rb = pc.row_j;
     if (MODE == MODE_UPDATE && p_row0 >= 0) {  // packed panel: block (p_row0 / 128 + 1) sits at buffer row 0
       ra -= p_row0;
@@ -289,7 +320,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tma_load_2d(sA + pc.stage * kTileBytes, &tmA, k, ra, full);
     if (MODE == MODE_TRSM)
-      tma_load_2d(sB + pc.stage * kTileBytes, &tmB, pc.kb * BK, 0, full);
+      tma_load_2d(sB + pc.stage * kTileBytes, &tmB, (pc.kb_lo + pc.kb) * BK, 0, full);
     else
       tma_load_2d(sB + pc.stage * kTileBytes, &tmA, k, rb, full);
     if (SCALE) tma_load_2d(sD + pc.stage * kDBytes, &tmB, k, 0, full);
@@ -297,7 +328,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       pc.stage = 0;
       pc.phase ^= 1u;
     }
-    if (++pc.kb == nkb) {
+    if (++pc.kb == pc.kb_n) {
       pc.kb = 0;
       pc.L += gridDim.x;
       cursor_tile();
@@ -344,8 +375,18 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t rt_zero = static_cast<uint32_t>(static_cast<uint64_t>(ldc) >> 62);  // 0 at run time, opaque to the compiler
   int tile_n = 0;  // tiles this CTA has started (parity of the C-prefetch barriers)
   for (int L = blockIdx.x; L < ntiles; L += gridDim.x, ++tile_n) {
-    int ti, tj;
-    decode(L, &ti, &tj);
+    int ti, tj, Lt, part, kb_lo, kbn;
+    item(L, &Lt, &part, &kb_lo, &kbn);
+    decode(Lt, &ti, &tj);
+    // destination of this item: the tile of C, or (a K-part of a tail tile) its private slot in ts.ws, addressed with
+    // the same global row / column indices
+    double* Cd = C;
+    int64_t ldd = ldc;
+    if (SPLIT && part >= 0) {
+      ldd = BN;
+      Cd = ts.ws + (static_cast<int64_t>(Lt - ts.n_full) * ts.nsplit + part) * (BM * BN) -
+           (static_cast<int64_t>(tile0 + ti) * BM * BN + static_cast<int64_t>(tile0 + tj) * BN);
+    }
     const int row0 = (tile0 + ti) * BM + wm * 64 + g;
     const int col0 = (MODE == MODE_TRSM ? col_origin : (tile0 + tj) * BN) + wn * 32 + 2 * t;
     const int col_limit = MODE == MODE_TRSM ? col_origin + BN : m_total;
@@ -391,7 +432,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
     }
 
-    for (int kb = 0; kb < nkb; ++kb) {
+    for (int kb = 0; kb < kbn; ++kb) {
       // keep the ring kLead iterations ahead: the stage being refilled was released kStages - kLead
       // iterations ago, so this wait does not normally stall
       if (is_producer) {
@@ -468,7 +509,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int mi = 0; mi < 8; ++mi)
             if ((grp_bit >> mi) & 1u) {
               const int r = rbase + mi * 8;
-              const double* crow = C + static_cast<int64_t>(r) * ldc;
+              const double* crow = Cd + static_cast<int64_t>(r) * ldd;
 #pragma unroll
               for (int ni = 0; ni < 4; ++ni) {
                 const int cc = col0 + ni * 8;
@@ -476,7 +517,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           cp_async_commit();
-        } else if (sub == fstride - 1 && kb + 1 < nkb) {
+        } else if (sub == fstride - 1 && kb + 1 < kbn) {
           const bool first = kb < fblocks;
           int rbase = row0;
           asm volatile("" : "+r"(rbase));
@@ -485,7 +526,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int mi = 0; mi < 8; ++mi)
             if ((grp_bit >> mi) & 1u) {
               const int r = rbase + mi * 8;
-              double* crow = C + static_cast<int64_t>(r) * ldc;
+              double* crow = Cd + static_cast<int64_t>(r) * ldd;
 #pragma unroll
               for (int ni = 0; ni < 4; ++ni) {
                 const int cc = col0 + ni * 8;
@@ -508,7 +549,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int mi = 0; mi < 8; ++mi) {
       const int r = row0 + mi * 8;
       if (r < m_total) {
-        double* crow = C + static_cast<int64_t>(r) * ldc;
+        double* crow = Cd + static_cast<int64_t>(r) * ldd;
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
           const int c = col0 + ni * 8;
@@ -516,7 +557,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
             // MODE_SYRK: row group mi has been folded into C before iff its first flush point lies inside the tile
             if ((MODE == MODE_UPDATE && (VAR & 1)) ||
-                (MODE == MODE_SYRK && FLUSH && fstride * (mi + 1) - fwarp < nkb)) {
+                (MODE == MODE_SYRK && FLUSH && fstride * (mi + 1) - fwarp < kbn)) {
               const double2 o = *reinterpret_cast<const double2*>(crow + c);
               v.x += o.x;
               v.y += o.y;
@@ -527,6 +568,25 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     if (VAR & 2) __syncthreads();
+  }
+}
+
+// Sum of the K-parts of the tail tiles (TailSplit), in part order, into C: one CTA per tail tile.
+__global__ void __launch_bounds__(256)
+syrk_tail_fixup_kernel(double* __restrict__ C, int64_t ldc, int m_total, int ntr, TailSplit ts) {
+  int ti, tj;
+  band_decode(ts.n_full + blockIdx.x, ntr, &ti, &tj);
+  const double* w = ts.ws + static_cast<int64_t>(blockIdx.x) * ts.nsplit * (BM * BN);
+  for (int e = threadIdx.x; e < BM * BN / 2; e += 256) {
+    const int r = ti * BM + (e >> 6), c = tj * BN + 2 * (e & 63);
+    if (r >= m_total || c >= m_total) continue;  // m_total and ldc are even: a pair is in or out as a whole
+    double2 sum = make_double2(0.0, 0.0);
+    for (int p = 0; p < ts.nsplit; ++p) {
+      const double2 v = *reinterpret_cast<const double2*>(w + static_cast<int64_t>(p) * (BM * BN) + 2 * e);
+      sum.x += v.x;
+      sum.y += v.y;
+    }
+    *reinterpret_cast<double2*>(C + static_cast<int64_t>(r) * ldc + c) = sum;
   }
 }
 
@@ -576,7 +636,7 @@ int make_tmap(CUtensorMap* tm, const double* base, uint64_t rows, uint64_t cols,
 template <int MODE, bool SCALE, int VAR = 0>
 int launch_dmma(LaunchCtx& lc, const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, int64_t ldc, int m_total,
                 int tile0, int ntr, int k_begin, int nkb, int col_origin, int shape = SHAPE_TRI,
-                OwnedCols own = OwnedCols{1, 0, 0}, int p_row0 = -1) {
+                OwnedCols own = OwnedCols{1, 0, 0}, int p_row0 = -1, TailSplit ts = TailSplit{0, 1, nullptr}) {
   static PerDeviceOnce once;  // one per template instantiation
   auto kern = syrk_dmma_kernel<MODE, SCALE, VAR>;
   LPB_TRY(once.run([&](int) -> int {
@@ -586,11 +646,12 @@ int launch_dmma(LaunchCtx& lc, const CUtensorMap& tmA, const CUtensorMap& tmB, d
   const int ntiles = (MODE == MODE_TRSM || shape == SHAPE_COL) ? ntr
                      : (shape == SHAPE_COLB ? ntr - 1 : (shape == SHAPE_OWNED ? own.count() : ntr * (ntr + 1) / 2));
   if (ntiles <= 0) return LPB_OK;
+  if (ts.nsplit <= 1) ts = TailSplit{ntiles, 1, nullptr};  // every item is a whole tile
   int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
   if (MODE == MODE_UPDATE && lc.update_grid_cap > 0 && grid > lc.update_grid_cap) grid = lc.update_grid_cap;
   cudaStream_t st = lc.launch_on_side ? lc.side_stream : lc.stream;
   kern<<<grid, kThreads, Plan<MODE, VAR>::kAlloc, st>>>(tmA, tmB, C, ldc, m_total, tile0, ntr, k_begin, nkb, col_origin, shape, own,
-                                           p_row0);
+                                           p_row0, ts);
   lc.launches++;
   LPB_CUDA(cudaGetLastError());
   return LPB_OK;
@@ -619,8 +680,45 @@ int k_syrk_dmma(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t ld
     return launch_dmma<MODE_SYRK, false, 16>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, 0);
   }
   const int fb = lc.syrk_flush_blocks;  // option "syrk_flush_blocks": K-blocks between two flushes (power of two >= 32)
-  if (d) return launch_dmma<MODE_SYRK, true>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, fb);
-  return launch_dmma<MODE_SYRK, false>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, fb);
+  // Tail split (option "syrk_tail_split", default on): worth it when the last wave is at most 3/4 full.  The number of
+  // parts minimises the length of the tail, ceil(rem * S / SMs) / S tile-times, plus a little for the extra traffic.
+  TailSplit ts{0, 1, nullptr};
+  const int ntiles = ntr * (ntr + 1) / 2;
+  const int rem = ntiles % kNumSMs;
+  if (lc.syrk_tail_split && ntiles > kNumSMs && rem > 0 && 4 * rem <= 3 * kNumSMs && nkb >= 64 && !(m & 1)) {
+    int best_s = 1;
+    double best = 1.0;
+    for (int sp = 2; sp <= 8; ++sp) {
+      const double len = (double)ceil_div((int64_t)rem * sp, (int64_t)kNumSMs) / sp + 0.01 * sp;
+      if (len < best - 1e-9) {
+        best = len;
+        best_s = sp;
+      }
+    }
+    if (best_s > 1) {
+      const int64_t need = (int64_t)rem * best_s * BM * BN;
+      if (lc.syrk_ws_cap < need) {
+        if (lc.syrk_ws) LPB_CUDA(cudaFree(lc.syrk_ws));
+        lc.syrk_ws = nullptr;
+        lc.syrk_ws_cap = 0;
+        void* p = nullptr;
+        LPB_CUDA(cudaMalloc(&p, sizeof(double) * (size_t)need));
+        lc.syrk_ws = static_cast<double*>(p);
+        lc.syrk_ws_cap = need;
+      }
+      ts = TailSplit{ntiles - rem, best_s, lc.syrk_ws};
+    }
+  }
+  if (d)
+    LPB_TRY((launch_dmma<MODE_SYRK, true>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, fb, SHAPE_TRI, OwnedCols{1, 0, 0}, -1, ts)));
+  else
+    LPB_TRY((launch_dmma<MODE_SYRK, false>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, fb, SHAPE_TRI, OwnedCols{1, 0, 0}, -1, ts)));
+  if (ts.nsplit > 1) {
+    syrk_tail_fixup_kernel<<<rem, 256, 0, lc.stream>>>(Cmat, ldc, (int)m, ntr, ts);
+    lc.launches++;
+    LPB_CUDA(cudaGetLastError());
+  }
+  return LPB_OK;
 }
 
 int k_trailing_update_dmma(LaunchCtx& lc, int64_t m, double* Mat, int64_t ldm, int64_t k0, int64_t kb) {

@@ -741,6 +741,7 @@ void ctx_free(lpb_ctx* c) {
   for (auto e : c->ev_free) cudaEventDestroy(e);
   for (void* p : c->allocs) cudaFree(p);
   if (c->lc.chol_ws) cudaFree(c->lc.chol_ws);
+  if (c->lc.syrk_ws) cudaFree(c->lc.syrk_ws);
   if (c->lc.panel_buf) cudaFree(c->lc.panel_buf);
   k_peer_release(c->lc);
   for (int i = 0; i < 2; ++i)
@@ -1412,6 +1413,10 @@ int lpb_set_option(lpb_ctx* c, const char* key, int64_t value) {
   if (k == "trsm_impl" || k == "update_impl") {
     if (value < 0 || value > 6) return LPB_ERR_BAD_ARGUMENT;
     (k == "trsm_impl" ? c->lc.trsm_impl : c->lc.update_impl) = (int)value;
+    return LPB_OK;
+  }
+  if (k == "syrk_tail_split") {  // K1: 0 = every work item is a whole tile (a short last wave then costs a full tile-time)
+    c->lc.syrk_tail_split = value != 0;
     return LPB_OK;
   }
   if (k == "syrk_chain") {  // 1: K1 without blocked accumulation (the round-1 summation order)

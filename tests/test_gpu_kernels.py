@@ -14,8 +14,10 @@ pytestmark = pytest.mark.gpu
 
 # the last three cross K1's blocked-accumulation boundaries (a row group of the slab is folded into C every 2048 columns,
 # first at column 256 (mi + 1)): one flush per group, a ragged tail behind a flush, three flushes per group
+# ... and the last two have more tiles than SMs with a short last wave (153 tiles: 5 left over; 171: 23), so the tail tiles
+# are cut into K-parts with private slots and summed by syrk_tail_fixup_kernel (dmma_gemm.cu: TailSplit)
 SYRK_SHAPES = [(8, 16), (100, 250), (128, 256), (129, 257), (300, 1000), (513, 1031), (1024, 2048), (257, 2320),
-               (129, 4130), (200, 6500)]
+               (129, 4130), (200, 6500), (2176, 1024), (2200, 1100)]
 
 
 @pytest.mark.parametrize("impl", [0, 1])
@@ -70,6 +72,31 @@ def test_syrk_every_flush_period_gives_the_same_matrix_up_to_rounding(m, n, peri
     low = np.tril_indices(m)
     assert np.isfinite(M[low]).all()
     assert (np.abs(M[low] - ref[low]) / scale[low]).max() < 1e-13
+
+
+def test_syrk_tail_split_changes_nothing_but_the_rounding_of_the_tail_tiles():
+    """Option "syrk_tail_split" = 0 (every work item a whole tile) against the default on a shape whose last wave holds 23
+    of 171 tiles: the same matrix up to rounding, every entry finite, and bit-identical from run to run (the parts are
+    summed in a fixed order: no atomics)."""
+    import torch
+    m, n = 2200, 1100
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((m, n))
+    d = np.exp(rng.uniform(-3, 3, n))
+    Ap, lda = pad_cols(A)
+    dA, dd = to_dev(Ap), to_dev(d)
+    out = []
+    for split in (1, 1, 0):
+        dM = torch.full((m, m), float("nan"), dtype=torch.float64, device="cuda")
+        with BareCtx(m, n) as ctx:
+            ctx.set("syrk_tail_split", split)
+            ok(ctx.lib.lpb_k_syrk_adat(ctx.h, m, n, dA.data_ptr(), lda, dd.data_ptr(), dM.data_ptr(), m))
+        out.append(np.tril(dM.cpu().numpy()))
+    assert np.isfinite(out[0]).all()
+    assert np.array_equal(out[0], out[1])
+    scale = np.tril((np.abs(A) * d) @ np.abs(A).T) + 1e-300
+    assert (np.abs(out[0] - out[2]) / scale).max() < 1e-13
+    assert not np.array_equal(out[0], out[2])     # the tail tiles really took the other path
 
 
 def test_syrk_blocked_accumulation_keeps_long_same_sign_sums_to_a_few_ulp():
