@@ -274,6 +274,7 @@ int64_t lpb_launch_count(lpb_ctx* ctx);
  * substitution; "refine": iterative-refinement steps per sym_solve (default 0 = the reference's plain
  * factor-and-solve); "syrk_flush_blocks": K-blocks of 16 columns K1 sums in registers between two folds into M
  * (power of two >= 32, default 32); "syrk_chain": 1 = one register chain over the whole K extent (round-1 kernel);
+ * "syrk_tail_split": 0 = never cut the tiles of a short last wave of K1 into K-parts (default 1);
  * "solve_grid_cap": > 0 caps the pipelined solve's grid (tests: several block rows per CTA);
  * "profile": 1 = record per-phase events; "structure": 0 = contract the SYRK over every column of A
  * (default 1: trailing singleton columns -- the slack block -- are folded into the diagonal of M).  Unknown key -> BAD_ARGUMENT. */
