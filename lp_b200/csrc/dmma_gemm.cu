@@ -249,7 +249,9 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   __syncthreads();
 
-  constexpr bool SPLIT = MODE == MODE_SYRK && FLUSH;  // tail tiles may be cut along K (TailSplit)
+  // VAR bit 5: tail tiles may be cut along K (TailSplit).  A separate instantiation: the item / destination indirection
+  // costs the plain kernel 0.8 % at C3 (193.7 against 192.3 ms), where no launch ever splits.
+  constexpr bool SPLIT = MODE == MODE_SYRK && FLUSH && (VAR & 32) != 0;
   const int ntiles_whole = (MODE == MODE_TRSM || shape == SHAPE_COL) ? ntr
                      : (shape == SHAPE_COLB ? ntr - 1 : (shape == SHAPE_OWNED ? own.count() : ntr * (ntr + 1) / 2));
   // work items: whole tiles, then (SPLIT only) the K-parts of the tail tiles
@@ -709,10 +711,16 @@ int k_syrk_dmma(LaunchCtx& lc, int64_t m, int64_t n, const double* A, int64_t ld
       ts = TailSplit{ntiles - rem, best_s, lc.syrk_ws};
     }
   }
-  if (d)
-    LPB_TRY((launch_dmma<MODE_SYRK, true>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, fb, SHAPE_TRI, OwnedCols{1, 0, 0}, -1, ts)));
-  else
-    LPB_TRY((launch_dmma<MODE_SYRK, false>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, fb, SHAPE_TRI, OwnedCols{1, 0, 0}, -1, ts)));
+  if (ts.nsplit > 1) {
+    if (d)
+      LPB_TRY((launch_dmma<MODE_SYRK, true, 32>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, fb, SHAPE_TRI, OwnedCols{1, 0, 0}, -1, ts)));
+    else
+      LPB_TRY((launch_dmma<MODE_SYRK, false, 32>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, fb, SHAPE_TRI, OwnedCols{1, 0, 0}, -1, ts)));
+  } else if (d) {
+    LPB_TRY((launch_dmma<MODE_SYRK, true>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, fb)));
+  } else {
+    LPB_TRY((launch_dmma<MODE_SYRK, false>(lc, tmA, tmD, Cmat, ldc, (int)m, 0, ntr, 0, nkb, fb)));
+  }
   if (ts.nsplit > 1) {
     syrk_tail_fixup_kernel<<<rem, 256, 0, lc.stream>>>(Cmat, ldc, (int)m, ntr, ts);
     lc.launches++;
